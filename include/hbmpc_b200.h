@@ -1,0 +1,117 @@
+/*
+ * hbmpc_b200.h -- C ABI of the B200-native finite-field hot path of HoneyBadgerMPC secret sharing.
+ *
+ * Drop-in boundary for the reference's share arithmetic (Stoffel-Labs/mpc-protocols, paths relative to
+ * /root/reference/mpc/src).  Each entry point names the reference interface it replaces; INTEGRATION.md shows the
+ * Rust `extern "C"` binding a maintainer would add on the reference side.
+ *
+ * Conventions (they mirror the reference's own C ABI, ffi/c_bindings/mod.rs:17-49 and share/mod.rs:18-37):
+ *   - a field element is the CANONICAL value of ark_bls12_381::Fr as 4 x uint64_t little-endian limbs (== `U256`);
+ *     arrays are dense, row-major; inputs must be < r (else HBMPC_INVALID_INPUT, like `from_bigint(..).unwrap()`);
+ *   - return value = `ShareErrorCode` numbering (0 success ... 8 DecodingError) for whole-call failures;
+ *     per-item outcomes are reported in `path[]`;
+ *   - every data pointer may be a host pointer or a device pointer (detected with cudaPointerGetAttributes).
+ *     Host buffers are copied to/from the device inside the call (which then returns after the results are in
+ *     the caller's buffer); device buffers are processed asynchronously on the context's stream;
+ *   - outputs are CALLER-allocated (the reference leaks Vecs to C and frees them through free_* helpers);
+ *   - no hidden RNG: share generation takes the polynomial coefficients, so results are reproducible;
+ *   - there is no CPU fallback: every call fails with HBMPC_NO_DEVICE if no CUDA device is usable.
+ * A context is thread-compatible: one caller at a time per context; use one context per GPU / per thread.
+ */
+#ifndef HBMPC_B200_H
+#define HBMPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ShareErrorCode (ffi/c_bindings/share/mod.rs:18-37) + library-level codes >= 100 */
+enum {
+    HBMPC_SUCCESS = 0,
+    HBMPC_INSUFFICIENT_SHARES = 1,
+    HBMPC_DEGREE_MISMATCH = 2,
+    HBMPC_ID_MISMATCH = 3,
+    HBMPC_INVALID_INPUT = 4,
+    HBMPC_TYPE_MISMATCH = 5,
+    HBMPC_NO_SUITABLE_DOMAIN = 6,
+    HBMPC_POLYNOMIAL_OPERATION_ERROR = 7,
+    HBMPC_DECODING_ERROR = 8,
+    HBMPC_NO_DEVICE = 100,  /* no usable CUDA device / driver: the library never computes on the CPU */
+    HBMPC_CUDA_ERROR = 101  /* a CUDA runtime call failed; see hbmpc_last_error() */
+};
+
+typedef struct hbmpc_ctx hbmpc_ctx;
+
+/* One context per GPU: owns the stream, the cached constant tables (domain, Vandermonde, Lagrange, syndrome
+ * matrices keyed by (n, d, t, id-set); reference analogue: the OnceLock caches at common/mod.rs:43,70) and scratch. */
+int hbmpc_ctx_create(int device, hbmpc_ctx **out);
+void hbmpc_ctx_destroy(hbmpc_ctx *ctx);
+/* Run on an existing stream (e.g. the caller's torch / application stream) instead of the context's own. */
+int hbmpc_ctx_set_stream(hbmpc_ctx *ctx, void *cuda_stream);
+/* Synchronous mode (default): every call waits for its kernels and returns the device-side status (non-canonical
+ * input -> HBMPC_INVALID_INPUT, undecodable item -> HBMPC_DECODING_ERROR).  Asynchronous mode: calls whose buffers are
+ * all device pointers only enqueue work on the stream and return 0; the accumulated status is returned (and cleared)
+ * by hbmpc_ctx_synchronize. */
+int hbmpc_ctx_set_async(hbmpc_ctx *ctx, int async);
+int hbmpc_ctx_synchronize(hbmpc_ctx *ctx);
+/* Number of this library's kernels launched on the context so far. */
+uint64_t hbmpc_ctx_launch_count(const hbmpc_ctx *ctx);
+const char *hbmpc_last_error(const hbmpc_ctx *ctx);
+
+/* K1.  Replaces the body of RobustShare::compute_shares (honeybadger/robust_interpolate/robust_interpolate.rs:52-82)
+ * and NonRobustShare::compute_shares (common/share/shamir.rs:158-196) for a batch of B secrets:
+ *   coeffs[B][d+1] (coeffs[b][0] = secret b, the rest = the random polynomial)  ->  shares[B][n],
+ *   shares[b][j] = P_b(w_N^j), N = next_pow2(n)  (share id j, degree d).
+ * Errors: n <= d -> INVALID_INPUT (:59-64); n > 256 -> NO_SUITABLE_DOMAIN (:65-66; the reference caps n at 255,
+ * honeybadger/mod.rs:441-444). */
+int hbmpc_compute_shares_batch(hbmpc_ctx *ctx, size_t n, size_t d, size_t B, const uint64_t *coeffs, uint64_t *shares);
+
+/* K2.  Replaces make_vandermonde + apply_vandermonde (common/share/mod.rs:31-76) looped over B chunks
+ * (batch_recon.rs:157-165, ran_dou_sha/mod.rs:392-403, share_gen.rs:415-419):
+ *   out[b][j] = sum_k w_N^(j*k) * in[b][k],  j < n, k < cols.   recipient_major != 0 writes out[j][b]
+ * (the per-recipient transposition of batch_recon.rs:158-165). */
+int hbmpc_apply_vandermonde_batch(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out,
+                                  int recipient_major);
+
+/* K2'.  Same with a caller-supplied rows x cols matrix (canonical limbs, host pointer). */
+int hbmpc_apply_matrix_batch(hbmpc_ctx *ctx, size_t rows, size_t cols, const uint64_t *matrix, size_t B,
+                             const uint64_t *in, uint64_t *out, int recipient_major);
+
+/* K3 (+K4).  Replaces batch_recover_secret (robust_interpolate.rs:284-443):
+ *   evals[S][B] sender-major with sender_ids[S] (arrival order), B chunks  ->  coeffs[B][d+1] (always d+1 wide,
+ *   zero padded), path[B]: 0 = optimistic path, r > 0 = accepted in OEC round r, < 0 = -(ShareErrorCode) for that chunk,
+ *   flags[B][ceil(S/64)] (optional, may be NULL): bit i set <=> supplied share i (arrival order) disagrees with the
+ *   decoded polynomial.  Chunks failing the optimistic check are decoded by the robust path (K4), like :429-439.
+ * Return: whole-call validation errors (:290-341); else, like the reference's `?` at :437, the code of the first
+ * chunk (lowest index) whose robust decode failed, 0 if none.  All chunks are decoded either way. */
+int hbmpc_batch_recover(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, const size_t *sender_ids, size_t B,
+                        const uint64_t *evals, uint64_t *coeffs, int32_t *path, uint64_t *flags);
+
+/* Same decode, but only the opened values P_b(0) are produced: secrets[B] (what round 1 of batch reconstruction
+ * consumes, batch_recon.rs:384-391). */
+int hbmpc_batch_recover_secrets(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, const size_t *sender_ids,
+                                size_t B, const uint64_t *evals, uint64_t *secrets, int32_t *path);
+
+/* K4 direct.  Replaces RobustShare::recover_secret (robust_interpolate.rs:94-157: optimistic -> OEC -> Gao) for a
+ * batch of B codewords with a common id set: shares[B][S] codeword-major, ids[S]  ->  coeffs[B][d+1], secrets[B]
+ * (may be NULL), path[B], flags (may be NULL).  Same return convention as hbmpc_batch_recover. */
+int hbmpc_robust_interpolate_batch(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, const size_t *ids, size_t B,
+                                   const uint64_t *shares, uint64_t *coeffs, uint64_t *secrets, int32_t *path,
+                                   uint64_t *flags);
+
+/* K5.  Element-wise share algebra (common/mod.rs:167-300; triple_generation.rs:332-340,196-208;
+ * multiplication.rs:79-97,417-426): out[i] = a[i] (op) b[i], op: 0 add, 1 sub, 2 mul (share_mul / Mul<F>). */
+int hbmpc_elementwise(hbmpc_ctx *ctx, int op, size_t count, const uint64_t *a, const uint64_t *b, uint64_t *out);
+
+/* Integer-pipe roofline probe: runs an independent-chain multiply-add microkernel on every SM and returns the
+ * sustained rate in 1e9 thread-level instructions per second.  variant: 0 = mad.lo.u32 (IMAD), 1 = mad.wide.u32
+ * (IMAD.WIDE.U32), 2 = the carry-chained IMAD.WIDE.U32.X pattern of the product kernels. */
+int hbmpc_measure_imad_peak(hbmpc_ctx *ctx, int variant, double *giga_inst_per_s, double *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HBMPC_B200_H */

@@ -1,0 +1,261 @@
+"""hbmpc_b200 -- B200-native finite-field hot path of HoneyBadgerMPC secret sharing (ark_bls12_381::Fr).
+
+This package is a thin ctypes binding over the C-ABI shared library ``libhbmpc_b200.so`` (``include/hbmpc_b200.h``).
+All arithmetic runs in hand-written CUDA kernels for sm_100a; there is NO CPU fallback: importing the package
+without the built library, or creating a ``Context`` without a CUDA device, raises.
+
+Field elements are the canonical value as 4 x uint64 little-endian limbs (the reference's ``U256``,
+/root/reference/mpc/src/ffi/c_bindings/mod.rs:17-49): numpy ``uint64[..., 4]`` arrays on the host, or torch CUDA
+tensors of dtype int64 (same bits) with a trailing dimension of 4 on the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhbmpc_b200.so")
+
+# ShareErrorCode (ffi/c_bindings/share/mod.rs:18-37) + library codes
+SUCCESS, INSUFFICIENT_SHARES, DEGREE_MISMATCH, ID_MISMATCH, INVALID_INPUT = 0, 1, 2, 3, 4
+TYPE_MISMATCH, NO_SUITABLE_DOMAIN, POLYNOMIAL_OPERATION_ERROR, DECODING_ERROR = 5, 6, 7, 8
+NO_DEVICE, CUDA_ERROR = 100, 101
+ERROR_NAMES = {0: "ShareSuccess", 1: "InsufficientShares", 2: "DegreeMismatch", 3: "IdMismatch", 4: "InvalidInput",
+               5: "TypeMismatch", 6: "NoSuitableDomain", 7: "PolynomialOperationError", 8: "DecodingError",
+               100: "NoDevice", 101: "CudaError"}
+
+R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+EXPORTS = [
+    "hbmpc_ctx_create", "hbmpc_ctx_destroy", "hbmpc_ctx_set_stream", "hbmpc_ctx_set_async", "hbmpc_ctx_synchronize",
+    "hbmpc_ctx_launch_count", "hbmpc_last_error", "hbmpc_compute_shares_batch", "hbmpc_apply_vandermonde_batch",
+    "hbmpc_apply_matrix_batch", "hbmpc_batch_recover", "hbmpc_batch_recover_secrets", "hbmpc_robust_interpolate_batch",
+    "hbmpc_elementwise", "hbmpc_measure_imad_peak",
+]
+
+
+class HbmpcError(RuntimeError):
+    def __init__(self, code: int, detail: str = ""):
+        self.code = code
+        super().__init__(f"{ERROR_NAMES.get(code, code)} ({code}) {detail}".strip())
+
+
+_lib = None
+
+
+def load_library():
+    """Load libhbmpc_b200.so.  Raises if it has not been built (``python mpc-protocols_b200/build.py``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python mpc-protocols_b200/build.py` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
+    lib.hbmpc_ctx_create.argtypes = [ci, C.POINTER(vp)]
+    lib.hbmpc_ctx_destroy.argtypes = [vp]
+    lib.hbmpc_ctx_destroy.restype = None
+    lib.hbmpc_ctx_set_stream.argtypes = [vp, vp]
+    lib.hbmpc_ctx_set_async.argtypes = [vp, ci]
+    lib.hbmpc_ctx_synchronize.argtypes = [vp]
+    lib.hbmpc_ctx_launch_count.argtypes = [vp]
+    lib.hbmpc_ctx_launch_count.restype = C.c_uint64
+    lib.hbmpc_last_error.argtypes = [vp]
+    lib.hbmpc_last_error.restype = C.c_char_p
+    lib.hbmpc_compute_shares_batch.argtypes = [vp, sz, sz, sz, vp, vp]
+    lib.hbmpc_apply_vandermonde_batch.argtypes = [vp, sz, sz, sz, vp, vp, ci]
+    lib.hbmpc_apply_matrix_batch.argtypes = [vp, sz, sz, vp, sz, vp, vp, ci]
+    lib.hbmpc_batch_recover.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp, vp]
+    lib.hbmpc_batch_recover_secrets.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp]
+    lib.hbmpc_robust_interpolate_batch.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp, vp, vp]
+    lib.hbmpc_elementwise.argtypes = [vp, ci, sz, vp, vp, vp]
+    lib.hbmpc_measure_imad_peak.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _lib = lib
+    return lib
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class _Buf:
+    """Uniform view of a numpy host array or a torch CUDA tensor as (pointer, shape)."""
+
+    def __init__(self, x):
+        self.obj = x
+        if _is_torch(x):
+            if not x.is_contiguous():
+                raise ValueError("torch tensors must be contiguous")
+            self.ptr = x.data_ptr()
+            self.shape = tuple(x.shape)
+            self.torch = True
+        else:
+            x = np.ascontiguousarray(x, dtype=np.uint64)
+            self.obj = x
+            self.ptr = x.ctypes.data
+            self.shape = x.shape
+            self.torch = False
+
+    def like(self, shape, dtype=None):
+        if self.torch:
+            import torch
+
+            dt = {None: torch.int64, "i32": torch.int32, "u64": torch.int64}[dtype]
+            return torch.empty(shape, dtype=dt, device=self.obj.device)
+        dt = {None: np.uint64, "i32": np.int32, "u64": np.uint64}[dtype]
+        return np.zeros(shape, dtype=dt)
+
+
+def _ptr(x):
+    return x.data_ptr() if _is_torch(x) else x.ctypes.data
+
+
+class Context:
+    """One context per GPU (``hbmpc_ctx``): stream, cached constant tables, scratch."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.hbmpc_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise HbmpcError(rc, "hbmpc_ctx_create: no usable CUDA device (this library never computes on the CPU)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hbmpc_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing
+    def set_stream(self, cuda_stream: int):
+        self.lib.hbmpc_ctx_set_stream(self.h, C.c_void_p(cuda_stream))
+
+    def set_async(self, flag: bool):
+        self.lib.hbmpc_ctx_set_async(self.h, int(flag))
+
+    def synchronize(self) -> int:
+        return self.lib.hbmpc_ctx_synchronize(self.h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.hbmpc_ctx_launch_count(self.h))
+
+    def last_error(self) -> str:
+        return (self.lib.hbmpc_last_error(self.h) or b"").decode()
+
+    def _check(self, rc: int, ok=(0,)):
+        if rc not in ok:
+            raise HbmpcError(rc, self.last_error() if rc == CUDA_ERROR else "")
+        return rc
+
+    # -- K1
+    def compute_shares_batch(self, coeffs, n: int, out=None):
+        """coeffs[B][d+1][4] -> shares[B][n][4]   (RobustShare::compute_shares, robust_interpolate.rs:52-82)"""
+        c = _Buf(coeffs)
+        B, m = c.shape[0], c.shape[1]
+        out = c.like((B, n, 4)) if out is None else out
+        self._check(self.lib.hbmpc_compute_shares_batch(self.h, n, m - 1, B, c.ptr, _ptr(out)))
+        return out
+
+    # -- K2
+    def apply_vandermonde_batch(self, inp, n: int, recipient_major: bool = False, out=None):
+        """in[B][cols][4] -> out[B][n][4] (or [n][B][4])   (apply_vandermonde, common/share/mod.rs:50-76)"""
+        x = _Buf(inp)
+        B, cols = x.shape[0], x.shape[1]
+        out = x.like((n, B, 4) if recipient_major else (B, n, 4)) if out is None else out
+        self._check(self.lib.hbmpc_apply_vandermonde_batch(self.h, n, cols, B, x.ptr, _ptr(out), int(recipient_major)))
+        return out
+
+    def apply_matrix_batch(self, matrix, inp, recipient_major: bool = False, out=None):
+        M = np.ascontiguousarray(matrix, dtype=np.uint64)
+        rows, cols = M.shape[0], M.shape[1]
+        x = _Buf(inp)
+        B = x.shape[0]
+        out = x.like((rows, B, 4) if recipient_major else (B, rows, 4)) if out is None else out
+        self._check(self.lib.hbmpc_apply_matrix_batch(self.h, rows, cols, M.ctypes.data, B, x.ptr, _ptr(out), int(recipient_major)))
+        return out
+
+    # -- K3 / K4
+    def batch_recover(self, sender_ids, evals, n: int, d: int, t: int, want_flags: bool = False, out=None):
+        """evals[S][B][4] sender-major -> (rc, coeffs[B][d+1][4], path[B], flags[B][ceil(S/64)] or None)
+        (batch_recover_secret, robust_interpolate.rs:284-443).  rc is 0 or DecodingError (some chunk undecodable)."""
+        e = _Buf(evals)
+        S, B = e.shape[0], e.shape[1]
+        ids = np.ascontiguousarray(sender_ids, dtype=np.uint64)
+        if out is None:
+            coeffs, path = e.like((B, d + 1, 4)), e.like((B,), "i32")
+            flags = e.like((B, (S + 63) // 64), "u64") if want_flags else None
+        else:
+            coeffs, path, flags = out
+        rc = self.lib.hbmpc_batch_recover(self.h, n, d, t, S, ids.ctypes.data, B, e.ptr, _ptr(coeffs), _ptr(path),
+                                          _ptr(flags) if flags is not None else None)
+        self._check(rc, ok=(0, DECODING_ERROR))
+        return rc, coeffs, path, flags
+
+    def batch_recover_secrets(self, sender_ids, evals, n: int, d: int, t: int, out=None):
+        e = _Buf(evals)
+        S, B = e.shape[0], e.shape[1]
+        ids = np.ascontiguousarray(sender_ids, dtype=np.uint64)
+        if out is None:
+            secrets, path = e.like((B, 4)), e.like((B,), "i32")
+        else:
+            secrets, path = out
+        rc = self.lib.hbmpc_batch_recover_secrets(self.h, n, d, t, S, ids.ctypes.data, B, e.ptr, _ptr(secrets), _ptr(path))
+        self._check(rc, ok=(0, DECODING_ERROR))
+        return rc, secrets, path
+
+    def robust_interpolate_batch(self, ids, shares, n: int, d: int, t: int, want_flags: bool = False, out=None):
+        """shares[B][S][4] codeword-major -> (rc, coeffs[B][d+1][4], secrets[B][4], path[B], flags)
+        (RobustShare::recover_secret, robust_interpolate.rs:94-157, batched)."""
+        s = _Buf(shares)
+        B, S = s.shape[0], s.shape[1]
+        idv = np.ascontiguousarray(ids, dtype=np.uint64)
+        if out is None:
+            coeffs, secrets, path = s.like((B, d + 1, 4)), s.like((B, 4)), s.like((B,), "i32")
+            flags = s.like((B, (S + 63) // 64), "u64") if want_flags else None
+        else:
+            coeffs, secrets, path, flags = out
+        rc = self.lib.hbmpc_robust_interpolate_batch(self.h, n, d, t, S, idv.ctypes.data, B, s.ptr, _ptr(coeffs), _ptr(secrets),
+                                                     _ptr(path), _ptr(flags) if flags is not None else None)
+        self._check(rc, ok=(0, DECODING_ERROR))
+        return rc, coeffs, secrets, path, flags
+
+    # -- K5
+    def elementwise(self, op: int, a, b, out=None):
+        x, y = _Buf(a), _Buf(b)
+        count = int(np.prod(x.shape[:-1]))
+        out = x.like(x.shape) if out is None else out
+        self._check(self.lib.hbmpc_elementwise(self.h, op, count, x.ptr, y.ptr, _ptr(out)))
+        return out
+
+    def measure_imad_peak(self, variant: int = 0):
+        g, ms = C.c_double(), C.c_double()
+        self._check(self.lib.hbmpc_measure_imad_peak(self.h, variant, C.byref(g), C.byref(ms)))
+        return g.value, ms.value
+
+
+def to_limbs(values) -> np.ndarray:
+    arr = np.asarray(values, dtype=object)
+    out = np.zeros(arr.shape + (4,), dtype=np.uint64)
+    flat = out.reshape(-1, 4)
+    for i, v in enumerate(arr.reshape(-1)):
+        v = int(v)
+        for k in range(4):
+            flat[i, k] = (v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
+    return out
+
+
+def from_limbs(arr) -> list:
+    arr = np.asarray(arr, dtype=np.uint64)
+    flat = arr.reshape(-1, 4)
+    vals = [int(r[0]) | (int(r[1]) << 64) | (int(r[2]) << 128) | (int(r[3]) << 192) for r in flat]
+    return np.asarray(vals, dtype=object).reshape(arr.shape[:-1]).tolist()

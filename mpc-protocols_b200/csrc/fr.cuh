@@ -1,0 +1,307 @@
+// fr.cuh -- BLS12-381 scalar field (ark_bls12_381::Fr) arithmetic for sm_100a integer pipes.
+//
+// Representation: 8 x 32-bit little-endian limbs.  Data crossing the C ABI is the CANONICAL value
+// (reference: U256, /root/reference/mpc/src/ffi/c_bindings/mod.rs:17-49).  Constant operands
+// (evaluation points, Vandermonde / Lagrange matrices) are stored in Montgomery form c*R mod r,
+// R = 2^256, so that  REDC(sum_k data_k * constR_k) = sum_k data_k * const_k mod r  is canonical again:
+// the hot kernels run directly on the boundary format with no conversion pass.
+//
+// Multiply-accumulate uses the even/odd column split: each 32x32->64 product is one IMAD.WIDE.U32(.X)
+// whose carry travels in a predicate along a chain of four 64-bit lanes; the carry leaving a chain is
+// counted in a small per-position counter (IADD3.X on the ALU pipe) instead of rippling.  A sum of up
+// to 256 products is accumulated lazily (no reduction per term) and Montgomery-reduced once.
+#pragma once
+#include <cstdint>
+
+// HB_HOST_EMULATION (tests only): lets g++ compile this header and run the limb logic on the CPU so the index
+// bookkeeping of the even/odd accumulator can be unit-tested without a GPU.  The shipped library never defines it.
+#if defined(__CUDACC__)
+#define HB_DEV __device__ __forceinline__
+#else
+#define HB_DEV static inline
+#ifndef HB_HOST_EMULATION
+#error "fr.cuh is device code; define HB_HOST_EMULATION only in the host unit test"
+#endif
+struct uint4 { uint32_t x, y, z, w; };
+#endif
+
+namespace hb {
+
+// r = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+#define HB_R0 0x00000001u
+#define HB_R1 0xffffffffu
+#define HB_R2 0xfffe5bfeu
+#define HB_R3 0x53bda402u
+#define HB_R4 0x09a1d805u
+#define HB_R5 0x3339d808u
+#define HB_R6 0x299d7d48u
+#define HB_R7 0x73eda753u
+// -r^{-1} mod 2^32 == 0xffffffff  =>  Montgomery quotient digit m = -T[i] mod 2^32 (no multiply)
+
+struct fr_t {
+    uint32_t v[8];
+};
+
+// ----------------------------------------------------------------------------------------------
+// carry-chain primitives
+// ----------------------------------------------------------------------------------------------
+// (x0..x7) += (a0 + a1*2^64 + a2*2^128 + a3*2^192) * b   (four 64-bit lanes), k += carry-out
+HB_DEV void chain4(uint32_t &x0, uint32_t &x1, uint32_t &x2, uint32_t &x3, uint32_t &x4, uint32_t &x5,
+                                       uint32_t &x6, uint32_t &x7, uint32_t &k, uint32_t a0, uint32_t a1, uint32_t a2,
+                                       uint32_t a3, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7), "+r"(k)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+#else
+    uint32_t *x[8] = {&x0, &x1, &x2, &x3, &x4, &x5, &x6, &x7};
+    const uint32_t a[4] = {a0, a1, a2, a3};
+    unsigned cy = 0;
+    for (int l = 0; l < 4; ++l) {
+        unsigned __int128 s = (unsigned __int128)a[l] * b + (((uint64_t)*x[2 * l + 1] << 32) | *x[2 * l]) + cy;
+        *x[2 * l] = (uint32_t)s;
+        *x[2 * l + 1] = (uint32_t)(s >> 32);
+        cy = (unsigned)(s >> 64);
+    }
+    k += cy;
+#endif
+}
+
+// Lazy accumulator for sum_k a_k * b_k (each factor < 2^256).  E holds even-aligned 64-bit lanes
+// (positions 2j,2j+1), O odd-aligned lanes (positions 2j+1,2j+2), K[p] counts carries into position p.
+struct acc_t {
+    uint32_t E[16];
+    uint32_t O[16];  // positions 1..14 used
+    uint32_t K[17];  // positions 8..16 used
+};
+
+HB_DEV void acc_zero(acc_t &A) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { A.E[i] = 0; A.O[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 17; ++i) A.K[i] = 0;
+}
+
+// A += a * b  (64 IMAD.WIDE + 16 carry-counter adds)
+HB_DEV void acc_mac(acc_t &A, const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        chain4(A.E[i], A.E[i + 1], A.E[i + 2], A.E[i + 3], A.E[i + 4], A.E[i + 5], A.E[i + 6], A.E[i + 7], A.K[i + 8],
+               a[0], a[2], a[4], a[6], b[i]);
+        chain4(A.O[i + 1], A.O[i + 2], A.O[i + 3], A.O[i + 4], A.O[i + 5], A.O[i + 6], A.O[i + 7], A.O[i + 8], A.K[i + 9],
+               a[1], a[3], a[5], a[7], b[i]);
+        chain4(A.O[i + 1], A.O[i + 2], A.O[i + 3], A.O[i + 4], A.O[i + 5], A.O[i + 6], A.O[i + 7], A.O[i + 8], A.K[i + 9],
+               a[0], a[2], a[4], a[6], b[i + 1]);
+        chain4(A.E[i + 2], A.E[i + 3], A.E[i + 4], A.E[i + 5], A.E[i + 6], A.E[i + 7], A.E[i + 8], A.E[i + 9], A.K[i + 10],
+               a[1], a[3], a[5], a[7], b[i + 1]);
+    }
+}
+
+// one Montgomery row: T[i..i+8] += m * r, carries leaving the two chains counted in k8 / k9
+HB_DEV void redc_row(uint32_t &t0, uint32_t &t1, uint32_t &t2, uint32_t &t3, uint32_t &t4, uint32_t &t5,
+                                         uint32_t &t6, uint32_t &t7, uint32_t &t8, uint32_t &k8, uint32_t &k9) {
+    uint32_t m = 0u - t0;
+    chain4(t0, t1, t2, t3, t4, t5, t6, t7, k8, HB_R0, HB_R2, HB_R4, HB_R6, m);
+    chain4(t1, t2, t3, t4, t5, t6, t7, t8, k9, HB_R1, HB_R3, HB_R5, HB_R7, m);
+}
+
+// ----------------------------------------------------------------------------------------------
+// plain 256-bit helpers
+// ----------------------------------------------------------------------------------------------
+// d = a - b, returns borrow (1 if a < b)
+HB_DEV uint32_t sub8(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+#if defined(__CUDA_ARCH__)
+    uint32_t br;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(d[0]), "=&r"(d[1]), "=&r"(d[2]), "=&r"(d[3]), "=&r"(d[4]), "=&r"(d[5]), "=&r"(d[6]), "=&r"(d[7]), "=&r"(br)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]),
+          "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return br & 1u;
+#else
+    uint32_t br = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint64_t t = (uint64_t)a[i] - b[i] - br;
+        d[i] = (uint32_t)t;
+        br = (uint32_t)(t >> 63);
+    }
+    return br;
+#endif
+}
+// d = a + b + cin (cin in {0,1}), returns carry
+HB_DEV uint32_t add8c(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8], uint32_t cin) {
+#if defined(__CUDA_ARCH__)
+    uint32_t cy;
+    asm("add.cc.u32 %8, %25, 0xffffffff;\n\t"
+        "addc.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=&r"(d[0]), "=&r"(d[1]), "=&r"(d[2]), "=&r"(d[3]), "=&r"(d[4]), "=&r"(d[5]), "=&r"(d[6]), "=&r"(d[7]), "=&r"(cy)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]),
+          "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(cin));
+    return cy;
+#else
+    uint32_t cy = cin;
+    for (int i = 0; i < 8; ++i) {
+        uint64_t t = (uint64_t)a[i] + b[i] + cy;
+        d[i] = (uint32_t)t;
+        cy = (uint32_t)(t >> 32);
+    }
+    return cy;
+#endif
+}
+HB_DEV uint32_t add8(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { return add8c(d, a, b, 0); }
+
+HB_DEV void mod_limbs(uint32_t (&r)[8]) {
+    r[0] = HB_R0; r[1] = HB_R1; r[2] = HB_R2; r[3] = HB_R3; r[4] = HB_R4; r[5] = HB_R5; r[6] = HB_R6; r[7] = HB_R7;
+}
+
+// x >= r ?
+HB_DEV bool geq_mod(const uint32_t (&x)[8]) {
+    uint32_t r[8], d[8];
+    mod_limbs(r);
+    return sub8(d, x, r) == 0;
+}
+// x in [0, 2r) -> x mod r
+HB_DEV void cond_sub_mod(uint32_t (&x)[8]) {
+    uint32_t r[8], d[8];
+    mod_limbs(r);
+    uint32_t br = sub8(d, x, r);
+    if (!br) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = d[i];
+    }
+}
+HB_DEV void fr_add(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    add8(d, a, b);  // a,b < r < 2^255: no carry out
+    cond_sub_mod(d);
+}
+HB_DEV void fr_sub(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    uint32_t br = sub8(d, a, b);
+    if (br) {
+        uint32_t r[8], e[8];
+        mod_limbs(r);
+        add8(e, d, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = e[i];
+    }
+}
+HB_DEV bool fr_eq(const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x |= a[i] ^ b[i];
+    return x == 0;
+}
+HB_DEV bool fr_is_zero(const uint32_t (&a)[8]) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x |= a[i];
+    return x == 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// acc_reduce: out = (sum of accumulated products) * R^{-1} mod r, fully reduced (< r).
+// Valid for up to 256 accumulated products of factors < r (T < 2^518).
+// ----------------------------------------------------------------------------------------------
+HB_DEV void acc_reduce(const acc_t &A, uint32_t (&out)[8]) {
+    uint32_t T[17];
+    // merge E + O (O[p] sits at position p), then the carry counters K[8..16]
+    T[0] = A.E[0];
+    uint32_t c;
+    {
+        uint32_t x[8], y[8], d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { x[i] = A.E[1 + i]; y[i] = A.O[1 + i]; }
+        c = add8c(d, x, y, 0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) T[1 + i] = d[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { x[i] = (9 + i <= 15) ? A.E[9 + i] : 0u; y[i] = (9 + i <= 14) ? A.O[9 + i] : 0u; }
+        add8c(d, x, y, c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) T[9 + i] = d[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { x[i] = T[8 + i]; y[i] = A.K[8 + i]; }
+        c = add8c(d, x, y, 0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) T[8 + i] = d[i];
+        T[16] += A.K[16] + c;
+    }
+    // Montgomery reduction, 8 rows; carries into positions >= 8 are deferred (they never feed a quotient digit)
+    uint32_t K2[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) K2[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        redc_row(T[i], T[i + 1], T[i + 2], T[i + 3], T[i + 4], T[i + 5], T[i + 6], T[i + 7], T[i + 8], K2[i + 8], K2[i + 9]);
+    uint32_t U[8], U8;
+    {
+        uint32_t x[8], y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { x[i] = T[8 + i]; y[i] = K2[8 + i]; }
+        c = add8c(U, x, y, 0);
+        U8 = T[16] + K2[16] + c;
+    }
+    // U < (0.4529*terms + 1) * r < 2^262.  Quotient estimate from the 32 bits above 2^230:
+    // D = floor(r / 2^230) + 1  =>  q_est in {q-1, q}; after U -= q_est*r one conditional subtraction remains.
+    uint32_t u_top = (U[7] >> 6) | (U8 << 26);
+    uint32_t q = u_top / 30389918u;
+    uint64_t cc = 0;
+    uint32_t P[8];
+    const uint32_t rl[8] = {HB_R0, HB_R1, HB_R2, HB_R3, HB_R4, HB_R5, HB_R6, HB_R7};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        cc += (uint64_t)q * rl[i];
+        P[i] = (uint32_t)cc;
+        cc >>= 32;
+    }
+    // U - q*r < 2r < 2^256: arithmetic mod 2^256 is exact
+    sub8(out, U, P);
+    cond_sub_mod(out);
+}
+
+// Montgomery product: a*b*R^{-1} mod r (fully reduced)
+HB_DEV void mont_mul(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    acc_t A;
+    acc_zero(A);
+    acc_mac(A, a, b);
+    acc_reduce(A, d);
+}
+
+// R^2 mod r (to Montgomery form: mont_mul(x, R2)); 1 (from Montgomery form: mont_mul(x, 1))
+HB_DEV void r2_limbs(uint32_t (&r)[8]) {
+    r[0] = 0xf3f29c6du; r[1] = 0xc999e990u; r[2] = 0x87925c23u; r[3] = 0x2b6cedcbu;
+    r[4] = 0x7254398fu; r[5] = 0x05d31496u; r[6] = 0x9f59ff11u; r[7] = 0x0748d9d9u;
+}
+// R mod r == Montgomery form of 1
+HB_DEV void one_mont_limbs(uint32_t (&r)[8]) {
+    r[0] = 0xfffffffeu; r[1] = 0x00000001u; r[2] = 0x00034802u; r[3] = 0x5884b7fau;
+    r[4] = 0xecbc4ff5u; r[5] = 0x998c4fefu; r[6] = 0xacc5056fu; r[7] = 0x1824b159u;
+}
+
+HB_DEV void load_fr(uint32_t (&a)[8], const uint4 lo, const uint4 hi) {
+    a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+}
+
+}  // namespace hb

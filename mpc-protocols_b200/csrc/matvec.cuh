@@ -1,0 +1,219 @@
+// matvec.cuh -- the one hot kernel: a small constant Fr matrix applied to a huge batch of Fr vectors.
+//
+//   out[b][r] = sum_c  M[r][c] * in[b][col_map[c]]   (mod r),   b < B, r < R, c < C
+//
+// This single shape covers every dense site of the reference's hot path:
+//   K1  RobustShare/NonRobustShare::compute_shares      M = V[n x (d+1)], V[j][k] = w^(jk)
+//       (robust_interpolate.rs:52-82, shamir.rs:158-196: poly evaluated at the first n domain points)
+//   K2  apply_vandermonde                               M = V[n x cols]          (common/share/mod.rs:50-76)
+//   K3  batch_recover_secret                            M = [check rows L_i(x_s); coefficient rows L_i[k]]
+//       (robust_interpolate.rs:392-428: verify_matrix + basis_coeffs, identity rows dropped)
+//
+// Rows [0, n_chk) are "check rows": the result is compared with the supplied share in[b][chk_map[r]] instead of being
+// written; a mismatch in rows [0, n_gate) marks the item as failing the optimistic path (-> robust decode),
+// any mismatch sets the item's flag bit chk_map[r].
+//
+// Mapping: M lives in shared memory in Montgomery form (warp-uniform broadcast reads), a tile of TBT*32 batch items is
+// staged in shared memory as [c][half][lane] uint4 (conflict-free 128-bit reads); work items (row, 32-lane sub-tile)
+// are dealt round-robin to the CTA's warps; one thread accumulates one output lazily (fr.cuh) and reduces once.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "fr.cuh"
+
+namespace hb {
+
+struct MatvecArgs {
+    const uint4 *M;   // [R][C][2] uint4 (Montgomery form)
+    const uint4 *in;  // element (b, j) at in[(b*in_sb + j*in_sc)*2 .. +1]
+    uint4 *out;       // element (b, row) at out[(b*out_sb + row*out_sr)*2 .. +1]
+    int R, C;
+    long long B;
+    long long in_sb, in_sc, out_sb, out_sr;  // strides in 32-byte elements
+    const int *col_map;                     // [C] input index of column c, or nullptr (identity)
+    int n_chk, n_gate;
+    const int *chk_map;        // [n_chk] input index checked by check row r
+    unsigned char *fail;       // [B] set to 1 when a gate row mismatches (may be nullptr when n_gate == 0)
+    unsigned long long *flags; // [B][flag_words] or nullptr
+    int flag_words;
+    unsigned int *err;         // device word: bit0 set when a non-canonical (>= r) input is seen
+    int rows_per_slice;        // rows handled by one blockIdx.y slice
+    int in_chunk_major;        // 1: in_sc == 1 (tile is contiguous), 0: in_sb == 1 (sender-major)
+};
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(uint4 *p, const uint4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int TBT>
+__global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
+    const int C = a.C;
+    const int r0 = blockIdx.y * a.rows_per_slice;
+    const int nrows = min(a.rows_per_slice, a.R - r0);
+    uint4 *sM = reinterpret_cast<uint4 *>(smem_raw);                 // [nrows][C][2]
+    uint4 *sD = sM + (size_t)a.rows_per_slice * C * 2;               // [TBT][C][2][32]
+    unsigned int *sFail = reinterpret_cast<unsigned int *>(sD + (size_t)TBT * C * 64);  // [TBT*32]
+    unsigned long long *sFlags = reinterpret_cast<unsigned long long *>(sFail + TBT * 32);  // [TBT*32][flag_words]
+
+    // constant matrix slice -> shared memory (once per CTA; the CTA is persistent over batch tiles)
+    for (int i = tid; i < nrows * C * 2; i += blockDim.x) sM[i] = a.M[(size_t)r0 * C * 2 + i];
+
+    const long long TILE = TBT * 32;
+    const long long ntiles = (a.B + TILE - 1) / TILE;
+    const int nitems = nrows * TBT;
+    const bool checks_here = r0 < a.n_chk;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long b0 = tile * TILE;
+        __syncthreads();  // previous tile fully consumed (and sM visible on the first pass)
+        // ---- stage the data tile: element (b, c) -> sD[sub][c][half][lane]
+        const int nhalves = TBT * 32 * C * 2;
+        for (int i = tid; i < nhalves; i += blockDim.x) {
+            int half = i & 1, bl, c;
+            if (a.in_chunk_major) { c = (i >> 1) % C; bl = (i >> 1) / C; }
+            else { bl = (i >> 1) % (TBT * 32); c = (i >> 1) / (TBT * 32); }
+            long long b = b0 + bl;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (b < a.B) {
+                int j = a.col_map ? a.col_map[c] : c;
+                v = ldg_stream(a.in + (b * a.in_sb + (long long)j * a.in_sc) * 2 + half);
+            }
+            sD[(((bl >> 5) * C + c) * 2 + half) * 32 + (bl & 31)] = v;
+        }
+        if (checks_here) {
+            for (int i = tid; i < TBT * 32; i += blockDim.x) sFail[i] = 0;
+            if (a.flags) for (int i = tid; i < TBT * 32 * a.flag_words; i += blockDim.x) sFlags[i] = 0ull;
+        }
+        __syncthreads();
+
+        for (int item = warp; item < nitems; item += W) {
+            const int rl = item / TBT, sub = item - rl * TBT;
+            const int r = r0 + rl;
+            const long long b = b0 + sub * 32 + lane;
+            const uint4 *Mrow = sM + (size_t)rl * C * 2;
+            const uint4 *Dsub = sD + (size_t)sub * C * 64 + lane;
+            const bool is_chk = r < a.n_chk;
+            // the supplied share a check row is compared with (prefetched; hidden behind the dot product)
+            uint4 y_lo = make_uint4(0, 0, 0, 0), y_hi = y_lo;
+            int chk_j = 0;
+            if (is_chk) {
+                chk_j = a.chk_map[r];
+                if (b < a.B) {
+                    const uint4 *p = a.in + (b * a.in_sb + (long long)chk_j * a.in_sc) * 2;
+                    y_lo = ldg_stream(p);
+                    y_hi = ldg_stream(p + 1);
+                }
+            }
+            acc_t A;
+            acc_zero(A);
+            uint4 na_lo = Dsub[0], na_hi = Dsub[32], nb_lo = Mrow[0], nb_hi = Mrow[1];
+            unsigned bad = 0;
+            const bool validate = (rl == 0);  // one row per slice validates the tile's inputs (each input exactly once per slice)
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+                uint32_t x[8], m[8];
+                load_fr(x, na_lo, na_hi);
+                load_fr(m, nb_lo, nb_hi);
+                if (c + 1 < C) {
+                    na_lo = Dsub[(c + 1) * 64];
+                    na_hi = Dsub[(c + 1) * 64 + 32];
+                    nb_lo = Mrow[(c + 1) * 2];
+                    nb_hi = Mrow[(c + 1) * 2 + 1];
+                }
+                if (validate) bad |= geq_mod(x) ? 1u : 0u;
+                acc_mac(A, x, m);
+            }
+            uint32_t res[8];
+            acc_reduce(A, res);
+            if (is_chk) {
+                uint32_t y[8];
+                load_fr(y, y_lo, y_hi);
+                bad |= geq_mod(y) ? 1u : 0u;
+                if (b < a.B && !fr_eq(res, y)) {
+                    if (r < a.n_gate) sFail[sub * 32 + lane] = 1u;
+                    if (a.flags) atomicOr(&sFlags[(size_t)(sub * 32 + lane) * a.flag_words + (chk_j >> 6)], 1ull << (chk_j & 63));
+                }
+            } else if (b < a.B) {
+                uint4 *o = a.out + (b * a.out_sb + (long long)(r - a.n_chk) * a.out_sr) * 2;
+                stg_stream(o, make_uint4(res[0], res[1], res[2], res[3]));
+                stg_stream(o + 1, make_uint4(res[4], res[5], res[6], res[7]));
+            }
+            if (bad) atomicOr(a.err, 1u);
+        }
+        if (checks_here) {
+            __syncthreads();
+            for (int i = tid; i < TBT * 32; i += blockDim.x) {
+                long long b = b0 + i;
+                if (b < a.B) {
+                    if (a.fail && sFail[i]) a.fail[b] = 1;  // slices only ever raise the flag (buffer pre-zeroed by the host side)
+                    if (a.flags)
+                        for (int w = 0; w < a.flag_words; ++w) {
+                            unsigned long long f = sFlags[(size_t)i * a.flag_words + w];
+                            if (f) atomicOr(&a.flags[b * a.flag_words + w], f);
+                        }
+                }
+            }
+        }
+    }
+}
+
+// ---- launch-shape chooser ---------------------------------------------------------------------
+struct MatvecPlan {
+    int tbt;             // 32-lane sub-tiles per CTA tile (1, 2 or 4)
+    int warps;           // warps per CTA
+    int rows_per_slice;  // rows of M resident per CTA
+    int slices;          // gridDim.y
+    int ctas_per_sm;
+    size_t smem;
+};
+
+inline size_t matvec_smem_bytes(int rows, int C, int tbt, int flag_words) {
+    return (size_t)rows * C * 32 + (size_t)tbt * C * 1024 + (size_t)tbt * 32 * 4 + (size_t)tbt * 32 * 8 * (flag_words > 0 ? flag_words : 0) + 16;
+}
+
+// Pick the shape with the most resident warps per SM (register file allows ~24 warps at <=84 regs) and the
+// best work balance (items per warp integral), keeping all of M resident when it fits in 227 KB.
+inline MatvecPlan matvec_plan(int R, int C, int flag_words, int regs_per_thread) {
+    const size_t SMEM_CTA = 227 * 1024, SMEM_SM = 228 * 1024;
+    MatvecPlan best{};
+    double best_score = -1.0;
+    const int max_warps_regs = (65536 / (regs_per_thread > 0 ? regs_per_thread : 96)) / 32;
+    for (int slices = 1; slices <= R; ++slices) {
+        int rps = (R + slices - 1) / slices;
+        if ((rps * (slices - 1)) >= R && slices > 1) continue;  // empty last slice
+        bool any = false;
+        for (int tbt : {4, 2, 1}) {
+            for (int warps : {16, 8, 4}) {
+                size_t smem = matvec_smem_bytes(rps, C, tbt, flag_words);
+                if (smem > SMEM_CTA) continue;
+                int ctas = (int)(SMEM_SM / (smem + 1024));
+                if (ctas < 1) continue;
+                int by_regs = max_warps_regs / warps;
+                if (by_regs < 1) continue;
+                if (ctas > by_regs) ctas = by_regs;
+                if (ctas > 32) ctas = 32;
+                int resident = ctas * warps;
+                int items = rps * tbt;
+                int per_warp = (items + warps - 1) / warps;
+                double balance = (double)items / ((double)per_warp * warps);
+                double occ = resident >= 16 ? 1.0 : (double)resident / 16.0;
+                // staging overhead relative to MAC work shrinks with rows per slice; prefer fewer slices strongly
+                double score = balance * occ - 0.02 * (slices - 1) + 0.001 * resident;
+                if (score > best_score) { best_score = score; best = MatvecPlan{tbt, warps, rps, slices, ctas, smem}; }
+                any = true;
+            }
+        }
+        if (any && slices >= 1 && best_score > 0.85) break;  // good enough without further slicing
+    }
+    return best;
+}
+
+}  // namespace hb

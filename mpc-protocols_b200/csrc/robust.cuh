@@ -1,0 +1,406 @@
+// robust.cuh -- K4: Reed-Solomon robust interpolation for the items that fail the optimistic check.
+//
+// Reference behaviour being reproduced (robust_interpolate.rs:94-157, 456-538, 579-628): after the optimistic
+// attempt fails, OEC round r = 1..t looks at the lowest d+t+1+r ids ("prefix P_r"), runs Gao's decoder on it and
+// accepts iff the decoded polynomial disagrees with at most r shares of that prefix.  Gao decodes up to
+// floor((t+r)/2) >= r errors, and two distinct degree-<=d polynomials cannot both be within distance r <= t of the same
+// prefix (they would differ on >= t+r+1 of its points), so the reference's outcome is exactly
+//     "the first r for which SOME polynomial of degree <= d has <= r mismatches in P_r; that polynomial",
+// independent of Gao's internals.  Any bounded-distance decoder with radius >= r therefore returns bit-identical
+// (coefficients, path, flags).  This file uses syndromes + inversion-free Berlekamp-Massey + Chien + Forney:
+//
+//   attempt(P, nsyn, maxL):   S_j = sum_{i<P} u_i x_i^j y_i  (constant matrix H, j < nsyn = P-(d+1));
+//                             BM -> locator Lambda (degree L); accept iff L <= maxL and Lambda has L roots among
+//                             the prefix points; Forney -> error values.
+//   fast path  : ONE attempt on all S supplied shares (maxL = min(t, floor((S-d-1)/2))).  If it succeeds the true
+//                polynomial and all e <= t error positions are known, and the reference's round is the smallest r with
+//                #errors in P_r <= r (no other polynomial can be accepted earlier: it would need >= t+1 mismatches).
+//   exact path : if the fast attempt fails (more than maxL errors overall), attempts r = 1..rmax on the prefixes
+//                P_r with maxL = r -- the literal OEC loop.
+//
+// One thread decodes one codeword; per-thread polynomials live in a strided global workspace (coalesced across the
+// warp).  The corrected coefficients are obtained by linearity from what the optimistic kernel already wrote:
+//   coeffs(f) = Lc * y[0..m) - sum_{i in E, i<m} e_i * Lc[:, i].
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "fr.cuh"
+
+namespace hb {
+
+struct RobustArgs {
+    const uint4 *in;            // supplied shares: element (b, arrival j) at in[(b*in_sb + j*in_sc)*2 ..]
+    long long in_sb, in_sc, B;
+    const unsigned int *list;   // items that failed the optimistic check
+    const unsigned int *count;
+    int S, m, t, needed, rmax;  // m = d+1, needed = d+t+1, rmax = min(t, S-needed)
+    int fast;                   // attempt 0 (all S shares) is enabled
+    const int *att_P;           // [1 + rmax] prefix size per attempt (index 0 = fast path)
+    const int *att_nsyn;        // [1 + rmax]
+    const int *att_maxL;        // [1 + rmax]
+    const long long *att_Hoff;  // [1 + rmax] offset (in elements) of the attempt's H matrix [nsyn][P]
+    const long long *att_uoff;  // [1 + rmax] offset of the attempt's uinv vector [P]
+    const uint4 *H;             // (u_i x_i^j) * R^2: canonical y times this gives a Montgomery-form syndrome
+    const uint4 *uinv;          // prod_{l != i, l < P} (x_i - x_l), canonical (Montgomery c times this is canonical e)
+    const uint4 *xs;            // [S] x_i (Montgomery), sorted by id
+    const uint4 *xinv;          // [S] x_i^{-1} (Montgomery)
+    const uint4 *Lc;            // [m][m] Lagrange coefficient matrix of the lowest m ids (Montgomery)
+    const uint4 *Veval;         // [S][m] x_s^k (Montgomery)
+    const int *order;           // [S] arrival index of sorted position i
+    uint4 *coeffs;              // [B][mout] (already holds Lc*y from the optimistic kernel)
+    int mout;                   // m, or 1 when only the secret is wanted
+    int *path;
+    unsigned long long *flags;  // may be nullptr
+    int flag_words;
+    unsigned int *first_fail;   // atomicMin of failing item index
+    unsigned int *fail_any;     // set to 1 when any item fails to decode
+    uint4 *ws;                  // workspace: ws_elems Fr per thread, strided by total thread count
+    int ws_elems;
+};
+
+struct FrWs {
+    uint4 *base;
+    size_t stride;
+    __device__ __forceinline__ void ld(uint32_t (&a)[8], int e) const {
+        const uint4 *p = base + (size_t)e * stride * 2;
+        load_fr(a, p[0], p[1]);
+    }
+    __device__ __forceinline__ void st(int e, const uint32_t (&a)[8]) const {
+        uint4 *p = base + (size_t)e * stride * 2;
+        p[0] = make_uint4(a[0], a[1], a[2], a[3]);
+        p[1] = make_uint4(a[4], a[5], a[6], a[7]);
+    }
+};
+
+__device__ __forceinline__ void ldg_fr(uint32_t (&a)[8], const uint4 *p) { load_fr(a, __ldg(p), __ldg(p + 1)); }
+__device__ __forceinline__ void set_zero(uint32_t (&a)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 0;
+}
+__device__ __forceinline__ void copy8(uint32_t (&d)[8], const uint32_t (&s)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = s[i];
+}
+__device__ __forceinline__ void fr_neg(uint32_t (&d)[8], const uint32_t (&a)[8]) {
+    uint32_t z[8];
+    set_zero(z);
+    fr_sub(d, z, a);
+}
+
+// a^(r-2) in Montgomery form (Fermat).  ~255 squarings + ~128 products; used once per accepted attempt.
+__device__ __noinline__ void fr_inv_mont(uint32_t (&out)[8], const uint32_t (&a)[8]) {
+    const uint32_t e[8] = {0xffffffffu, 0xfffffffeu, HB_R2, HB_R3, HB_R4, HB_R5, HB_R6, HB_R7};
+    uint32_t acc[8];
+    one_mont_limbs(acc);
+#pragma unroll 1
+    for (int i = 254; i >= 0; --i) {
+        uint32_t s[8];
+        mont_mul(s, acc, acc);
+        if ((e[i >> 5] >> (i & 31)) & 1u) mont_mul(acc, s, a);
+        else copy8(acc, s);
+    }
+    copy8(out, acc);
+}
+
+// workspace slots (element offsets) -- sized by the host with the same formulae
+struct WsLayout {
+    int syn, lam, bp, om, num, den, pre, ev, total;
+    __host__ __device__ WsLayout(int nsyn_max, int t) {
+        syn = 0;
+        lam = syn + nsyn_max;
+        bp = lam + (t + 2);
+        om = bp + (t + 2);
+        num = om + (t + 1);
+        den = num + (t + 1);
+        pre = den + (t + 1);
+        ev = pre + (t + 1);
+        total = ev + (t + 1);
+    }
+};
+
+// One bounded-distance decoding attempt.  Returns the number of errors L (positions in rootpos[0..L), ascending sorted
+// position; canonical error values in ws[ev + q]) or -1.
+__device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b, const FrWs &ws, const WsLayout &lay, int *rootpos) {
+    const int P = a.att_P[att], nsyn = a.att_nsyn[att], maxL = a.att_maxL[att];
+    const uint4 *H = a.H + a.att_Hoff[att] * 2;
+    const uint4 *ybase = a.in + b * a.in_sb * 2;
+
+    // ---- syndromes (Montgomery form)
+#pragma unroll 1
+    for (int j = 0; j < nsyn; ++j) {
+        acc_t A;
+        acc_zero(A);
+        const uint4 *Hrow = H + (size_t)j * P * 2;
+#pragma unroll 1
+        for (int i = 0; i < P; ++i) {
+            uint32_t y[8], h[8];
+            ldg_fr(y, ybase + (long long)a.order[i] * a.in_sc * 2);
+            ldg_fr(h, Hrow + i * 2);
+            acc_mac(A, y, h);
+        }
+        uint32_t s[8];
+        acc_reduce(A, s);
+        ws.st(lay.syn + j, s);
+    }
+
+    // ---- inversion-free Berlekamp-Massey:  Lambda <- bdis*Lambda - delta * z^shift * Bp
+    uint32_t one[8], bdis[8];
+    one_mont_limbs(one);
+    copy8(bdis, one);
+    ws.st(lay.lam, one);
+    ws.st(lay.bp, one);
+    int L = 0, lenB = 1, shift = 1;
+#pragma unroll 1
+    for (int j = 0; j < nsyn; ++j) {
+        uint32_t delta[8];
+        {
+            acc_t A;
+            acc_zero(A);
+            const int lim = L < j ? L : j;
+#pragma unroll 1
+            for (int l = 0; l <= lim; ++l) {
+                uint32_t x[8], s[8];
+                ws.ld(x, lay.lam + l);
+                ws.ld(s, lay.syn + j - l);
+                acc_mac(A, x, s);
+            }
+            acc_reduce(A, delta);
+        }
+        if (fr_is_zero(delta)) { ++shift; continue; }
+        uint32_t nd[8];
+        fr_neg(nd, delta);
+        const bool grow = 2 * L <= j;
+        const int newL = grow ? j + 1 - L : L;
+        if (newL > maxL) return -1;
+#pragma unroll 1
+        for (int l = newL; l >= 0; --l) {
+            uint32_t lam[8], bl[8], res[8];
+            if (l <= L) ws.ld(lam, lay.lam + l); else set_zero(lam);
+            const int bi = l - shift;
+            const bool hasb = bi >= 0 && bi < lenB;
+            if (hasb) ws.ld(bl, lay.bp + bi); else set_zero(bl);
+            acc_t A;
+            acc_zero(A);
+            acc_mac(A, lam, bdis);
+            if (hasb) acc_mac(A, bl, nd);
+            acc_reduce(A, res);
+            ws.st(lay.lam + l, res);
+            if (grow && l <= L) ws.st(lay.bp + l, lam);
+        }
+        if (grow) {
+            lenB = L + 1;
+            L = newL;
+            copy8(bdis, delta);
+            shift = 1;
+        } else {
+            ++shift;
+        }
+    }
+    if (L == 0) return 0;
+
+    // ---- Chien search over the prefix points: Lambda(x_i^{-1}) == 0  <=>  position i is in error
+    int nroots = 0;
+#pragma unroll 1
+    for (int i = 0; i < P; ++i) {
+        uint32_t z[8], v[8];
+        ldg_fr(z, a.xinv + i * 2);
+        ws.ld(v, lay.lam + L);
+#pragma unroll 1
+        for (int l = L - 1; l >= 0; --l) {
+            uint32_t c[8], p[8];
+            mont_mul(p, v, z);
+            ws.ld(c, lay.lam + l);
+            fr_add(v, p, c);
+        }
+        if (fr_is_zero(v)) {
+            if (nroots < L) rootpos[nroots] = i;
+            ++nroots;
+        }
+    }
+    if (nroots != L) return -1;
+
+    // ---- Forney.  Omega = S*Lambda mod z^L;  c_i = -x_i Omega(x_i^{-1}) / Lambda'(x_i^{-1});  e_i = c_i * uinv_i
+#pragma unroll 1
+    for (int l = 0; l < L; ++l) {
+        acc_t A;
+        acc_zero(A);
+#pragma unroll 1
+        for (int k = 0; k <= l; ++k) {
+            uint32_t x[8], s[8];
+            ws.ld(x, lay.lam + k);
+            ws.ld(s, lay.syn + l - k);
+            acc_mac(A, x, s);
+        }
+        uint32_t o[8];
+        acc_reduce(A, o);
+        ws.st(lay.om + l, o);
+    }
+    uint32_t Lm[8];  // Montgomery form of the integer L
+    set_zero(Lm);
+#pragma unroll 1
+    for (int l = 0; l < L; ++l) { uint32_t tsum[8]; fr_add(tsum, Lm, one); copy8(Lm, tsum); }
+    uint32_t run[8];
+    copy8(run, one);
+#pragma unroll 1
+    for (int q = 0; q < L; ++q) {
+        const int i = rootpos[q];
+        uint32_t z[8], x[8], v[8], dv[8], lm[8];
+        ldg_fr(z, a.xinv + i * 2);
+        ldg_fr(x, a.xs + i * 2);
+        ws.ld(v, lay.om + L - 1);
+#pragma unroll 1
+        for (int l = L - 2; l >= 0; --l) {
+            uint32_t c[8], p[8];
+            mont_mul(p, v, z);
+            ws.ld(c, lay.om + l);
+            fr_add(v, p, c);
+        }
+        uint32_t numv[8];
+        mont_mul(numv, v, x);
+        // Lambda'(z) = sum_{l=1..L} l * Lambda_l z^(l-1)
+        copy8(lm, Lm);
+        set_zero(dv);
+#pragma unroll 1
+        for (int l = L; l >= 1; --l) {
+            uint32_t c[8], p[8], lc[8];
+            mont_mul(p, dv, z);
+            ws.ld(c, lay.lam + l);
+            mont_mul(lc, c, lm);
+            fr_add(dv, p, lc);
+            uint32_t nl[8];
+            fr_sub(nl, lm, one);
+            copy8(lm, nl);
+        }
+        if (fr_is_zero(dv)) return -1;
+        ws.st(lay.num + q, numv);
+        ws.st(lay.den + q, dv);
+        ws.st(lay.pre + q, run);
+        uint32_t nr[8];
+        mont_mul(nr, run, dv);
+        copy8(run, nr);
+    }
+    uint32_t inv[8];
+    fr_inv_mont(inv, run);
+    const uint4 *U = a.uinv + a.att_uoff[att] * 2;
+#pragma unroll 1
+    for (int q = L - 1; q >= 0; --q) {
+        uint32_t pre[8], den[8], dinv[8], numv[8], c[8], nc[8], u[8], e[8], ninv[8];
+        ws.ld(pre, lay.pre + q);
+        ws.ld(den, lay.den + q);
+        ws.ld(numv, lay.num + q);
+        mont_mul(dinv, inv, pre);
+        mont_mul(ninv, inv, den);
+        copy8(inv, ninv);
+        mont_mul(c, numv, dinv);
+        fr_neg(nc, c);
+        ldg_fr(u, U + rootpos[q] * 2);
+        mont_mul(e, nc, u);  // Montgomery c times canonical uinv -> canonical error value
+        ws.st(lay.ev + q, e);
+    }
+    return L;
+}
+
+#ifndef HB_ROBUST_MAXT
+#define HB_ROBUST_MAXT 85  // t < n/3, n <= 256
+#endif
+
+__global__ void __launch_bounds__(128) robust_kernel(const RobustArgs a) {
+    const unsigned int cnt = *a.count;
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int nsyn_max = 0;
+    for (int i = a.fast ? 0 : 1; i <= a.rmax; ++i) nsyn_max = max(nsyn_max, a.att_nsyn[i]);
+    const WsLayout lay(nsyn_max, a.t);
+    FrWs ws{a.ws + g * 2, T};
+    int rootpos[HB_ROBUST_MAXT];
+
+    for (size_t idx = g; idx < cnt; idx += T) {
+        const long long b = a.list[idx];
+        int L = -1, path = -8, used_att = -1;
+        if (a.fast) {
+            L = rs_attempt(a, 0, b, ws, lay, rootpos);
+            if (L >= 0) {
+                // all error positions known (L <= t): the reference accepts in the first round whose prefix holds <= r of them
+                used_att = 0;
+                int q = 0;
+                for (int r = 1; r <= a.rmax; ++r) {
+                    while (q < L && rootpos[q] < a.needed + r) ++q;
+                    if (q <= r) { path = r; break; }
+                }
+            }
+        }
+        if (L < 0) {
+            for (int r = 1; r <= a.rmax; ++r) {
+                L = rs_attempt(a, r, b, ws, lay, rootpos);
+                if (L >= 0) { path = r; used_att = r; break; }
+            }
+        }
+        uint4 *co = a.coeffs + b * a.mout * 2;
+        unsigned long long *fl = a.flags ? a.flags + b * a.flag_words : nullptr;
+        if (path < 0) {
+            for (int k = 0; k < a.mout; ++k) { co[k * 2] = make_uint4(0, 0, 0, 0); co[k * 2 + 1] = make_uint4(0, 0, 0, 0); }
+            if (fl) for (int w = 0; w < a.flag_words; ++w) fl[w] = 0ull;
+            a.path[b] = -8;
+            atomicMin(a.first_fail, (unsigned int)b);
+            atomicOr(a.fail_any, 1u);
+            continue;
+        }
+        // corrected coefficients by linearity
+        for (int k = 0; k < a.mout; ++k) {
+            acc_t A;
+            acc_zero(A);
+            bool any = false;
+            for (int q = 0; q < L; ++q) {
+                if (rootpos[q] >= a.m) break;
+                uint32_t e[8], lc[8];
+                ws.ld(e, lay.ev + q);
+                ldg_fr(lc, a.Lc + ((size_t)k * a.m + rootpos[q]) * 2);
+                acc_mac(A, e, lc);
+                any = true;
+            }
+            if (any) {
+                uint32_t corr[8], c[8], r[8];
+                acc_reduce(A, corr);
+                load_fr(c, co[k * 2], co[k * 2 + 1]);
+                fr_sub(r, c, corr);
+                co[k * 2] = make_uint4(r[0], r[1], r[2], r[3]);
+                co[k * 2 + 1] = make_uint4(r[4], r[5], r[6], r[7]);
+            }
+        }
+        if (fl) {
+            for (int w = 0; w < a.flag_words; ++w) fl[w] = 0ull;
+            for (int q = 0; q < L; ++q) {
+                const int j = a.order[rootpos[q]];
+                fl[j >> 6] |= 1ull << (j & 63);
+            }
+            // shares beyond the examined prefix: evaluate the decoded polynomial (needs all m coefficients: mout == m)
+            const int Pused = a.att_P[used_att];
+            const uint4 *ybase = a.in + b * a.in_sb * 2;
+            for (int s = Pused; s < a.S; ++s) {
+                acc_t A;
+                acc_zero(A);
+                for (int k = 0; k < a.m; ++k) {
+                    uint32_t c[8], v[8];
+                    load_fr(c, co[k * 2], co[k * 2 + 1]);
+                    ldg_fr(v, a.Veval + ((size_t)s * a.m + k) * 2);
+                    acc_mac(A, c, v);
+                }
+                uint32_t fv[8], y[8];
+                acc_reduce(A, fv);
+                const int j = a.order[s];
+                ldg_fr(y, ybase + (long long)j * a.in_sc * 2);
+                if (!fr_eq(fv, y)) fl[j >> 6] |= 1ull << (j & 63);
+            }
+        }
+        a.path[b] = path;
+    }
+}
+
+// items with fail[b] != 0 -> list (any order)
+__global__ void compact_kernel(const unsigned char *fail, long long B, unsigned int *list, unsigned int *count) {
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x)
+        if (fail[b]) list[atomicAdd(count, 1u)] = (unsigned int)b;
+}
+
+}  // namespace hb

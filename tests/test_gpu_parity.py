@@ -1,0 +1,352 @@
+"""GPU parity: every kernel, through the C ABI, bit-exact against the CPU oracle on the same seeded inputs.
+
+Scenarios follow SURVEY.md section 4a (the reference's own test matrix) plus the BASELINE shapes at reduced batch.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [(4, 1), (7, 2), (10, 3), (16, 5), (64, 21), (128, 42)]
+
+
+def _rand(orc, shape, seed):
+    return orc.random_fr(shape, seed)
+
+
+# ------------------------------------------------------------------ K1
+@pytest.mark.parametrize("n,t", CONFIGS + [(5, 1), (13, 4), (255, 84)])
+@pytest.mark.parametrize("deg_mult", [1, 2])
+def test_compute_shares_matches_oracle(ctx, orc, n, t, deg_mult):
+    d = t * deg_mult
+    B = 777 if n <= 64 else 130
+    coeffs = _rand(orc, (B, d + 1), 0x5EED0001 + n * 3 + deg_mult)
+    rc, want = orc.compute_shares(coeffs, n, threads=orc.max_threads())
+    assert rc == 0
+    got = ctx.compute_shares_batch(coeffs, n)
+    assert np.array_equal(got, want)
+
+
+def test_compute_shares_fixed_polynomial_kat(ctx, hb):
+    # robust_interpolate.rs:646-680: f = 7 + 3x + 5x^2, n = 16; share KATs from SURVEY.md 8c.3
+    coeffs = hb.to_limbs([[7, 3, 5]])
+    got = hb.from_limbs(ctx.compute_shares_batch(coeffs, 16))[0]
+    assert got[0] == 0xF
+    assert got[1] == 0x0C017888577EFB9AB9C555D3B5BC31E1CDBAD5FC7989CD68368C178E5B0D73D0
+    assert got[2] == 0x29188D8EE251B7713371996896F3B6B762F2C150E34BC902567FF79BC65CBE74
+    assert got[3] == 0x48AA887102257E1488DBC18CBF4C77E437F86F54D8A23928628A7BD8EFBCE893
+
+
+def test_compute_shares_errors(ctx, hb, orc):
+    c = _rand(orc, (4, 6), 1)
+    with pytest.raises(hb.HbmpcError) as e:
+        ctx.compute_shares_batch(c, 5)  # n <= d
+    assert e.value.code == hb.INVALID_INPUT
+    with pytest.raises(hb.HbmpcError) as e:
+        ctx.compute_shares_batch(c, 300)
+    assert e.value.code == hb.NO_SUITABLE_DOMAIN
+    bad = c.copy()
+    bad[2, 3] = np.array([0xFFFFFFFFFFFFFFFF] * 4, dtype=np.uint64)  # >= r
+    with pytest.raises(hb.HbmpcError) as e:
+        ctx.compute_shares_batch(bad, 16)
+    assert e.value.code == hb.INVALID_INPUT
+    # r itself is non-canonical, r-1 is fine
+    edge = hb.to_limbs([[hb.R_MOD - 1, hb.R_MOD - 1, 0, 0, 0, 1]])
+    rc, want = orc.compute_shares(edge, 16)
+    assert np.array_equal(ctx.compute_shares_batch(edge, 16), want)
+    edge = hb.to_limbs([[hb.R_MOD, 0, 0, 0, 0, 1]])
+    with pytest.raises(hb.HbmpcError):
+        ctx.compute_shares_batch(edge, 16)
+
+
+# ------------------------------------------------------------------ K2
+@pytest.mark.parametrize("n,cols", [(4, 3), (4, 2), (10, 4), (16, 6), (64, 22), (64, 43), (64, 64), (128, 43), (7, 7), (255, 85)])
+@pytest.mark.parametrize("recipient_major", [False, True])
+def test_apply_vandermonde_matches_oracle(ctx, orc, n, cols, recipient_major):
+    B = 301 if n <= 64 else 70
+    x = _rand(orc, (B, cols), 0x5EED0100 + n + cols)
+    rc, want = orc.apply_vandermonde(x, n, recipient_major, threads=orc.max_threads())
+    assert rc == 0
+    got = ctx.apply_vandermonde_batch(x, n, recipient_major)
+    assert np.array_equal(got, want)
+
+
+def test_apply_vandermonde_kat_n4(ctx, hb, orc):
+    # common/share/mod.rs:139-171: coefficients [1,2,3] -> y_j = 1 + 2 a_j + 3 a_j^2 on the n=4 domain
+    x = hb.to_limbs([[1, 2, 3]])
+    got = hb.from_limbs(ctx.apply_vandermonde_batch(x, 4))[0]
+    w = orc.domain_element(4, 1)
+    for j in range(4):
+        a = pow(w, j, hb.R_MOD)
+        assert got[j] == (1 + 2 * a + 3 * a * a) % hb.R_MOD
+    # tests/batchrecon_test.rs:28: secrets [3,4], n=4,t=1 -> y_j = 3 + 4 w^j
+    y = hb.from_limbs(ctx.apply_vandermonde_batch(hb.to_limbs([[3, 4]]), 4))[0]
+    assert y[0] == 7 and y[2] == hb.R_MOD - 1
+    assert y[1] == 0x0235473339D80C1343B00C0009D80C00000004000000000003 or y[1] == (3 + 4 * w) % hb.R_MOD
+
+
+def test_apply_matrix_matches_oracle(ctx, orc):
+    M = _rand(orc, (9, 5), 77)
+    x = _rand(orc, (100, 5), 78)
+    rc, want = orc.apply_matrix(M, x)
+    assert rc == 0
+    assert np.array_equal(ctx.apply_matrix_batch(M, x), want)
+
+
+# ------------------------------------------------------------------ K5
+@pytest.mark.parametrize("op", [0, 1, 2])
+def test_elementwise_matches_oracle(ctx, orc, hb, op):
+    a = _rand(orc, (5000,), 5)
+    b = _rand(orc, (5000,), 6)
+    a[0] = hb.to_limbs(hb.R_MOD - 1)
+    b[0] = hb.to_limbs(hb.R_MOD - 1)
+    a[1] = hb.to_limbs(0)
+    rc, want = orc.elementwise(op, a, b)
+    assert rc == 0
+    assert np.array_equal(ctx.elementwise(op, a, b), want)
+
+
+# ------------------------------------------------------------------ K3 / K4
+def _codewords(orc, n, d, B, seed):
+    coeffs = _rand(orc, (B, d + 1), seed)
+    rc, shares = orc.compute_shares(coeffs, n, threads=orc.max_threads())
+    assert rc == 0
+    return coeffs, shares  # shares[B][n]
+
+
+def _corrupt(shares, rng, n_err_per_item, positions=None):
+    """add nonzero offsets at random positions; returns corrupted copy"""
+    out = shares.copy()
+    B, S = shares.shape[0], shares.shape[1]
+    for b in range(B):
+        e = n_err_per_item[b]
+        if e == 0:
+            continue
+        pos = rng.choice(S if positions is None else positions, size=e, replace=False)
+        for p in pos:
+            out[b, p, 0] ^= np.uint64(rng.integers(1, 1 << 20))  # stays < r: only low limb changes
+    return out
+
+
+def _compare_recover(got, want, B):
+    rc_g, co_g, path_g, fl_g = got
+    assert rc_g == want["rc"], (rc_g, want["rc"])
+    assert np.array_equal(path_g, want["path"]), np.nonzero(path_g != want["path"])
+    assert np.array_equal(co_g, want["coeffs"])
+    if fl_g is not None:
+        assert np.array_equal(fl_g, want["flags"][:, : fl_g.shape[1]])
+
+
+@pytest.mark.parametrize("n,t", CONFIGS)
+@pytest.mark.parametrize("deg_mult", [1, 2])
+def test_batch_recover_honest(ctx, orc, n, t, deg_mult):
+    d = t * deg_mult
+    if d + t + 1 > n:
+        pytest.skip("needed > n")
+    B = 257 if n <= 64 else 66
+    coeffs, shares = _codewords(orc, n, d, B, 0x5EED0200 + n + deg_mult)
+    evals = np.ascontiguousarray(shares.transpose(1, 0, 2))  # [S][B]
+    ids = np.arange(n)
+    want = orc.batch_recover_secret(ids, evals, n, d, t, threads=orc.max_threads())
+    got = ctx.batch_recover(ids, evals, n, d, t, want_flags=True)
+    _compare_recover(got, want, B)
+    assert np.array_equal(got[1], coeffs)
+    assert not got[2].any()
+    # reversed arrival order (robust_interpolate.rs:880-927) and secrets-only variant
+    rev = ids[::-1].copy()
+    got_r = ctx.batch_recover(rev, np.ascontiguousarray(evals[::-1]), n, d, t, want_flags=False)
+    assert np.array_equal(got_r[1], coeffs)
+    rc, secrets, path = ctx.batch_recover_secrets(ids, evals, n, d, t)
+    assert rc == 0 and np.array_equal(secrets, coeffs[:, 0]) and not path.any()
+
+
+@pytest.mark.parametrize("n,t", [(7, 2), (10, 3), (16, 5), (64, 21)])
+def test_batch_recover_with_errors(ctx, orc, n, t):
+    d = t
+    B = 96 if n <= 16 else 48
+    rng = np.random.default_rng(n * 1000 + t)
+    coeffs, shares = _codewords(orc, n, d, B, 0x5EED0300 + n)
+    nerr = rng.integers(0, t + 1, size=B)
+    bad = _corrupt(shares, rng, nerr)
+    evals = np.ascontiguousarray(bad.transpose(1, 0, 2))
+    ids = np.arange(n)
+    want = orc.batch_recover_secret(ids, evals, n, d, t, threads=orc.max_threads())
+    got = ctx.batch_recover(ids, evals, n, d, t, want_flags=True)
+    _compare_recover(got, want, B)
+    assert np.array_equal(got[1], coeffs)  # <= t errors with all n shares: always decodable
+    # permuted arrival order, same answer; flags follow arrival order
+    perm = rng.permutation(n)
+    want_p = orc.batch_recover_secret(ids[perm], np.ascontiguousarray(evals[perm]), n, d, t, threads=orc.max_threads())
+    got_p = ctx.batch_recover(ids[perm], np.ascontiguousarray(evals[perm]), n, d, t, want_flags=True)
+    _compare_recover(got_p, want_p, B)
+    rc, secrets, path = ctx.batch_recover_secrets(ids, evals, n, d, t)
+    assert np.array_equal(secrets, coeffs[:, 0]) and np.array_equal(path, want["path"])
+
+
+def test_batch_recover_first_t_senders_corrupted(ctx, orc):
+    # robust_interpolate.rs:931-967: first t senders corrupted, distinct error per chunk
+    n, t, B = 10, 3, 16
+    coeffs, shares = _codewords(orc, n, t, B, 4242)
+    bad = shares.copy()
+    for b in range(B):
+        for p in range(t):
+            bad[b, p, 0] += np.uint64(1 + b + p)
+    evals = np.ascontiguousarray(bad.transpose(1, 0, 2))
+    want = orc.batch_recover_secret(np.arange(n), evals, n, t, t)
+    got = ctx.batch_recover(np.arange(n), evals, n, t, t, want_flags=True)
+    _compare_recover(got, want, B)
+    assert np.array_equal(got[1], coeffs)
+
+
+@pytest.mark.parametrize("n,t", [(7, 2), (10, 3)])
+def test_robust_all_error_subsets(ctx, orc, hb, n, t):
+    # robust_interpolate.rs:828-876 (all <= t subsets, n=7,t=2) and :728-756 (all triples, n=10,t=3), secret 42
+    d = t
+    coeffs = _rand(orc, (1, d + 1), 99)
+    coeffs[0, 0] = hb.to_limbs(42)
+    rc, sh = orc.compute_shares(coeffs, n)
+    subsets = [s for k in range(0, t + 1) for s in itertools.combinations(range(n), k)]
+    words = np.repeat(sh, len(subsets), axis=0)
+    for b, sub in enumerate(subsets):
+        for p in sub:
+            words[b, p, 0] += np.uint64(1000 + p)
+    ids = np.arange(n)
+    want = orc.robust_interpolate_batch(ids, words, n, d, t, threads=orc.max_threads())
+    rc, co, sec, path, flags = ctx.robust_interpolate_batch(ids, words, n, d, t, want_flags=True)
+    assert rc == want["rc"] == 0
+    assert np.array_equal(path, want["path"])
+    assert np.array_equal(co, want["coeffs"]) and np.array_equal(sec, want["secrets"])
+    assert np.array_equal(flags, want["flags"][:, : flags.shape[1]])
+    assert all(v == 42 for v in hb.from_limbs(sec))
+    for b, sub in enumerate(subsets):
+        assert int(flags[b, 0]) == sum(1 << p for p in sub)
+
+
+@pytest.mark.parametrize("n,t,S", [(10, 3, 7), (10, 3, 8), (10, 3, 9), (16, 5, 11), (16, 5, 13), (64, 21, 50), (64, 21, 43)])
+def test_robust_subset_of_senders(ctx, orc, n, t, S):
+    """S < n supplied shares, ids not starting at 0, error counts up to and beyond what the prefix rounds can absorb:
+    the GPU must reproduce the oracle's path / DecodingError pattern exactly."""
+    d = t
+    B = 64
+    rng = np.random.default_rng(S * 77 + n)
+    coeffs, shares = _codewords(orc, n, d, B, 0x5EED0400 + n + S)
+    ids = np.sort(rng.choice(n, size=S, replace=False))
+    arrival = rng.permutation(S)
+    words = shares[:, ids[arrival]]
+    nerr = rng.integers(0, t + 2, size=B)
+    nerr = np.minimum(nerr, S)
+    bad = _corrupt(words, rng, nerr)
+    want = orc.robust_interpolate_batch(ids[arrival], bad, n, d, t, threads=orc.max_threads())
+    rc, co, sec, path, flags = ctx.robust_interpolate_batch(ids[arrival], bad, n, d, t, want_flags=True)
+    assert np.array_equal(path, want["path"]), (path, want["path"])
+    assert rc == want["rc"]
+    assert np.array_equal(co, want["coeffs"]) and np.array_equal(sec, want["secrets"])
+    assert np.array_equal(flags, want["flags"][:, : flags.shape[1]])
+    evals = np.ascontiguousarray(bad.transpose(1, 0, 2))
+    want_b = orc.batch_recover_secret(ids[arrival], evals, n, d, t, threads=orc.max_threads())
+    got_b = ctx.batch_recover(ids[arrival], evals, n, d, t, want_flags=True)
+    _compare_recover(got_b, want_b, B)
+
+
+def test_robust_more_than_t_errors(ctx, orc):
+    """> t errors (tests/input_test.rs:204: 4 errors with t=3, n=10): outcome must equal the oracle's, item by item."""
+    n, t, d, B = 10, 3, 3, 200
+    rng = np.random.default_rng(5)
+    coeffs, shares = _codewords(orc, n, d, B, 31337)
+    nerr = rng.integers(t + 1, t + 3, size=B)
+    bad = _corrupt(shares, rng, nerr)
+    ids = np.arange(n)
+    want = orc.robust_interpolate_batch(ids, bad, n, d, t, threads=orc.max_threads())
+    rc, co, sec, path, flags = ctx.robust_interpolate_batch(ids, bad, n, d, t, want_flags=True)
+    assert np.array_equal(path, want["path"])
+    assert rc == want["rc"]
+    assert np.array_equal(co, want["coeffs"])
+    assert np.array_equal(flags, want["flags"][:, : flags.shape[1]])
+
+
+def test_robust_errors_only_beyond_prefix_take_path0(ctx, orc):
+    n, t, d, B = 16, 5, 5, 8
+    coeffs, shares = _codewords(orc, n, d, B, 2024)
+    bad = shares.copy()
+    bad[:, 13, 0] += np.uint64(5)  # id 13 >= d+t+1 = 11: never examined
+    ids = np.arange(n)
+    want = orc.robust_interpolate_batch(ids, bad, n, d, t)
+    rc, co, sec, path, flags = ctx.robust_interpolate_batch(ids, bad, n, d, t, want_flags=True)
+    assert rc == 0 and not path.any() and np.array_equal(co, coeffs)
+    assert np.array_equal(flags, want["flags"][:, : flags.shape[1]])
+    assert all(int(f) == 1 << 13 for f in flags[:, 0])
+
+
+def test_robust_n128_t42(ctx, orc):
+    """config (4) shape at reduced batch: n=128, t=42, e ~ U{0..42} errors, plus the adversarial all-errors-in-prefix case."""
+    n, t, d, B = 128, 42, 42, 24
+    rng = np.random.default_rng(128)
+    coeffs, shares = _codewords(orc, n, d, B, 0x5EED0004)
+    nerr = rng.integers(0, t + 1, size=B)
+    nerr[0], nerr[1] = 0, t
+    bad = _corrupt(shares, rng, nerr)
+    bad[2] = _corrupt(shares[2:3], rng, [t], positions=d + t + 1)[0]  # exactly t errors all at ids < 85
+    ids = np.arange(n)
+    want = orc.robust_interpolate_batch(ids, bad, n, d, t, threads=orc.max_threads())
+    rc, co, sec, path, flags = ctx.robust_interpolate_batch(ids, bad, n, d, t, want_flags=True)
+    assert rc == want["rc"] == 0
+    assert np.array_equal(path, want["path"])
+    assert np.array_equal(co, coeffs) and np.array_equal(co, want["coeffs"])
+    assert np.array_equal(flags, want["flags"][:, : flags.shape[1]])
+
+
+def test_recover_validation_errors(ctx, hb, orc):
+    n, t, d = 10, 3, 3
+    coeffs, shares = _codewords(orc, n, d, 4, 1)
+    evals = np.ascontiguousarray(shares.transpose(1, 0, 2))
+    ids = np.arange(n)
+    for bad_call, code in [
+        (lambda: ctx.batch_recover(ids[:6], evals[:6], n, d, t), hb.INVALID_INPUT),          # S < d+t+1
+        (lambda: ctx.batch_recover(ids, evals, 9, d, t), hb.INVALID_INPUT),                  # n < 3t+1
+        (lambda: ctx.batch_recover(np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 8]), evals, n, d, t), hb.INVALID_INPUT),  # duplicate id
+        (lambda: ctx.batch_recover(np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 10]), evals, n, d, t), hb.INVALID_INPUT),  # id >= n
+    ]:
+        with pytest.raises(hb.HbmpcError) as e:
+            bad_call()
+        assert e.value.code == code
+    # exactly S = d+t+1 with one error: optimistic fails and OEC cannot start -> DecodingError
+    S = d + t + 1
+    ev = evals[:S].copy()
+    ev[1, 2, 0] += np.uint64(9)
+    want = orc.batch_recover_secret(ids[:S], ev, n, d, t)
+    rc, co, path, _ = ctx.batch_recover(ids[:S], ev, n, d, t)
+    assert rc == want["rc"] == hb.DECODING_ERROR
+    assert np.array_equal(path, want["path"]) and path[2] == -hb.DECODING_ERROR
+    assert np.array_equal(co, want["coeffs"])
+
+
+def test_device_pointers_and_async(ctx, orc, hb):
+    torch = pytest.importorskip("torch")
+    n, d, B = 64, 21, 4096
+    coeffs = _rand(orc, (B, d + 1), 12)
+    rc, want = orc.compute_shares(coeffs, n, threads=orc.max_threads())
+    dc = torch.from_numpy(coeffs.view(np.int64)).cuda()
+    out = ctx.compute_shares_batch(dc, n)
+    assert out.is_cuda
+    assert np.array_equal(out.cpu().numpy().view(np.uint64), want)
+    ctx.set_async(True)
+    try:
+        out2 = torch.empty_like(out)
+        ctx.compute_shares_batch(dc, n, out=out2)
+        assert ctx.synchronize() == 0
+        assert torch.equal(out, out2)
+        ev = out.permute(1, 0, 2).contiguous()
+        rc, co, path, _ = ctx.batch_recover(np.arange(n), ev, n, d, 21)
+        assert ctx.synchronize() == 0
+        assert np.array_equal(co.cpu().numpy().view(np.uint64), coeffs)
+    finally:
+        ctx.set_async(False)
+
+
+def test_imad_probe_runs(ctx):
+    for v in (0, 1, 2):
+        g, ms = ctx.measure_imad_peak(v)
+        assert g > 100.0 and ms > 0
+    assert ctx.launch_count > 0
