@@ -225,7 +225,7 @@ def random_fr(shape, seed: int) -> np.ndarray:
     rnd = 0
     mod = np.array([(R_MOD >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(4)], dtype=np.uint64)
     while todo.size:
-        ctr = (np.uint64(seed) * np.uint64(0x100000001B3) + np.uint64(rnd) * np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+        ctr = np.uint64(((seed * 0x100000001B3) + rnd * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
         base = (todo.astype(np.uint64) * np.uint64(4) + ctr)
         limbs = np.stack([_splitmix(base + np.uint64(k)) for k in range(4)], axis=1)
         limbs[:, 3] >>= np.uint64(1)
