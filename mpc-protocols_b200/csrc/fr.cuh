@@ -45,7 +45,46 @@ struct fr_t {
 // ----------------------------------------------------------------------------------------------
 // carry-chain primitives
 // ----------------------------------------------------------------------------------------------
-// (x0..x7) += (a0 + a1*2^64 + a2*2^128 + a3*2^192) * b   (four 64-bit lanes), k += carry-out
+// (l0,l1,l2,l3) += (a0 + a1*2^64 + a2*2^128 + a3*2^192) * b   (four 64-bit lanes), k += carry-out.
+// The lanes are 64-bit variables so that ptxas keeps each (lo,hi) in the aligned register pair IMAD.WIDE needs.
+HB_DEV void chain4w(unsigned long long &l0, unsigned long long &l1, unsigned long long &l2, unsigned long long &l3, uint32_t &k,
+                    uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t"
+        ".reg .u32 x0, x1, x2, x3, x4, x5, x6, x7;\n\t"
+        "mov.b64 {x0, x1}, %0;\n\t"
+        "mov.b64 {x2, x3}, %1;\n\t"
+        "mov.b64 {x4, x5}, %2;\n\t"
+        "mov.b64 {x6, x7}, %3;\n\t"
+        "mad.lo.cc.u32 x0, %5, %9, x0;\n\t"
+        "madc.hi.cc.u32 x1, %5, %9, x1;\n\t"
+        "madc.lo.cc.u32 x2, %6, %9, x2;\n\t"
+        "madc.hi.cc.u32 x3, %6, %9, x3;\n\t"
+        "madc.lo.cc.u32 x4, %7, %9, x4;\n\t"
+        "madc.hi.cc.u32 x5, %7, %9, x5;\n\t"
+        "madc.lo.cc.u32 x6, %8, %9, x6;\n\t"
+        "madc.hi.cc.u32 x7, %8, %9, x7;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "mov.b64 %0, {x0, x1};\n\t"
+        "mov.b64 %1, {x2, x3};\n\t"
+        "mov.b64 %2, {x4, x5};\n\t"
+        "mov.b64 %3, {x6, x7};\n\t"
+        "}"
+        : "+l"(l0), "+l"(l1), "+l"(l2), "+l"(l3), "+r"(k)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
+#else
+    unsigned long long *x[4] = {&l0, &l1, &l2, &l3};
+    const uint32_t a[4] = {a0, a1, a2, a3};
+    unsigned cy = 0;
+    for (int l = 0; l < 4; ++l) {
+        unsigned __int128 s = (unsigned __int128)a[l] * b + *x[l] + cy;
+        *x[l] = (unsigned long long)s;
+        cy = (unsigned)(s >> 64);
+    }
+    k += cy;
+#endif
+}
+// 32-bit view kept for the Montgomery rows of acc_reduce
 HB_DEV void chain4(uint32_t &x0, uint32_t &x1, uint32_t &x2, uint32_t &x3, uint32_t &x4, uint32_t &x5,
                                        uint32_t &x6, uint32_t &x7, uint32_t &k, uint32_t a0, uint32_t a1, uint32_t a2,
                                        uint32_t a3, uint32_t b) {
@@ -75,17 +114,19 @@ HB_DEV void chain4(uint32_t &x0, uint32_t &x1, uint32_t &x2, uint32_t &x3, uint3
 #endif
 }
 
-// Lazy accumulator for sum_k a_k * b_k (each factor < 2^256).  E holds even-aligned 64-bit lanes
-// (positions 2j,2j+1), O odd-aligned lanes (positions 2j+1,2j+2), K[p] counts carries into position p.
+// Lazy accumulator for sum_k a_k * b_k (each factor < 2^256).  E[j] holds the even-aligned 64-bit lane at limb positions
+// (2j, 2j+1), O[j] the odd-aligned lane at (2j+1, 2j+2), K[p] counts carries into limb position p.
 struct acc_t {
-    uint32_t E[16];
-    uint32_t O[16];  // positions 1..14 used
+    unsigned long long E[8];
+    unsigned long long O[7];
     uint32_t K[17];  // positions 8..16 used
 };
 
 HB_DEV void acc_zero(acc_t &A) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { A.E[i] = 0; A.O[i] = 0; }
+    for (int i = 0; i < 8; ++i) A.E[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) A.O[i] = 0;
 #pragma unroll
     for (int i = 0; i < 17; ++i) A.K[i] = 0;
 }
@@ -93,15 +134,12 @@ HB_DEV void acc_zero(acc_t &A) {
 // A += a * b  (64 IMAD.WIDE + 16 carry-counter adds)
 HB_DEV void acc_mac(acc_t &A, const uint32_t (&a)[8], const uint32_t (&b)[8]) {
 #pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-        chain4(A.E[i], A.E[i + 1], A.E[i + 2], A.E[i + 3], A.E[i + 4], A.E[i + 5], A.E[i + 6], A.E[i + 7], A.K[i + 8],
-               a[0], a[2], a[4], a[6], b[i]);
-        chain4(A.O[i + 1], A.O[i + 2], A.O[i + 3], A.O[i + 4], A.O[i + 5], A.O[i + 6], A.O[i + 7], A.O[i + 8], A.K[i + 9],
-               a[1], a[3], a[5], a[7], b[i]);
-        chain4(A.O[i + 1], A.O[i + 2], A.O[i + 3], A.O[i + 4], A.O[i + 5], A.O[i + 6], A.O[i + 7], A.O[i + 8], A.K[i + 9],
-               a[0], a[2], a[4], a[6], b[i + 1]);
-        chain4(A.E[i + 2], A.E[i + 3], A.E[i + 4], A.E[i + 5], A.E[i + 6], A.E[i + 7], A.E[i + 8], A.E[i + 9], A.K[i + 10],
-               a[1], a[3], a[5], a[7], b[i + 1]);
+    for (int h = 0; h < 4; ++h) {
+        const int i = 2 * h;
+        chain4w(A.E[h], A.E[h + 1], A.E[h + 2], A.E[h + 3], A.K[i + 8], a[0], a[2], a[4], a[6], b[i]);
+        chain4w(A.O[h], A.O[h + 1], A.O[h + 2], A.O[h + 3], A.K[i + 9], a[1], a[3], a[5], a[7], b[i]);
+        chain4w(A.O[h], A.O[h + 1], A.O[h + 2], A.O[h + 3], A.K[i + 9], a[0], a[2], a[4], a[6], b[i + 1]);
+        chain4w(A.E[h + 1], A.E[h + 2], A.E[h + 3], A.E[h + 4], A.K[i + 10], a[1], a[3], a[5], a[7], b[i + 1]);
     }
 }
 
@@ -226,18 +264,24 @@ HB_DEV bool fr_is_zero(const uint32_t (&a)[8]) {
 // ----------------------------------------------------------------------------------------------
 HB_DEV void acc_reduce(const acc_t &A, uint32_t (&out)[8]) {
     uint32_t T[17];
+    uint32_t AE[16], AO[16];  // 32-bit views: AE[p] / AO[p] = limb at position p
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { AE[2 * j] = (uint32_t)A.E[j]; AE[2 * j + 1] = (uint32_t)(A.E[j] >> 32); }
+    AO[0] = 0; AO[15] = 0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) { AO[2 * j + 1] = (uint32_t)A.O[j]; AO[2 * j + 2] = (uint32_t)(A.O[j] >> 32); }
     // merge E + O (O[p] sits at position p), then the carry counters K[8..16]
-    T[0] = A.E[0];
+    T[0] = AE[0];
     uint32_t c;
     {
         uint32_t x[8], y[8], d[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { x[i] = A.E[1 + i]; y[i] = A.O[1 + i]; }
+        for (int i = 0; i < 8; ++i) { x[i] = AE[1 + i]; y[i] = AO[1 + i]; }
         c = add8c(d, x, y, 0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) T[1 + i] = d[i];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { x[i] = (9 + i <= 15) ? A.E[9 + i] : 0u; y[i] = (9 + i <= 14) ? A.O[9 + i] : 0u; }
+        for (int i = 0; i < 8; ++i) { x[i] = (9 + i <= 15) ? AE[9 + i] : 0u; y[i] = (9 + i <= 14) ? AO[9 + i] : 0u; }
         add8c(d, x, y, c);
 #pragma unroll
         for (int i = 0; i < 8; ++i) T[9 + i] = d[i];

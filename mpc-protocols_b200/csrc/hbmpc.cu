@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -14,6 +15,7 @@
 #include "../../include/hbmpc_b200.h"
 #include "fr.cuh"
 #include "matvec.cuh"
+#include "ntt.cuh"
 #include "robust.cuh"
 #include "tables.hpp"
 
@@ -139,6 +141,8 @@ struct hbmpc_ctx {
     std::string err;
     int num_sms = 148;
     int matvec_regs[3] = {0, 0, 0};
+    int ntt_ctas[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // resident CTAs per SM of ntt_kernel<LOGN>
+    bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
     unsigned int *d_status = nullptr;  // [0] non-canonical input seen, [1] first failing item, [2] failing-item count
     unsigned int *h_status = nullptr;  // pinned
     int sticky = 0;
@@ -222,6 +226,10 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
         return HBMPC_NO_DEVICE;  // sm_100a only
     }
     ctx->num_sms = prop.multiProcessorCount;
+    {
+        const char *fd = getenv("HBMPC_FORCE_DENSE");
+        ctx->force_dense = fd && fd[0] == '1';
+    }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc((void **)&ctx->d_status, 16) != cudaSuccess || cudaMallocHost((void **)&ctx->h_status, 16) != cudaSuccess) {
         delete ctx;
@@ -364,6 +372,60 @@ static int launch_matvec(hbmpc_ctx *ctx, MatvecArgs a, int flag_words) {
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------ NTT launch (K1/K2 on the domain)
+template <int LOGN>
+static int launch_ntt_t(hbmpc_ctx *ctx, const NttArgs &a) {
+    const size_t smem = ntt_smem_bytes<LOGN>();
+    if (ctx->ntt_ctas[LOGN] == 0) {
+        CK(cudaFuncSetAttribute(ntt_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ntt_kernel<LOGN>, 256, smem));
+        ctx->ntt_ctas[LOGN] = nb > 0 ? nb : 1;
+    }
+    const int ipc = ntt_items_per_cta<LOGN>();
+    long long ntiles = (a.B + ipc - 1) / ipc;
+    long long grid = std::min<long long>(ntiles, (long long)ctx->num_sms * ctx->ntt_ctas[LOGN]);
+    ntt_kernel<LOGN><<<(unsigned)grid, 256, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+static int launch_ntt(hbmpc_ctx *ctx, int logn, const NttArgs &a) {
+    switch (logn) {
+        case 1: return launch_ntt_t<1>(ctx, a);
+        case 2: return launch_ntt_t<2>(ctx, a);
+        case 3: return launch_ntt_t<3>(ctx, a);
+        case 4: return launch_ntt_t<4>(ctx, a);
+        case 5: return launch_ntt_t<5>(ctx, a);
+        case 6: return launch_ntt_t<6>(ctx, a);
+        case 7: return launch_ntt_t<7>(ctx, a);
+        case 8: return launch_ntt_t<8>(ctx, a);
+    }
+    ctx->err = "ntt: unsupported domain size";
+    return HBMPC_NO_SUITABLE_DOMAIN;
+}
+
+static int get_twiddles(hbmpc_ctx *ctx, int N, uint4 **out) {
+    char key[64];
+    snprintf(key, sizeof key, "W %d", N);
+    auto it = ctx->matrices.find(key);
+    if (it != ctx->matrices.end()) {
+        *out = it->second;
+        return 0;
+    }
+    std::vector<HFr> tw = domain_elements((size_t)N, (size_t)std::max(N / 2, 1));
+    uint4 *d = nullptr;
+    int rc = upload_fr(ctx, tw, &d);
+    if (rc) return rc;
+    ctx->matrices[key] = d;
+    *out = d;
+    return 0;
+}
+
+// out[b][j] = sum_k w_N^(jk) in[b][k]: NTT when the zero-padded input fits the domain, dense matvec otherwise
+static int apply_domain_dev(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out, int recipient_major);
+
 static int get_vandermonde(hbmpc_ctx *ctx, size_t n, size_t cols, uint4 **out) {
     char key[64];
     snprintf(key, sizeof key, "V %zu %zu", n, cols);
@@ -410,6 +472,41 @@ static int apply_matrix_dev(hbmpc_ctx *ctx, const uint4 *M, size_t rows, size_t 
     return finish(ctx);
 }
 
+static int apply_domain_dev(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out, int recipient_major) {
+    const int N = domain_size(n);
+    int logn = 0;
+    while ((1 << logn) < N) ++logn;
+    if (ctx->force_dense || N < 2 || cols > (size_t)N) {
+        uint4 *V = nullptr;
+        int rc = get_vandermonde(ctx, n, cols, &V);
+        if (rc) return rc;
+        return apply_matrix_dev(ctx, V, n, cols, B, in, out, recipient_major);
+    }
+    uint4 *tw = nullptr;
+    int rc = get_twiddles(ctx, N, &tw);
+    if (rc) return rc;
+    Staged si, so;
+    if ((rc = stage_in(ctx, 0, in, B * cols * 32, si))) return rc;
+    if ((rc = stage_out(ctx, 1, out, B * n * 32, so))) return rc;
+    NttArgs a{};
+    a.in = (const uint4 *)si.dev;
+    a.out = (uint4 *)so.dev;
+    a.tw = tw;
+    a.B = (long long)B;
+    a.in_sb = (long long)cols;
+    a.in_sc = 1;
+    if (recipient_major) { a.out_sb = 1; a.out_sr = (long long)B; }
+    else { a.out_sb = (long long)n; a.out_sr = 1; }
+    a.cols = (int)cols;
+    a.n = (int)n;
+    a.err = ctx->d_status;
+    if ((rc = launch_ntt(ctx, logn, a))) return rc;
+    bool ns = false;
+    if ((rc = unstage_out(ctx, so, ns))) return rc;
+    if (ns && ctx->async) CK(cudaStreamSynchronize(ctx->stream));
+    return finish(ctx);
+}
+
 extern "C" int hbmpc_compute_shares_batch(hbmpc_ctx *ctx, size_t n, size_t d, size_t B, const uint64_t *coeffs, uint64_t *shares) {
     if (!ctx) return HBMPC_INVALID_INPUT;
     if (n <= d) return HBMPC_INVALID_INPUT;          // robust_interpolate.rs:59-64
@@ -417,10 +514,7 @@ extern "C" int hbmpc_compute_shares_batch(hbmpc_ctx *ctx, size_t n, size_t d, si
     if (B == 0) return HBMPC_SUCCESS;
     if (!coeffs || !shares) return HBMPC_INVALID_INPUT;
     cudaSetDevice(ctx->device);
-    uint4 *V = nullptr;
-    int rc = get_vandermonde(ctx, n, d + 1, &V);
-    if (rc) return rc;
-    return apply_matrix_dev(ctx, V, n, d + 1, B, coeffs, shares, 0);
+    return apply_domain_dev(ctx, n, d + 1, B, coeffs, shares, 0);
 }
 
 extern "C" int hbmpc_apply_vandermonde_batch(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out,
@@ -431,10 +525,7 @@ extern "C" int hbmpc_apply_vandermonde_batch(hbmpc_ctx *ctx, size_t n, size_t co
     if (B == 0) return HBMPC_SUCCESS;
     if (!in || !out) return HBMPC_INVALID_INPUT;
     cudaSetDevice(ctx->device);
-    uint4 *V = nullptr;
-    int rc = get_vandermonde(ctx, n, cols, &V);
-    if (rc) return rc;
-    return apply_matrix_dev(ctx, V, n, cols, B, in, out, recipient_major);
+    return apply_domain_dev(ctx, n, cols, B, in, out, recipient_major);
 }
 
 extern "C" int hbmpc_apply_matrix_batch(hbmpc_ctx *ctx, size_t rows, size_t cols, const uint64_t *matrix, size_t B, const uint64_t *in,

@@ -114,22 +114,37 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
             }
             acc_t A;
             acc_zero(A);
-            uint4 na_lo = Dsub[0], na_hi = Dsub[32], nb_lo = Mrow[0], nb_hi = Mrow[1];
             unsigned bad = 0;
             const bool validate = (rl == 0);  // one row per slice validates the tile's inputs (each input exactly once per slice)
+            // two register sets, loads issued one term ahead, no register moves (loop unrolled by two)
+            uint4 a0 = Dsub[0], a1 = Dsub[32], b0 = Mrow[0], b1 = Mrow[1];
+            uint4 c0 = a0, c1 = a1, d0 = b0, d1 = b1;
 #pragma unroll 1
-            for (int c = 0; c < C; ++c) {
-                uint32_t x[8], m[8];
-                load_fr(x, na_lo, na_hi);
-                load_fr(m, nb_lo, nb_hi);
+            for (int c = 0; c < C; c += 2) {
                 if (c + 1 < C) {
-                    na_lo = Dsub[(c + 1) * 64];
-                    na_hi = Dsub[(c + 1) * 64 + 32];
-                    nb_lo = Mrow[(c + 1) * 2];
-                    nb_hi = Mrow[(c + 1) * 2 + 1];
+                    c0 = Dsub[(c + 1) * 64];
+                    c1 = Dsub[(c + 1) * 64 + 32];
+                    d0 = Mrow[(c + 1) * 2];
+                    d1 = Mrow[(c + 1) * 2 + 1];
                 }
-                if (validate) bad |= geq_mod(x) ? 1u : 0u;
-                acc_mac(A, x, m);
+                {
+                    const uint32_t x[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const uint32_t m[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    if (validate) bad |= geq_mod(x) ? 1u : 0u;
+                    acc_mac(A, x, m);
+                }
+                if (c + 2 < C) {
+                    a0 = Dsub[(c + 2) * 64];
+                    a1 = Dsub[(c + 2) * 64 + 32];
+                    b0 = Mrow[(c + 2) * 2];
+                    b1 = Mrow[(c + 2) * 2 + 1];
+                }
+                if (c + 1 < C) {
+                    const uint32_t x[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                    const uint32_t m[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                    if (validate) bad |= geq_mod(x) ? 1u : 0u;
+                    acc_mac(A, x, m);
+                }
             }
             uint32_t res[8];
             acc_reduce(A, res);

@@ -1,0 +1,189 @@
+// ntt.cuh -- K1/K2 on the evaluation domain: out[b][j] = sum_{k<cols} in[b][k] * w_N^(jk), j < n <= N = next_pow2(n).
+//
+// The reference evaluates the share polynomial with `domain.fft(&poly)` and keeps the first n values
+// (robust_interpolate.rs:68-79, shamir.rs:181-193), and its Vandermonde matrix has entries element(j)^k = w_N^(jk)
+// (common/share/mod.rs:31-45): both are the first n outputs of a zero-padded size-N number-theoretic transform.
+// Residues are unique, so a radix-2 NTT returns bit-identical shares with ~N/2*log2(N) modular products per item instead
+// of n*cols (n=64, d=21: ~130 products against 1408 multiply-accumulates + 64 reductions).
+//
+// Mapping: decimation in time.  N/8 threads (all in one warp) own one item; each thread holds 8 elements in registers
+// and runs up to 3 butterfly stages per pass; passes exchange through a padded shared-memory buffer (conflict-free
+// 128-bit accesses) with __syncwarp only.  Pass 0 gathers the input in bit-reversed order straight from global memory
+// (zero padding beyond `cols` costs no loads), the last pass writes natural-order outputs j < n.  Data stays canonical,
+// twiddles are in Montgomery form (fr.cuh), so there is no conversion pass.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "fr.cuh"
+#include "matvec.cuh"  // ldg_stream / stg_stream
+
+namespace hb {
+
+struct NttArgs {
+    const uint4 *in;   // element (b, k) at in[(b*in_sb + k*in_sc)*2 ..]
+    uint4 *out;        // element (b, j) at out[(b*out_sb + j*out_sr)*2 ..]
+    const uint4 *tw;   // [N/2][2] w_N^k in Montgomery form
+    long long B, in_sb, in_sc, out_sb, out_sr;
+    int cols, n;
+    unsigned int *err;
+};
+
+__device__ __forceinline__ void ntt_butterfly(uint32_t (&u)[8], uint32_t (&v)[8], const uint4 *tw, int twidx) {
+    uint32_t t[8], s[8], d[8];
+    if (twidx != 0) {
+        uint32_t w[8];
+        load_fr(w, tw[twidx * 2], tw[twidx * 2 + 1]);
+        mont_mul(t, v, w);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = v[i];
+    }
+    fr_add(s, u, t);
+    fr_sub(d, u, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { u[i] = s[i]; v[i] = d[i]; }
+}
+
+// GG butterfly stages on the 2^GG register-resident elements x[e] that sit at positions base + e*h0
+template <int GG, int E>
+__device__ __forceinline__ void ntt_stages(uint32_t (&x)[E][8], const uint4 *tw, int low, int h0, int tw_shift0) {
+#pragma unroll
+    for (int q = 0; q < GG; ++q) {
+        // half = h0 << q; twiddle exponent of position p: (p mod half) * N/(2*half)
+        const int tws = tw_shift0 - q;  // log2(N / (2*half))
+#pragma unroll
+        for (int e = 0; e < (1 << GG); ++e) {
+            if (e & (1 << q)) continue;
+            const int twidx = (low + (e & ((1 << q) - 1)) * h0) << tws;
+            ntt_butterfly(x[e], x[e | (1 << q)], tw, twidx);
+        }
+    }
+}
+
+template <int LOGN>
+__host__ __device__ constexpr int ntt_g() { return LOGN < 3 ? LOGN : 3; }
+
+template <int LOGN>
+__global__ void __launch_bounds__(256, 2) ntt_kernel(const NttArgs a) {
+    constexpr int N = 1 << LOGN;
+    constexpr int G = ntt_g<LOGN>();
+    constexpr int E = 1 << G;
+    constexpr int TPI = N / E;                  // threads per item (<= 32)
+    constexpr int IPC = 256 / TPI;              // items per CTA tile
+    constexpr int NP = (LOGN + G - 1) / G;      // passes
+    constexpr int GL = LOGN - G * (NP - 1);     // stages in the last pass
+    constexpr int PADN = N + N / 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4 *sTw = reinterpret_cast<uint4 *>(smem_raw);            // [N/2][2]
+    uint4 *sD = sTw + (N > 1 ? N : 2);                           // [IPC][2][PADN]
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sTw[i] = a.tw[i];  // N/2 entries * 2 halves
+    __syncthreads();
+
+    const int tid_i = threadIdx.x % TPI, item_l = threadIdx.x / TPI;
+    uint4 *myD = sD + (size_t)item_l * 2 * PADN;
+    const long long ntiles = (a.B + IPC - 1) / IPC;
+    unsigned bad = 0;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long b = tile * IPC + item_l;
+        const bool active = b < a.B;
+        uint32_t x[E][8];
+        // ---- pass 0: bit-reversed gather from global, stages with half = 1, 2, 4 (twiddles depend on e only)
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int pos = tid_i * E + e;
+            const int k = (int)(__brev((unsigned)pos) >> (32 - LOGN));
+            if (active && k < a.cols) {
+                const uint4 *p = a.in + (b * a.in_sb + (long long)k * a.in_sc) * 2;
+                load_fr(x[e], ldg_stream(p), ldg_stream(p + 1));
+                bad |= geq_mod(x[e]) ? 1u : 0u;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[e][i] = 0;
+            }
+        }
+        ntt_stages<G, E>(x, sTw, 0, 1, LOGN - 1);
+        if constexpr (NP == 1) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int pos = tid_i * E + e;
+                if (active && pos < a.n) {
+                    uint4 *o = a.out + (b * a.out_sb + (long long)pos * a.out_sr) * 2;
+                    stg_stream(o, make_uint4(x[e][0], x[e][1], x[e][2], x[e][3]));
+                    stg_stream(o + 1, make_uint4(x[e][4], x[e][5], x[e][6], x[e][7]));
+                }
+            }
+        } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int pos = tid_i * E + e, idx = pos + (pos >> 3);
+            myD[idx] = make_uint4(x[e][0], x[e][1], x[e][2], x[e][3]);
+            myD[PADN + idx] = make_uint4(x[e][4], x[e][5], x[e][6], x[e][7]);
+        }
+        __syncwarp();
+        // ---- middle passes (G stages each)
+#pragma unroll
+        for (int p = 1; p < NP - 1; ++p) {
+            const int sh = G * p, h0 = 1 << sh;
+            const int low = tid_i & (h0 - 1), base = ((tid_i >> sh) << (sh + G)) | low;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int pos = base + e * h0, idx = pos + (pos >> 3);
+                load_fr(x[e], myD[idx], myD[PADN + idx]);
+            }
+            ntt_stages<G, E>(x, sTw, low, h0, LOGN - 1 - sh);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int pos = base + e * h0, idx = pos + (pos >> 3);
+                myD[idx] = make_uint4(x[e][0], x[e][1], x[e][2], x[e][3]);
+                myD[PADN + idx] = make_uint4(x[e][4], x[e][5], x[e][6], x[e][7]);
+            }
+            __syncwarp();
+        }
+        // ---- last pass (GL stages): N >> GL units per item, natural-order outputs to global
+        {
+            constexpr int sh = G * (NP - 1), h0 = 1 << sh, EL = 1 << GL;
+#pragma unroll 1
+            for (int u = tid_i; u < (N >> GL); u += TPI) {
+                const int low = u & (h0 - 1), base = ((u >> sh) << (sh + GL)) | low;
+                uint32_t y[EL][8];
+#pragma unroll
+                for (int e = 0; e < EL; ++e) {
+                    const int pos = base + e * h0, idx = pos + (pos >> 3);
+                    load_fr(y[e], myD[idx], myD[PADN + idx]);
+                }
+                ntt_stages<GL, EL>(y, sTw, low, h0, LOGN - 1 - sh);
+#pragma unroll
+                for (int e = 0; e < EL; ++e) {
+                    const int pos = base + e * h0;
+                    if (active && pos < a.n) {
+                        uint4 *o = a.out + (b * a.out_sb + (long long)pos * a.out_sr) * 2;
+                        stg_stream(o, make_uint4(y[e][0], y[e][1], y[e][2], y[e][3]));
+                        stg_stream(o + 1, make_uint4(y[e][4], y[e][5], y[e][6], y[e][7]));
+                    }
+                }
+            }
+            __syncwarp();  // the tile's buffer is reused by the next tile's pass 0 writes
+        }
+        }  // NP > 1
+    }
+    if (bad) atomicOr(a.err, 1u);
+}
+
+template <int LOGN>
+inline size_t ntt_smem_bytes() {
+    constexpr int N = 1 << LOGN;
+    constexpr int G = ntt_g<LOGN>();
+    constexpr int TPI = N / (1 << G);
+    constexpr int IPC = 256 / TPI;
+    constexpr int NP = (LOGN + G - 1) / G;
+    size_t tw = (size_t)(N > 1 ? N : 2) * 16;
+    return tw + (NP > 1 ? (size_t)IPC * 2 * (N + N / 8) * 16 : 0) + 16;
+}
+template <int LOGN>
+inline int ntt_items_per_cta() {
+    return 256 / ((1 << LOGN) / (1 << ntt_g<LOGN>()));
+}
+
+}  // namespace hb

@@ -103,6 +103,22 @@ __global__ void __launch_bounds__(256) probeD(uint32_t *sink, uint32_t seed, int
     if (s == 0x1234567u) sink[0] = s;
 }
 
+__global__ void __launch_bounds__(256) probeF(double *sink, double seed, int iters) {
+    double x[8], m = 1.0 + seed * 1e-9, c = seed * 1e-7;
+    for (int i = 0; i < 8; ++i) x[i] = threadIdx.x + i;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __fma_rz(x[i], m, c);
+        }
+    }
+    double s = 0;
+    for (int i = 0; i < 8; ++i) s += x[i];
+    if (s == 1.2345) sink[0] = s;
+}
+
 template <typename F>
 static float timeit(F f) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -137,6 +153,8 @@ int main() {
     printf("D3 lo + hi separate   : %.3f ms  %.2f T (lo+hi pairs)/s\n", ms, T * it2 * 64 / ms / 1e9);
     ms = timeit([&] { probeD<4><<<blocks, threads>>>(sink, 12345, it2); });
     printf("D4 wide mul + add64   : %.3f ms  %.2f T wide/s\n", ms, T * it2 * 64 / ms / 1e9);
+    ms = timeit([&] { probeF<<<blocks, threads>>>((double *)sink, 3.0, it2); });
+    printf("F  DFMA chains        : %.3f ms  %.2f T dfma/s\n", ms, T * it2 * 64 / ms / 1e9);
     printf("err=%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
