@@ -311,8 +311,12 @@ def run_b200(args):
         shares_per_step = 2 * B * N_PARTIES
         value = n_gpus * args.steps * shares_per_step / t_tot
         gen_launch_s = t_gen / args.steps
-        alg_imad = B * ALG_MODMUL_GEN * IMAD_PER_MODMUL
-        achieved = alg_imad / gen_launch_s
+        rec_launch_s = t_rec / args.steps
+        hbm = measured_hbm()
+        # dominant kernel of the step: matvec_kernel (the recon launch: 43 check/coefficient rows x 22 terms per chunk)
+        rec_alg_imad = B * ALG_MODMUL_REC * IMAD_PER_MODMUL
+        rec_exec_wide = B * ((T_FAULTS + M) * M + (T_FAULTS + M)) * 64  # IMAD.WIDE issued: 64 per term + 64 per reduction
+        gen_alg_imad = B * ALG_MODMUL_GEN * IMAD_PER_MODMUL
         line = {
             "metric": "Fr shares generated+reconstructed per second (n=64,t=21)", "value": value, "unit": "shares/s",
             "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
@@ -321,12 +325,18 @@ def run_b200(args):
             "breakdown": {"gen_ms": 1e3 * t_gen / args.steps, "recon_ms": 1e3 * t_rec / args.steps,
                           "gen_shares_per_s": n_gpus * args.steps * B * N_PARTIES / t_gen, "recon_shares_per_s": n_gpus * args.steps * B * N_PARTIES / t_rec,
                           "alg_modmul_per_s": n_gpus * args.steps * B * (ALG_MODMUL_GEN + ALG_MODMUL_REC) / t_tot, "gather_ms": gather_ms},
-            "roofline": {"kernel": "matvec_kernel (K1 share generation launch, 64x22 matrix)", "bound": "int32-imad", "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
-                         "unit": "TIMAD/s", "frac": achieved / imad_peak,
-                         "how": "algorithmic IMAD = B * 1344 modmul * 256 IMAD (SURVEY 8d) / CUDA-event launch time; peak = mad.lo.u32 probe kernel measured in this run",
-                         "imad_wide_peak_tinst": imad_wide_peak / 1e12, "traffic": None},
-            "roofline_hbm": {"bound": "hbm", "achieved": B * BYTES_GEN / gen_launch_s / 1e9, "peak": measured_hbm(), "unit": "GB/s",
-                             "frac": B * BYTES_GEN / gen_launch_s / 1e9 / measured_hbm(), "traffic": None},
+            "roofline": {"kernel": "matvec_kernel<4> (K3 batch_recover launch: 43x22 check+coefficient matrix per chunk)", "bound": "int32-imad",
+                         "achieved": rec_alg_imad / rec_launch_s / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
+                         "frac": rec_alg_imad / rec_launch_s / imad_peak,
+                         "how": "algorithmic IMAD = B * 1430 modmul * 256 IMAD (SURVEY 8d) / CUDA-event launch time; peak = mad.lo.u32 probe measured in this run on this GPU",
+                         "executed_wide_tinst": rec_exec_wide / rec_launch_s / 1e12, "imad_wide_peak_tinst": imad_wide_peak / 1e12,
+                         "executed_frac_of_imad_wide_peak": rec_exec_wide / rec_launch_s / imad_wide_peak,
+                         "hbm_gbs": B * BYTES_REC / rec_launch_s / 1e9, "hbm_frac": B * BYTES_REC / rec_launch_s / 1e9 / hbm, "traffic": None},
+            "roofline_gen": {"kernel": "ntt_kernel<6> (K1 compute_shares launch: zero-padded 64-point NTT per secret)", "bound": "int32-imad",
+                             "achieved": gen_alg_imad / gen_launch_s / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
+                             "frac": gen_alg_imad / gen_launch_s / imad_peak,
+                             "how": "algorithmic IMAD = B * 1344 modmul * 256 IMAD (dense Horner count of SURVEY 8d; the NTT executes ~130 modmul per secret)",
+                             "hbm_gbs": B * BYTES_GEN / gen_launch_s / 1e9, "hbm_frac": B * BYTES_GEN / gen_launch_s / 1e9 / hbm, "traffic": None},
             "cpu_baseline": cpu,
             "e2e": {"value": n_gpus * e2e_steps * 2 * Be * N_PARTIES / t_e2e, "unit": "shares/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps, "host_buffers": "pinned"},

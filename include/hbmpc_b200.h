@@ -11,8 +11,9 @@
  *   - return value = `ShareErrorCode` numbering (0 success ... 8 DecodingError) for whole-call failures;
  *     per-item outcomes are reported in `path[]`;
  *   - every data pointer may be a host pointer or a device pointer (detected with cudaPointerGetAttributes).
- *     Host buffers are copied to/from the device inside the call (which then returns after the results are in
- *     the caller's buffer); device buffers are processed asynchronously on the context's stream;
+ *     Calls with a host buffer are pipelined in chunks over internal streams (host->device copy, kernels and
+ *     device->host copy of neighbouring chunks overlap; use pinned memory for full PCIe speed) and return after the
+ *     results are in the caller's buffers; calls with device buffers only run on the context's stream;
  *   - outputs are CALLER-allocated (the reference leaks Vecs to C and frees them through free_* helpers);
  *   - no hidden RNG: share generation takes the polynomial coefficients, so results are reproducible;
  *   - there is no CPU fallback: every call fails with HBMPC_NO_DEVICE if no CUDA device is usable.
@@ -106,9 +107,9 @@ int hbmpc_robust_interpolate_batch(hbmpc_ctx *ctx, size_t n, size_t d, size_t t,
  * multiplication.rs:79-97,417-426): out[i] = a[i] (op) b[i], op: 0 add, 1 sub, 2 mul (share_mul / Mul<F>). */
 int hbmpc_elementwise(hbmpc_ctx *ctx, int op, size_t count, const uint64_t *a, const uint64_t *b, uint64_t *out);
 
-/* Integer-pipe roofline probe: runs an independent-chain multiply-add microkernel on every SM and returns the
- * sustained rate in 1e9 thread-level instructions per second.  variant: 0 = mad.lo.u32 (IMAD), 1 = mad.wide.u32
- * (IMAD.WIDE.U32), 2 = the carry-chained IMAD.WIDE.U32.X pattern of the product kernels. */
+/* Integer-pipe roofline probe: runs a register-only dependent-chain microkernel on every SM and returns the sustained
+ * rate in 1e9 thread-level instructions per second.  variant: 0 = mad.lo.u32 (IMAD, the north star's "IMAD peak"),
+ * 1 = IMAD.WIDE.U32(.X) carry chains (the 32x32->64 multiply-add the product kernels issue), 2 = DFMA (FP64 pipe). */
 int hbmpc_measure_imad_peak(hbmpc_ctx *ctx, int variant, double *giga_inst_per_s, double *elapsed_ms);
 
 #ifdef __cplusplus

@@ -54,12 +54,14 @@ __global__ void gather_first_kernel(long long B, long long stride, const uint4 *
     }
 }
 
-// Integer-pipe roofline probes: CHAINS independent dependent-chains per thread, fully unrolled.
+// Integer-pipe roofline probes (register-only, multiplicands depend on the running values so nothing is hoisted):
+//   0: mad.lo.u32 (IMAD)            -- the "IMAD peak" of the north star: 64 lanes/clk/SM
+//   1: IMAD.WIDE.U32(.X) 4-lane carry chains, the product kernels' instruction (32x32->64 multiply-add)
+//   2: DFMA chains (FP64 pipe, for reference)
 template <int VARIANT>
 __global__ void __launch_bounds__(256) imad_probe_kernel(unsigned int *sink, unsigned int seed, int iters) {
-    unsigned int m0 = seed | 1u, m1 = (seed * 2654435761u) | 1u, m2 = m0 ^ 0x9e3779b9u, m3 = m1 + 0x7f4a7c15u;
     if (VARIANT == 0) {
-        unsigned int x[16];
+        unsigned int x[16], m1 = (seed * 2654435761u) | 1u;
 #pragma unroll
         for (int i = 0; i < 16; ++i) x[i] = threadIdx.x + i;
 #pragma unroll 1
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(unsigned int *sink, uns
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(m0), "r"(m1));
+                for (int i = 0; i < 16; ++i) asm volatile("mad.lo.u32 %0, %0, %0, %1;" : "+r"(x[i]) : "r"(m1));
             }
         }
         unsigned int s = 0;
@@ -75,7 +77,24 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(unsigned int *sink, uns
         for (int i = 0; i < 16; ++i) s ^= x[i];
         if (s == 0x12345u) sink[0] = s;
     } else if (VARIANT == 1) {
-        unsigned long long x[8];
+        unsigned long long l[8];
+        unsigned int k = 0, m1 = seed * 77u + 5u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) l[i] = (unsigned long long)(threadIdx.x * 2654435761u + i) << 7;
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                chain4w(l[0], l[1], l[2], l[3], k, (unsigned int)l[4], (unsigned int)l[5], (unsigned int)l[6], (unsigned int)l[7], m1 + u);
+                chain4w(l[4], l[5], l[6], l[7], k, (unsigned int)l[0], (unsigned int)l[1], (unsigned int)l[2], (unsigned int)l[3], m1 - u);
+            }
+        }
+        unsigned long long s = k;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s ^= l[i];
+        if (s == 0x12345ull) sink[0] = (unsigned int)s;
+    } else {
+        double x[8], m = 1.0 + seed * 1e-9, c = seed * 1e-7;
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = threadIdx.x + i;
 #pragma unroll 1
@@ -83,32 +102,13 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(unsigned int *sink, uns
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x[i]) : "r"(m0 + i), "r"(m1));
+                for (int i = 0; i < 8; ++i) x[i] = __fma_rz(x[i], m, c);
             }
         }
-        unsigned long long s = 0;
+        double s = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s ^= x[i];
-        if (s == 0x12345ull) sink[0] = (unsigned int)s;
-    } else {
-        // the product kernels' pattern: 4-lane carry chains (IMAD.WIDE.U32.X) + a carry counter on the ALU pipe
-        unsigned int e[16], k[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < 16; ++i) e[i] = threadIdx.x + i;
-#pragma unroll 1
-        for (int it = 0; it < iters; ++it) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                chain4(e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], k[0], m0, m1, m2, m3, m0 + u);
-                chain4(e[8], e[9], e[10], e[11], e[12], e[13], e[14], e[15], k[1], m1, m2, m3, m0, m1 + u);
-                chain4(e[2], e[3], e[4], e[5], e[6], e[7], e[8], e[9], k[2], m2, m3, m0, m1, m2 + u);
-                chain4(e[10], e[11], e[12], e[13], e[14], e[15], e[0], e[1], k[3], m3, m0, m1, m2, m3 + u);
-            }
-        }
-        unsigned int s = k[0] ^ k[1] ^ k[2] ^ k[3];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) s ^= e[i];
-        if (s == 0x12345u) sink[0] = s;
+        for (int i = 0; i < 8; ++i) s += x[i];
+        if (s == 1.2345) sink[0] = 1u;
     }
 }
 
@@ -119,6 +119,14 @@ struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
 };
+
+// A lane = a stream with its own scratch.  Lane 0 is the context's (user-visible) stream and serves calls whose buffers
+// are all device pointers; lanes 1..3 pipeline calls with host buffers chunk by chunk (H2D | kernels | D2H overlap).
+struct Lane {
+    cudaStream_t stream = nullptr;
+    DevBuf scratch[10];
+};
+static const int NLANES = 4;
 
 struct RecoverTables {
     // optimistic matvec
@@ -134,22 +142,23 @@ struct RecoverTables {
 
 struct hbmpc_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    Lane lanes[NLANES];
     bool own_stream = true;
     bool async = false;
     uint64_t launches = 0;
     std::string err;
     int num_sms = 148;
-    int matvec_regs[3] = {0, 0, 0};
+    int matvec_regs = 0;
     int ntt_ctas[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // resident CTAs per SM of ntt_kernel<LOGN>
     bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
-    unsigned int *d_status = nullptr;  // [0] non-canonical input seen, [1] first failing item, [2] failing-item count
+    size_t chunk_bytes = 24u << 20;                 // HBMPC_CHUNK_MB: target bytes per pipelined host copy
+    unsigned int *d_status = nullptr;  // [0] non-canonical input seen, [2] some item failed to decode
     unsigned int *h_status = nullptr;  // pinned
-    int sticky = 0;
-    std::map<std::string, uint4 *> matrices;          // Vandermonde matrices keyed by "V n cols"
+    cudaEvent_t ev_main = nullptr;
+    std::map<std::string, uint4 *> matrices;          // Vandermonde / twiddle tables keyed by "V n cols" / "W N"
     std::map<std::string, RecoverTables> recover;     // keyed by (n, d, t, ids, variant)
     std::vector<void *> owned;                        // device allocations freed at destroy
-    DevBuf scratch[8];
+    cudaStream_t main_stream() const { return lanes[0].stream; }
 };
 
 #define CK(call)                                                                                     \
@@ -171,11 +180,11 @@ static bool is_device_ptr(const void *p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-static int scratch_get(hbmpc_ctx *ctx, int slot, size_t bytes, void **out) {
-    DevBuf &b = ctx->scratch[slot];
+static int scratch_get(hbmpc_ctx *ctx, Lane &ln, int slot, size_t bytes, void **out) {
+    DevBuf &b = ln.scratch[slot];
     if (b.cap < bytes) {
         if (b.p) {
-            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaStreamSynchronize(ln.stream));
             CK(cudaFree(b.p));
             b.p = nullptr;
             b.cap = 0;
@@ -194,8 +203,7 @@ static int upload(hbmpc_ctx *ctx, const std::vector<T> &v, T **out) {
     size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
     CK(cudaMalloc(&p, bytes));
     ctx->owned.push_back(p);
-    if (!v.empty()) CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));  // v may be a temporary
+    if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     *out = (T *)p;
     return 0;
 }
@@ -218,32 +226,36 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
         return HBMPC_NO_DEVICE;
     }
     if (cudaSetDevice(device) != cudaSuccess) return HBMPC_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return HBMPC_NO_DEVICE;  // sm_100a only
     hbmpc_ctx *ctx = new hbmpc_ctx();
     ctx->device = device;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
-        delete ctx;
-        return HBMPC_NO_DEVICE;  // sm_100a only
-    }
     ctx->num_sms = prop.multiProcessorCount;
     {
         const char *fd = getenv("HBMPC_FORCE_DENSE");
         ctx->force_dense = fd && fd[0] == '1';
+        const char *cm = getenv("HBMPC_CHUNK_MB");
+        if (cm && atoi(cm) > 0) ctx->chunk_bytes = (size_t)atoi(cm) << 20;
     }
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc((void **)&ctx->d_status, 16) != cudaSuccess || cudaMallocHost((void **)&ctx->h_status, 16) != cudaSuccess) {
-        delete ctx;
-        return HBMPC_NO_DEVICE;
+    bool ok = true;
+    for (int i = 0; i < NLANES && ok; ++i) ok = cudaStreamCreateWithFlags(&ctx->lanes[i].stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&ctx->d_status, 16) == cudaSuccess && cudaMallocHost((void **)&ctx->h_status, 16) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) {
+        cudaMemsetAsync(ctx->d_status, 0, 16, ctx->main_stream());
+        cudaFuncAttributes fa;
+        int regs = 0;
+        if (cudaFuncGetAttributes(&fa, matvec_kernel<1>) == cudaSuccess) regs = std::max(regs, fa.numRegs);
+        if (cudaFuncGetAttributes(&fa, matvec_kernel<2>) == cudaSuccess) regs = std::max(regs, fa.numRegs);
+        if (cudaFuncGetAttributes(&fa, matvec_kernel<4>) == cudaSuccess) regs = std::max(regs, fa.numRegs);
+        ctx->matvec_regs = regs;
+        cudaFuncSetAttribute(matvec_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(matvec_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(matvec_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        ok = cudaGetLastError() == cudaSuccess && regs > 0;  // regs == 0: no sm_100a image for this device
     }
-    cudaMemsetAsync(ctx->d_status, 0, 16, ctx->stream);
-    cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, matvec_kernel<1>) == cudaSuccess) ctx->matvec_regs[0] = fa.numRegs;
-    if (cudaFuncGetAttributes(&fa, matvec_kernel<2>) == cudaSuccess) ctx->matvec_regs[1] = fa.numRegs;
-    if (cudaFuncGetAttributes(&fa, matvec_kernel<4>) == cudaSuccess) ctx->matvec_regs[2] = fa.numRegs;
-    cudaFuncSetAttribute(matvec_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(matvec_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(matvec_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (cudaGetLastError() != cudaSuccess) {
+    if (!ok) {
+        cudaGetLastError();
         delete ctx;
         return HBMPC_NO_DEVICE;
     }
@@ -254,22 +266,26 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
 extern "C" void hbmpc_ctx_destroy(hbmpc_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    for (auto &ln : ctx->lanes)
+        if (ln.stream) cudaStreamSynchronize(ln.stream);
     for (void *p : ctx->owned) cudaFree(p);
-    for (auto &b : ctx->scratch)
-        if (b.p) cudaFree(b.p);
+    for (auto &ln : ctx->lanes)
+        for (auto &b : ln.scratch)
+            if (b.p) cudaFree(b.p);
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
-    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
+    for (int i = 0; i < NLANES; ++i)
+        if (ctx->lanes[i].stream && (i > 0 || ctx->own_stream)) cudaStreamDestroy(ctx->lanes[i].stream);
     delete ctx;
 }
 
 extern "C" int hbmpc_ctx_set_stream(hbmpc_ctx *ctx, void *cuda_stream) {
     if (!ctx) return HBMPC_INVALID_INPUT;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
-    ctx->stream = (cudaStream_t)cuda_stream;
+    cudaStreamSynchronize(ctx->main_stream());
+    if (ctx->own_stream && ctx->main_stream()) cudaStreamDestroy(ctx->main_stream());
+    ctx->lanes[0].stream = (cudaStream_t)cuda_stream;
     ctx->own_stream = false;
     return HBMPC_SUCCESS;
 }
@@ -280,16 +296,15 @@ extern "C" int hbmpc_ctx_set_async(hbmpc_ctx *ctx, int async) {
     return HBMPC_SUCCESS;
 }
 
-// reads the device status words, folds them into a ShareErrorCode and clears them
+// reads the device status words, folds them into a ShareErrorCode and clears them (all lanes must be quiescent or
+// ordered before the main stream)
 static int collect_status(hbmpc_ctx *ctx) {
-    CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_status, 0, 16, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    int rc = ctx->sticky;
-    ctx->sticky = 0;
-    if (ctx->h_status[0]) rc = HBMPC_INVALID_INPUT;
-    else if (!rc && ctx->h_status[2]) rc = HBMPC_DECODING_ERROR;
-    return rc;
+    CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, 16, cudaMemcpyDeviceToHost, ctx->main_stream()));
+    CK(cudaMemsetAsync(ctx->d_status, 0, 16, ctx->main_stream()));
+    CK(cudaStreamSynchronize(ctx->main_stream()));
+    if (ctx->h_status[0]) return HBMPC_INVALID_INPUT;
+    if (ctx->h_status[2]) return HBMPC_DECODING_ERROR;
+    return HBMPC_SUCCESS;
 }
 
 extern "C" int hbmpc_ctx_synchronize(hbmpc_ctx *ctx) {
@@ -301,54 +316,100 @@ extern "C" int hbmpc_ctx_synchronize(hbmpc_ctx *ctx) {
 extern "C" uint64_t hbmpc_ctx_launch_count(const hbmpc_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" const char *hbmpc_last_error(const hbmpc_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-// finish a call: in synchronous mode wait and report the device-side status
-static int finish(hbmpc_ctx *ctx) {
-    if (ctx->async) return HBMPC_SUCCESS;
+// ------------------------------------------------------------------------------------------------ batch buffers and chunking
+// A batch buffer holds J records of `esz` bytes per item; record (b, j) lives at base + (b*sb + j*sj)*esz.
+// item-major: sb = J, sj = 1 (coeffs[B][d+1], shares[B][n]);  record-major: sb = 1, sj = B (evals[S][B], out[n][B]).
+struct BatchBuf {
+    void *user = nullptr;
+    bool host = false, present = false, record_major = false;
+    long long J = 0;
+    size_t esz = 32;
+    size_t B = 0;
+};
+static BatchBuf make_buf(const void *p, size_t B, long long J, bool record_major, size_t esz = 32) {
+    BatchBuf b;
+    b.user = const_cast<void *>(p);
+    b.present = p != nullptr;
+    b.host = b.present && !is_device_ptr(p);
+    b.J = J;
+    b.record_major = record_major;
+    b.esz = esz;
+    b.B = B;
+    return b;
+}
+// device view of the chunk [b0, b0+Bc)
+struct ChunkView {
+    void *dev = nullptr;
+    long long sb = 0, sj = 0;
+};
+static int chunk_prepare(hbmpc_ctx *ctx, Lane &ln, int slot, const BatchBuf &bb, size_t b0, size_t Bc, bool copy_in, ChunkView &v) {
+    if (!bb.present) return 0;
+    if (!bb.host) {
+        v.sb = bb.record_major ? 1 : bb.J;
+        v.sj = bb.record_major ? (long long)bb.B : 1;
+        v.dev = (char *)bb.user + (size_t)b0 * (size_t)v.sb * bb.esz;
+        return 0;
+    }
+    int rc = scratch_get(ctx, ln, slot, Bc * (size_t)bb.J * bb.esz, &v.dev);
+    if (rc) return rc;
+    if (bb.record_major) {
+        v.sb = 1;
+        v.sj = (long long)Bc;
+        if (copy_in)
+            CK(cudaMemcpy2DAsync(v.dev, Bc * bb.esz, (char *)bb.user + b0 * bb.esz, bb.B * bb.esz, Bc * bb.esz, (size_t)bb.J, cudaMemcpyHostToDevice, ln.stream));
+    } else {
+        v.sb = bb.J;
+        v.sj = 1;
+        if (copy_in)
+            CK(cudaMemcpyAsync(v.dev, (char *)bb.user + b0 * (size_t)bb.J * bb.esz, Bc * (size_t)bb.J * bb.esz, cudaMemcpyHostToDevice, ln.stream));
+    }
+    return 0;
+}
+static int chunk_commit(hbmpc_ctx *ctx, Lane &ln, const BatchBuf &bb, size_t b0, size_t Bc, const ChunkView &v) {
+    if (!bb.present || !bb.host) return 0;
+    if (bb.record_major)
+        CK(cudaMemcpy2DAsync((char *)bb.user + b0 * bb.esz, bb.B * bb.esz, v.dev, Bc * bb.esz, Bc * bb.esz, (size_t)bb.J, cudaMemcpyDeviceToHost, ln.stream));
+    else
+        CK(cudaMemcpyAsync((char *)bb.user + b0 * (size_t)bb.J * bb.esz, v.dev, Bc * (size_t)bb.J * bb.esz, cudaMemcpyDeviceToHost, ln.stream));
+    return 0;
+}
+
+// Runs `body(lane, b0, Bc)` over the batch: one pass on lane 0 when every buffer is a device pointer, otherwise chunk by
+// chunk round-robin over lanes 1..3 so that host->device copies, kernels and device->host copies of neighbouring chunks
+// overlap.  Returns after the host buffers are complete (or, all-device in async mode, after enqueueing).
+template <typename Body>
+static int run_batched(hbmpc_ctx *ctx, size_t B, bool any_host, size_t max_item_bytes, Body body) {
+    if (!any_host) {
+        int rc = body(ctx->lanes[0], (size_t)0, B);
+        if (rc) return rc;
+        return ctx->async ? HBMPC_SUCCESS : collect_status(ctx);
+    }
+    size_t Bc = ctx->chunk_bytes / std::max<size_t>(max_item_bytes, 32);
+    Bc = std::max<size_t>(Bc & ~(size_t)255, 1024);
+    if (Bc >= B || B <= 4096) Bc = B;
+    CK(cudaEventRecord(ctx->ev_main, ctx->main_stream()));
+    for (int i = 1; i < NLANES; ++i) CK(cudaStreamWaitEvent(ctx->lanes[i].stream, ctx->ev_main, 0));
+    int li = 0, rc = 0;
+    for (size_t b0 = 0; b0 < B && !rc; b0 += Bc) {
+        Lane &ln = ctx->lanes[1 + li];
+        li = (li + 1) % (NLANES - 1);
+        rc = body(ln, b0, std::min(Bc, B - b0));
+    }
+    for (int i = 1; i < NLANES; ++i) {
+        cudaError_t e = cudaStreamSynchronize(ctx->lanes[i].stream);
+        if (e != cudaSuccess && !rc) {
+            ctx->err = std::string("pipeline lane: ") + cudaGetErrorString(e);
+            rc = HBMPC_CUDA_ERROR;
+        }
+    }
+    if (rc) return rc;
     return collect_status(ctx);
 }
 
-// ------------------------------------------------------------------------------------------------ staging of host buffers
-struct Staged {
-    const void *user = nullptr;
-    void *dev = nullptr;
-    size_t bytes = 0;
-    bool host = false;
-};
-static int stage_in(hbmpc_ctx *ctx, int slot, const void *p, size_t bytes, Staged &s) {
-    s.user = p;
-    s.bytes = bytes;
-    s.host = !is_device_ptr(p);
-    if (!s.host) {
-        s.dev = const_cast<void *>(p);
-        return 0;
-    }
-    int rc = scratch_get(ctx, slot, bytes, &s.dev);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(s.dev, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    return 0;
-}
-static int stage_out(hbmpc_ctx *ctx, int slot, void *p, size_t bytes, Staged &s) {
-    s.user = p;
-    s.bytes = bytes;
-    s.host = !is_device_ptr(p);
-    if (!s.host) {
-        s.dev = p;
-        return 0;
-    }
-    return scratch_get(ctx, slot, bytes, &s.dev);
-}
-static int unstage_out(hbmpc_ctx *ctx, Staged &s, bool &need_sync) {
-    if (!s.host) return 0;
-    CK(cudaMemcpyAsync(const_cast<void *>(s.user), s.dev, s.bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    need_sync = true;
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------ matvec launch
-static int launch_matvec(hbmpc_ctx *ctx, MatvecArgs a, int flag_words) {
+// ------------------------------------------------------------------------------------------------ kernel launches
+static int launch_matvec(hbmpc_ctx *ctx, cudaStream_t st, MatvecArgs a, int flag_words) {
     if (a.B == 0) return 0;
-    int regs = ctx->matvec_regs[2] > 0 ? std::max(ctx->matvec_regs[0], std::max(ctx->matvec_regs[1], ctx->matvec_regs[2])) : 96;
-    MatvecPlan p = matvec_plan(a.R, a.C, flag_words, regs);
+    MatvecPlan p = matvec_plan(a.R, a.C, flag_words, ctx->matvec_regs > 0 ? ctx->matvec_regs : 112);
     if (p.tbt == 0) {
         ctx->err = "matvec: no launch shape fits shared memory";
         return HBMPC_INVALID_INPUT;
@@ -363,19 +424,17 @@ static int launch_matvec(hbmpc_ctx *ctx, MatvecArgs a, int flag_words) {
     if (gx > ntiles) gx = ntiles;
     dim3 grid((unsigned)gx, (unsigned)p.slices), block(p.warps * 32);
     switch (p.tbt) {
-        case 1: matvec_kernel<1><<<grid, block, p.smem, ctx->stream>>>(a); break;
-        case 2: matvec_kernel<2><<<grid, block, p.smem, ctx->stream>>>(a); break;
-        default: matvec_kernel<4><<<grid, block, p.smem, ctx->stream>>>(a); break;
+        case 1: matvec_kernel<1><<<grid, block, p.smem, st>>>(a); break;
+        case 2: matvec_kernel<2><<<grid, block, p.smem, st>>>(a); break;
+        default: matvec_kernel<4><<<grid, block, p.smem, st>>>(a); break;
     }
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 
-
-// ------------------------------------------------------------------------------------------------ NTT launch (K1/K2 on the domain)
 template <int LOGN>
-static int launch_ntt_t(hbmpc_ctx *ctx, const NttArgs &a) {
+static int launch_ntt_t(hbmpc_ctx *ctx, cudaStream_t st, const NttArgs &a) {
     const size_t smem = ntt_smem_bytes<LOGN>();
     if (ctx->ntt_ctas[LOGN] == 0) {
         CK(cudaFuncSetAttribute(ntt_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -386,25 +445,26 @@ static int launch_ntt_t(hbmpc_ctx *ctx, const NttArgs &a) {
     const int ipc = ntt_items_per_cta<LOGN>();
     long long ntiles = (a.B + ipc - 1) / ipc;
     long long grid = std::min<long long>(ntiles, (long long)ctx->num_sms * ctx->ntt_ctas[LOGN]);
-    ntt_kernel<LOGN><<<(unsigned)grid, 256, smem, ctx->stream>>>(a);
+    ntt_kernel<LOGN><<<(unsigned)grid, 256, smem, st>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
-static int launch_ntt(hbmpc_ctx *ctx, int logn, const NttArgs &a) {
+static int launch_ntt(hbmpc_ctx *ctx, cudaStream_t st, int logn, const NttArgs &a) {
     switch (logn) {
-        case 1: return launch_ntt_t<1>(ctx, a);
-        case 2: return launch_ntt_t<2>(ctx, a);
-        case 3: return launch_ntt_t<3>(ctx, a);
-        case 4: return launch_ntt_t<4>(ctx, a);
-        case 5: return launch_ntt_t<5>(ctx, a);
-        case 6: return launch_ntt_t<6>(ctx, a);
-        case 7: return launch_ntt_t<7>(ctx, a);
-        case 8: return launch_ntt_t<8>(ctx, a);
+        case 1: return launch_ntt_t<1>(ctx, st, a);
+        case 2: return launch_ntt_t<2>(ctx, st, a);
+        case 3: return launch_ntt_t<3>(ctx, st, a);
+        case 4: return launch_ntt_t<4>(ctx, st, a);
+        case 5: return launch_ntt_t<5>(ctx, st, a);
+        case 6: return launch_ntt_t<6>(ctx, st, a);
+        case 7: return launch_ntt_t<7>(ctx, st, a);
+        case 8: return launch_ntt_t<8>(ctx, st, a);
     }
     ctx->err = "ntt: unsupported domain size";
     return HBMPC_NO_SUITABLE_DOMAIN;
 }
+
 
 static int get_twiddles(hbmpc_ctx *ctx, int N, uint4 **out) {
     char key[64];
@@ -422,9 +482,6 @@ static int get_twiddles(hbmpc_ctx *ctx, int N, uint4 **out) {
     *out = d;
     return 0;
 }
-
-// out[b][j] = sum_k w_N^(jk) in[b][k]: NTT when the zero-padded input fits the domain, dense matvec otherwise
-static int apply_domain_dev(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out, int recipient_major);
 
 static int get_vandermonde(hbmpc_ctx *ctx, size_t n, size_t cols, uint4 **out) {
     char key[64];
@@ -444,35 +501,46 @@ static int get_vandermonde(hbmpc_ctx *ctx, size_t n, size_t cols, uint4 **out) {
     return 0;
 }
 
-static int apply_matrix_dev(hbmpc_ctx *ctx, const uint4 *M, size_t rows, size_t cols, size_t B, const uint64_t *in, uint64_t *out,
-                            int recipient_major) {
-    Staged si, so;
-    int rc = stage_in(ctx, 0, in, B * cols * 32, si);
-    if (rc) return rc;
-    rc = stage_out(ctx, 1, out, B * rows * 32, so);
-    if (rc) return rc;
-    MatvecArgs a{};
-    a.M = M;
-    a.in = (const uint4 *)si.dev;
-    a.out = (uint4 *)so.dev;
-    a.R = (int)rows;
-    a.C = (int)cols;
-    a.B = (long long)B;
-    a.in_sb = (long long)cols;
-    a.in_sc = 1;
-    a.in_chunk_major = 1;
-    if (recipient_major) { a.out_sb = 1; a.out_sr = (long long)B; }
-    else { a.out_sb = (long long)rows; a.out_sr = 1; }
-    rc = launch_matvec(ctx, a, 0);
-    if (rc) return rc;
-    bool ns = false;
-    rc = unstage_out(ctx, so, ns);
-    if (rc) return rc;
-    if (ns && ctx->async) CK(cudaStreamSynchronize(ctx->stream));
-    return finish(ctx);
+// ------------------------------------------------------------------------------------------------ K1 / K2
+// out[b][r] = sum_c M[r][c] in[b][c]: M == nullptr selects the domain transform (NTT) with `n` outputs
+static int apply_map(hbmpc_ctx *ctx, const uint4 *M, const uint4 *tw, int logn, size_t rows, size_t cols, size_t B, const uint64_t *in,
+                     uint64_t *out, int recipient_major) {
+    BatchBuf bi = make_buf(in, B, (long long)cols, false), bo = make_buf(out, B, (long long)rows, recipient_major != 0);
+    auto body = [&](Lane &ln, size_t b0, size_t Bc) -> int {
+        ChunkView vi, vo;
+        int rc;
+        if ((rc = chunk_prepare(ctx, ln, 0, bi, b0, Bc, true, vi))) return rc;
+        if ((rc = chunk_prepare(ctx, ln, 1, bo, b0, Bc, false, vo))) return rc;
+        if (M) {
+            MatvecArgs a{};
+            a.M = M;
+            a.in = (const uint4 *)vi.dev;
+            a.out = (uint4 *)vo.dev;
+            a.R = (int)rows;
+            a.C = (int)cols;
+            a.B = (long long)Bc;
+            a.in_sb = vi.sb; a.in_sc = vi.sj; a.in_chunk_major = 1;
+            a.out_sb = vo.sb; a.out_sr = vo.sj;
+            if ((rc = launch_matvec(ctx, ln.stream, a, 0))) return rc;
+        } else {
+            NttArgs a{};
+            a.in = (const uint4 *)vi.dev;
+            a.out = (uint4 *)vo.dev;
+            a.tw = tw;
+            a.B = (long long)Bc;
+            a.in_sb = vi.sb; a.in_sc = vi.sj;
+            a.out_sb = vo.sb; a.out_sr = vo.sj;
+            a.cols = (int)cols;
+            a.n = (int)rows;
+            a.err = ctx->d_status;
+            if ((rc = launch_ntt(ctx, ln.stream, logn, a))) return rc;
+        }
+        return chunk_commit(ctx, ln, bo, b0, Bc, vo);
+    };
+    return run_batched(ctx, B, bi.host || bo.host, std::max(rows, cols) * 32, body);
 }
 
-static int apply_domain_dev(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out, int recipient_major) {
+static int apply_domain(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out, int recipient_major) {
     const int N = domain_size(n);
     int logn = 0;
     while ((1 << logn) < N) ++logn;
@@ -480,41 +548,22 @@ static int apply_domain_dev(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, con
         uint4 *V = nullptr;
         int rc = get_vandermonde(ctx, n, cols, &V);
         if (rc) return rc;
-        return apply_matrix_dev(ctx, V, n, cols, B, in, out, recipient_major);
+        return apply_map(ctx, V, nullptr, 0, n, cols, B, in, out, recipient_major);
     }
     uint4 *tw = nullptr;
     int rc = get_twiddles(ctx, N, &tw);
     if (rc) return rc;
-    Staged si, so;
-    if ((rc = stage_in(ctx, 0, in, B * cols * 32, si))) return rc;
-    if ((rc = stage_out(ctx, 1, out, B * n * 32, so))) return rc;
-    NttArgs a{};
-    a.in = (const uint4 *)si.dev;
-    a.out = (uint4 *)so.dev;
-    a.tw = tw;
-    a.B = (long long)B;
-    a.in_sb = (long long)cols;
-    a.in_sc = 1;
-    if (recipient_major) { a.out_sb = 1; a.out_sr = (long long)B; }
-    else { a.out_sb = (long long)n; a.out_sr = 1; }
-    a.cols = (int)cols;
-    a.n = (int)n;
-    a.err = ctx->d_status;
-    if ((rc = launch_ntt(ctx, logn, a))) return rc;
-    bool ns = false;
-    if ((rc = unstage_out(ctx, so, ns))) return rc;
-    if (ns && ctx->async) CK(cudaStreamSynchronize(ctx->stream));
-    return finish(ctx);
+    return apply_map(ctx, nullptr, tw, logn, n, cols, B, in, out, recipient_major);
 }
 
 extern "C" int hbmpc_compute_shares_batch(hbmpc_ctx *ctx, size_t n, size_t d, size_t B, const uint64_t *coeffs, uint64_t *shares) {
     if (!ctx) return HBMPC_INVALID_INPUT;
-    if (n <= d) return HBMPC_INVALID_INPUT;          // robust_interpolate.rs:59-64
-    if (!domain_size(n)) return HBMPC_NO_SUITABLE_DOMAIN;  // :65-66
+    if (n <= d) return HBMPC_INVALID_INPUT;                 // robust_interpolate.rs:59-64
+    if (!domain_size(n)) return HBMPC_NO_SUITABLE_DOMAIN;   // :65-66
     if (B == 0) return HBMPC_SUCCESS;
     if (!coeffs || !shares) return HBMPC_INVALID_INPUT;
     cudaSetDevice(ctx->device);
-    return apply_domain_dev(ctx, n, d + 1, B, coeffs, shares, 0);
+    return apply_domain(ctx, n, d + 1, B, coeffs, shares, 0);
 }
 
 extern "C" int hbmpc_apply_vandermonde_batch(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out,
@@ -525,7 +574,7 @@ extern "C" int hbmpc_apply_vandermonde_batch(hbmpc_ctx *ctx, size_t n, size_t co
     if (B == 0) return HBMPC_SUCCESS;
     if (!in || !out) return HBMPC_INVALID_INPUT;
     cudaSetDevice(ctx->device);
-    return apply_domain_dev(ctx, n, cols, B, in, out, recipient_major);
+    return apply_domain(ctx, n, cols, B, in, out, recipient_major);
 }
 
 extern "C" int hbmpc_apply_matrix_batch(hbmpc_ctx *ctx, size_t rows, size_t cols, const uint64_t *matrix, size_t B, const uint64_t *in,
@@ -543,11 +592,11 @@ extern "C" int hbmpc_apply_matrix_batch(hbmpc_ctx *ctx, size_t rows, size_t cols
     std::vector<uint32_t> w;
     to_u32(M, w);
     void *dM = nullptr;
-    int rc = scratch_get(ctx, 2, w.size() * 4, &dM);
+    int rc = scratch_get(ctx, ctx->lanes[0], 9, w.size() * 4, &dM);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(dM, w.data(), w.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return apply_matrix_dev(ctx, (const uint4 *)dM, rows, cols, B, in, out, recipient_major);
+    CK(cudaStreamSynchronize(ctx->main_stream()));  // a previous async call may still read the old matrix
+    CK(cudaMemcpy(dM, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    return apply_map(ctx, (const uint4 *)dM, nullptr, 0, rows, cols, B, in, out, recipient_major);
 }
 
 // ------------------------------------------------------------------------------------------------ recovery tables
@@ -650,7 +699,8 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
     return 0;
 }
 
-// shared implementation of K3 / K4-direct: element (item b, arrival j) of `in` at (b*in_sb + j*in_sc)
+// ------------------------------------------------------------------------------------------------ K3 / K4
+// shared implementation: element (item b, arrival j) of `in` is sender-major [S][B] (K3) or codeword-major [B][S] (K4)
 static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, const size_t *ids, size_t B, const uint64_t *in,
                         bool sender_major, uint64_t *coeffs, bool secrets_only, uint64_t *secrets, int32_t *path, uint64_t *flags) {
     // validation order of robust_interpolate.rs:290-341 / :100-142
@@ -686,93 +736,97 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
     }
     const RecoverTables &T = it->second;
     const int fw = want_flags ? (int)((S + 63) / 64) : 0;
+    const bool want_secrets = !secrets_only && secrets != nullptr;
 
-    Staged si, sc, ss, sp, sf;
-    int rc;
-    if ((rc = stage_in(ctx, 0, in, B * S * 32, si))) return rc;
-    uint64_t *co_user = secrets_only ? secrets : coeffs;
-    if ((rc = stage_out(ctx, 1, co_user, B * T.mout * 32, sc))) return rc;
-    if ((rc = stage_out(ctx, 2, path, B * 4, sp))) return rc;
-    if (want_flags && (rc = stage_out(ctx, 3, flags, B * fw * 8, sf))) return rc;
-    if (!secrets_only && secrets && (rc = stage_out(ctx, 4, secrets, B * 32, ss))) return rc;
-    // scratch: fail bytes + list + counter
-    void *aux = nullptr;
-    size_t aux_bytes = ((B + 15) / 16) * 16 + B * 4 + 16;
-    if ((rc = scratch_get(ctx, 5, aux_bytes, &aux))) return rc;
-    unsigned char *fail = (unsigned char *)aux;
-    unsigned int *list = (unsigned int *)((char *)aux + ((B + 15) / 16) * 16);
-    unsigned int *count = list + B;
-    CK(cudaMemsetAsync(fail, 0, ((B + 15) / 16) * 16, ctx->stream));
-    CK(cudaMemsetAsync(count, 0, 16, ctx->stream));
-    CK(cudaMemsetAsync(sp.dev, 0, B * 4, ctx->stream));
-    if (want_flags) CK(cudaMemsetAsync(sf.dev, 0, B * fw * 8, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_status + 1, 0xff, 4, ctx->stream));
+    BatchBuf bi = make_buf(in, B, (long long)S, sender_major);
+    BatchBuf bc = make_buf(secrets_only ? secrets : coeffs, B, T.mout, false);
+    BatchBuf bp = make_buf(path, B, 1, false, 4);
+    BatchBuf bf = make_buf(flags, B, fw > 0 ? fw : 1, false, 8);
+    BatchBuf bs = make_buf(want_secrets ? secrets : nullptr, B, 1, false);
+    const WsLayout lay(T.nsyn_max, (int)t);
 
-    MatvecArgs a{};
-    a.M = T.M;
-    a.in = (const uint4 *)si.dev;
-    a.out = (uint4 *)sc.dev;
-    a.R = T.R;
-    a.C = T.C;
-    a.B = (long long)B;
-    if (sender_major) { a.in_sb = 1; a.in_sc = (long long)B; a.in_chunk_major = 0; }
-    else { a.in_sb = (long long)S; a.in_sc = 1; a.in_chunk_major = 1; }
-    a.out_sb = T.mout;
-    a.out_sr = 1;
-    a.col_map = T.col_map;
-    a.n_chk = T.n_chk;
-    a.n_gate = T.n_gate;
-    a.chk_map = T.chk_map;
-    a.fail = fail;
-    a.flags = want_flags ? (unsigned long long *)sf.dev : nullptr;
-    if ((rc = launch_matvec(ctx, a, fw))) return rc;
+    auto body = [&](Lane &ln, size_t b0, size_t Bc) -> int {
+        ChunkView vi, vc, vp, vf, vs;
+        int rc;
+        if ((rc = chunk_prepare(ctx, ln, 0, bi, b0, Bc, true, vi))) return rc;
+        if ((rc = chunk_prepare(ctx, ln, 1, bc, b0, Bc, false, vc))) return rc;
+        if ((rc = chunk_prepare(ctx, ln, 2, bp, b0, Bc, false, vp))) return rc;
+        if (want_flags && (rc = chunk_prepare(ctx, ln, 3, bf, b0, Bc, false, vf))) return rc;
+        if (want_secrets && (rc = chunk_prepare(ctx, ln, 4, bs, b0, Bc, false, vs))) return rc;
+        // scratch: fail bytes + list + counter
+        void *aux = nullptr;
+        const size_t fail_bytes = ((Bc + 15) / 16) * 16;
+        if ((rc = scratch_get(ctx, ln, 5, fail_bytes + Bc * 4 + 16, &aux))) return rc;
+        unsigned char *fail = (unsigned char *)aux;
+        unsigned int *list = (unsigned int *)((char *)aux + fail_bytes);
+        unsigned int *count = list + Bc;
+        CK(cudaMemsetAsync(fail, 0, fail_bytes, ln.stream));
+        CK(cudaMemsetAsync(count, 0, 16, ln.stream));
+        CK(cudaMemsetAsync(vp.dev, 0, Bc * 4, ln.stream));
+        if (want_flags) CK(cudaMemsetAsync(vf.dev, 0, Bc * fw * 8, ln.stream));
 
-    compact_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(fail, (long long)B, list, count);
-    ctx->launches++;
-    CK(cudaGetLastError());
+        MatvecArgs a{};
+        a.M = T.M;
+        a.in = (const uint4 *)vi.dev;
+        a.out = (uint4 *)vc.dev;
+        a.R = T.R;
+        a.C = T.C;
+        a.B = (long long)Bc;
+        a.in_sb = vi.sb; a.in_sc = vi.sj;
+        a.in_chunk_major = sender_major ? 0 : 1;
+        a.out_sb = T.mout;
+        a.out_sr = 1;
+        a.col_map = T.col_map;
+        a.n_chk = T.n_chk;
+        a.n_gate = T.n_gate;
+        a.chk_map = T.chk_map;
+        a.fail = fail;
+        a.flags = want_flags ? (unsigned long long *)vf.dev : nullptr;
+        if ((rc = launch_matvec(ctx, ln.stream, a, fw))) return rc;
 
-    {
+        compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail, (long long)Bc, list, count);
+        ctx->launches++;
+        CK(cudaGetLastError());
+
         RobustArgs r{};
-        r.in = (const uint4 *)si.dev;
-        r.in_sb = a.in_sb;
-        r.in_sc = a.in_sc;
-        r.B = (long long)B;
+        r.in = (const uint4 *)vi.dev;
+        r.in_sb = vi.sb; r.in_sc = vi.sj;
+        r.B = (long long)Bc;
         r.list = list;
         r.count = count;
         r.S = (int)S; r.m = (int)m; r.t = (int)t; r.needed = (int)needed; r.rmax = T.rmax; r.fast = T.fast;
         r.att_P = T.att_P; r.att_nsyn = T.att_nsyn; r.att_maxL = T.att_maxL; r.att_Hoff = T.att_Hoff; r.att_uoff = T.att_uoff;
         r.H = T.H; r.uinv = T.uinv; r.xs = T.xs; r.xinv = T.xinv; r.Lc = T.Lc; r.Veval = T.Veval; r.order = T.order;
-        r.coeffs = (uint4 *)sc.dev;
+        r.coeffs = (uint4 *)vc.dev;
         r.mout = T.mout;
-        r.path = (int *)sp.dev;
+        r.path = (int *)vp.dev;
         r.flags = a.flags;
         r.flag_words = fw;
-        r.first_fail = ctx->d_status + 1;
         r.fail_any = ctx->d_status + 2;
-        WsLayout lay(T.nsyn_max, (int)t);
         const int threads = 128;
-        long long blocks = std::min<long long>((long long)ctx->num_sms * 4, (long long)((B + threads - 1) / threads));
+        long long blocks = std::min<long long>((long long)ctx->num_sms * 4, (long long)((Bc + threads - 1) / threads));
         if (blocks < 1) blocks = 1;
         void *ws = nullptr;
-        if ((rc = scratch_get(ctx, 6, (size_t)blocks * threads * lay.total * 32 + 64, &ws))) return rc;
+        if ((rc = scratch_get(ctx, ln, 6, (size_t)blocks * threads * lay.total * 32 + 64, &ws))) return rc;
         r.ws = (uint4 *)ws;
         r.ws_elems = lay.total;
-        robust_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(r);
+        robust_kernel<<<(unsigned)blocks, threads, 0, ln.stream>>>(r);
         ctx->launches++;
         CK(cudaGetLastError());
-    }
-    if (!secrets_only && secrets) {
-        gather_first_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>((long long)B, (long long)m, (const uint4 *)sc.dev, (uint4 *)ss.dev);
-        ctx->launches++;
-        CK(cudaGetLastError());
-    }
-    bool ns = false;
-    if ((rc = unstage_out(ctx, sc, ns))) return rc;
-    if ((rc = unstage_out(ctx, sp, ns))) return rc;
-    if (want_flags && (rc = unstage_out(ctx, sf, ns))) return rc;
-    if (!secrets_only && secrets && (rc = unstage_out(ctx, ss, ns))) return rc;
-    if (ns && ctx->async) CK(cudaStreamSynchronize(ctx->stream));
-    return finish(ctx);
+
+        if (want_secrets) {
+            gather_first_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>((long long)Bc, (long long)m, (const uint4 *)vc.dev, (uint4 *)vs.dev);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+        if ((rc = chunk_commit(ctx, ln, bc, b0, Bc, vc))) return rc;
+        if ((rc = chunk_commit(ctx, ln, bp, b0, Bc, vp))) return rc;
+        if (want_flags && (rc = chunk_commit(ctx, ln, bf, b0, Bc, vf))) return rc;
+        if (want_secrets && (rc = chunk_commit(ctx, ln, bs, b0, Bc, vs))) return rc;
+        return 0;
+    };
+    const bool any_host = bi.host || bc.host || bp.host || (want_flags && bf.host) || (want_secrets && bs.host);
+    return run_batched(ctx, B, any_host, std::max<size_t>(S, T.mout) * 32, body);
 }
 
 extern "C" int hbmpc_batch_recover(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, const size_t *sender_ids, size_t B,
@@ -793,46 +847,49 @@ extern "C" int hbmpc_robust_interpolate_batch(hbmpc_ctx *ctx, size_t n, size_t d
     return recover_impl(ctx, n, d, t, S, ids, B, shares, false, coeffs, false, secrets, path, flags);
 }
 
+// ------------------------------------------------------------------------------------------------ K5
 extern "C" int hbmpc_elementwise(hbmpc_ctx *ctx, int op, size_t count, const uint64_t *a, const uint64_t *b, uint64_t *out) {
     if (!ctx) return HBMPC_INVALID_INPUT;
     if (op < 0 || op > 2) return HBMPC_INVALID_INPUT;
     if (count == 0) return HBMPC_SUCCESS;
     if (!a || !b || !out) return HBMPC_INVALID_INPUT;
     cudaSetDevice(ctx->device);
-    Staged sa, sb, so;
-    int rc;
-    if ((rc = stage_in(ctx, 0, a, count * 32, sa))) return rc;
-    if ((rc = stage_in(ctx, 1, b, count * 32, sb))) return rc;
-    if ((rc = stage_out(ctx, 2, out, count * 32, so))) return rc;
-    long long blocks = std::min<long long>((long long)ctx->num_sms * 8, (long long)((count + 255) / 256));
-    elementwise_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(op, (long long)count, (const uint4 *)sa.dev, (const uint4 *)sb.dev, (uint4 *)so.dev,
-                                                                  ctx->d_status);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    bool ns = false;
-    if ((rc = unstage_out(ctx, so, ns))) return rc;
-    if (ns && ctx->async) CK(cudaStreamSynchronize(ctx->stream));
-    return finish(ctx);
+    BatchBuf ba = make_buf(a, count, 1, false), bb = make_buf(b, count, 1, false), bo = make_buf(out, count, 1, false);
+    auto body = [&](Lane &ln, size_t b0, size_t Bc) -> int {
+        ChunkView va, vb, vo;
+        int rc;
+        if ((rc = chunk_prepare(ctx, ln, 0, ba, b0, Bc, true, va))) return rc;
+        if ((rc = chunk_prepare(ctx, ln, 1, bb, b0, Bc, true, vb))) return rc;
+        if ((rc = chunk_prepare(ctx, ln, 2, bo, b0, Bc, false, vo))) return rc;
+        long long blocks = std::min<long long>((long long)ctx->num_sms * 8, (long long)((Bc + 255) / 256));
+        elementwise_kernel<<<(unsigned)blocks, 256, 0, ln.stream>>>(op, (long long)Bc, (const uint4 *)va.dev, (const uint4 *)vb.dev, (uint4 *)vo.dev,
+                                                                   ctx->d_status);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return chunk_commit(ctx, ln, bo, b0, Bc, vo);
+    };
+    return run_batched(ctx, count, ba.host || bb.host || bo.host, 32, body);
 }
 
 extern "C" int hbmpc_measure_imad_peak(hbmpc_ctx *ctx, int variant, double *giga_inst_per_s, double *elapsed_ms) {
     if (!ctx || variant < 0 || variant > 2 || !giga_inst_per_s) return HBMPC_INVALID_INPUT;
     cudaSetDevice(ctx->device);
     void *sink = nullptr;
-    int rc = scratch_get(ctx, 7, 256, &sink);
+    int rc = scratch_get(ctx, ctx->lanes[0], 8, 256, &sink);
     if (rc) return rc;
     const int iters = 4096, blocks = ctx->num_sms * 8, threads = 256;
+    cudaStream_t st = ctx->main_stream();
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
-        CK(cudaEventRecord(e0, ctx->stream));
-        if (variant == 0) imad_probe_kernel<0><<<blocks, threads, 0, ctx->stream>>>((unsigned int *)sink, 12345u + rep, iters);
-        else if (variant == 1) imad_probe_kernel<1><<<blocks, threads, 0, ctx->stream>>>((unsigned int *)sink, 12345u + rep, iters);
-        else imad_probe_kernel<2><<<blocks, threads, 0, ctx->stream>>>((unsigned int *)sink, 12345u + rep, iters);
+        CK(cudaEventRecord(e0, st));
+        if (variant == 0) imad_probe_kernel<0><<<blocks, threads, 0, st>>>((unsigned int *)sink, 12345u + rep, iters);
+        else if (variant == 1) imad_probe_kernel<1><<<blocks, threads, 0, st>>>((unsigned int *)sink, 12345u + rep, iters);
+        else imad_probe_kernel<2><<<blocks, threads, 0, st>>>((unsigned int *)sink, 12345u + rep, iters);
         ctx->launches++;
-        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventRecord(e1, st));
         CK(cudaEventSynchronize(e1));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -840,9 +897,8 @@ extern "C" int hbmpc_measure_imad_peak(hbmpc_ctx *ctx, int variant, double *giga
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    // thread-level multiply-add instructions per thread: variant 0: 64/iter; 1: 64/iter; 2: 4*4*8 = 128/iter (+16 ALU adds)
-    double per_thread = variant == 2 ? 128.0 * iters : 64.0 * iters;
-    double total = per_thread * (double)blocks * threads;
+    // thread-level instructions per thread per iteration: 64 in every variant (16 chains x 4, 2 x 4 lanes x 8, 8 x 8)
+    double total = 64.0 * iters * (double)blocks * threads;
     *giga_inst_per_s = total / (best * 1e-3) / 1e9;
     if (elapsed_ms) *elapsed_ms = best;
     return HBMPC_SUCCESS;

@@ -53,7 +53,6 @@ struct RobustArgs {
     int *path;
     unsigned long long *flags;  // may be nullptr
     int flag_words;
-    unsigned int *first_fail;   // atomicMin of failing item index
     unsigned int *fail_any;     // set to 1 when any item fails to decode
     uint4 *ws;                  // workspace: ws_elems Fr per thread, strided by total thread count
     int ws_elems;
@@ -342,7 +341,6 @@ __global__ void __launch_bounds__(128) robust_kernel(const RobustArgs a) {
             for (int k = 0; k < a.mout; ++k) { co[k * 2] = make_uint4(0, 0, 0, 0); co[k * 2 + 1] = make_uint4(0, 0, 0, 0); }
             if (fl) for (int w = 0; w < a.flag_words; ++w) fl[w] = 0ull;
             a.path[b] = -8;
-            atomicMin(a.first_fail, (unsigned int)b);
             atomicOr(a.fail_any, 1u);
             continue;
         }

@@ -350,3 +350,35 @@ def test_imad_probe_runs(ctx):
         g, ms = ctx.measure_imad_peak(v)
         assert g > 100.0 and ms > 0
     assert ctx.launch_count > 0
+
+
+def test_pipelined_host_chunks(hb, orc, monkeypatch):
+    """Host buffers larger than one chunk go through the multi-lane copy/compute pipeline (1D and 2D chunk copies):
+    results must equal the single-pass device path and the oracle."""
+    monkeypatch.setenv("HBMPC_CHUNK_MB", "1")
+    c = hb.Context(0)
+    try:
+        n, t, d, B = 64, 21, 21, 9000
+        rng = np.random.default_rng(9)
+        coeffs = _rand(orc, (B, d + 1), 0xC0FFEE)
+        rc, want = orc.compute_shares(coeffs, n, threads=orc.max_threads())
+        shares = c.compute_shares_batch(coeffs, n)
+        assert np.array_equal(shares, want)
+        rm = c.apply_vandermonde_batch(coeffs, n, recipient_major=True)
+        assert np.array_equal(rm, np.ascontiguousarray(want.transpose(1, 0, 2)))
+        nerr = rng.integers(0, 3, size=B)
+        nerr[::7] = 0
+        bad = _corrupt(shares, rng, nerr)
+        evals = np.ascontiguousarray(bad.transpose(1, 0, 2))
+        ids = np.arange(n)
+        ref = orc.batch_recover_secret(ids, evals, n, d, t, threads=orc.max_threads())
+        got = c.batch_recover(ids, evals, n, d, t, want_flags=True)
+        _compare_recover(got, ref, B)
+        assert np.array_equal(got[1], coeffs)
+        rc, co, sec, path, flags = c.robust_interpolate_batch(ids, bad, n, d, t, want_flags=True)
+        assert np.array_equal(co, coeffs) and np.array_equal(sec, coeffs[:, 0]) and np.array_equal(path, ref["path"])
+        a, b = _rand(orc, (B,), 1), _rand(orc, (B,), 2)
+        rc, w = orc.elementwise(2, a, b)
+        assert np.array_equal(c.elementwise(2, a, b), w)
+    finally:
+        c.close()
