@@ -281,16 +281,18 @@ def run_b200(args):
     # ---- NCCL gather of the reconstructed secrets (the only collective; outside the hot path)
     gather_ms = None
     if world > 1:
+        sh = importlib.import_module("mpc-protocols_b200.sharding")
+        lo, hi = sh.shard_range(world * B, world, rank)      # this rank's contiguous range of the global batch
+        assert hi - lo == B
         secrets = rec[:, 0, :].contiguous()
-        allsec = torch.empty((world,) + tuple(secrets.shape), dtype=secrets.dtype, device=dev)
         torch.cuda.synchronize()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        dist.all_gather_into_tensor(allsec, secrets)
+        allsec = sh.gather_shards(secrets, world * B)
         g1.record()
         torch.cuda.synchronize()
         gather_ms = g0.elapsed_time(g1)
-        assert torch.equal(allsec[rank], secrets)
+        assert torch.equal(allsec[lo:hi], coeffs[:, 0, :])
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores
     cpu = None
