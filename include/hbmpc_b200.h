@@ -103,6 +103,16 @@ int hbmpc_robust_interpolate_batch(hbmpc_ctx *ctx, size_t n, size_t d, size_t t,
                                    const uint64_t *shares, uint64_t *coeffs, uint64_t *secrets, int32_t *path,
                                    uint64_t *flags);
 
+/* a10.  Replaces NonRobustShare::recover_secret (common/share/shamir.rs:199-239: Lagrange interpolation through ALL
+ * supplied points + degree check) for a batch with a common id set; it is the consistency check of the RanDouSha
+ * checkers (ran_dou_sha/mod.rs:568-602) and DoubleShare.  shares[B][S] (sender_major == 0) or shares[S][B]
+ * (sender_major != 0)  ->  coeffs[B][deg+1] (zero padded), secrets[B] = coefficient 0 (may be NULL),
+ * status[B] = degree of the interpolant (>= 0; the caller compares it with t / 2t like ran_dou_sha/mod.rs:589-595) or
+ * -HBMPC_DEGREE_MISMATCH when the interpolant exceeds `deg` (outputs of that item are zeroed).
+ * Whole-call errors: empty / duplicate ids / id >= n -> INVALID_INPUT, S < deg+1 -> INSUFFICIENT_SHARES. */
+int hbmpc_nonrobust_recover_batch(hbmpc_ctx *ctx, size_t n, size_t deg, size_t S, const size_t *ids, size_t B,
+                                  const uint64_t *shares, int sender_major, uint64_t *coeffs, uint64_t *secrets, int32_t *status);
+
 /* K5.  Element-wise share algebra (common/mod.rs:167-300; triple_generation.rs:332-340,196-208;
  * multiplication.rs:79-97,417-426): out[i] = a[i] (op) b[i], op: 0 add, 1 sub, 2 mul (share_mul / Mul<F>). */
 int hbmpc_elementwise(hbmpc_ctx *ctx, int op, size_t count, const uint64_t *a, const uint64_t *b, uint64_t *out);

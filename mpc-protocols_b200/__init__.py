@@ -32,7 +32,7 @@ EXPORTS = [
     "hbmpc_ctx_create", "hbmpc_ctx_destroy", "hbmpc_ctx_set_stream", "hbmpc_ctx_set_async", "hbmpc_ctx_synchronize",
     "hbmpc_ctx_launch_count", "hbmpc_last_error", "hbmpc_compute_shares_batch", "hbmpc_apply_vandermonde_batch",
     "hbmpc_apply_matrix_batch", "hbmpc_batch_recover", "hbmpc_batch_recover_secrets", "hbmpc_robust_interpolate_batch",
-    "hbmpc_elementwise", "hbmpc_measure_imad_peak",
+    "hbmpc_nonrobust_recover_batch", "hbmpc_elementwise", "hbmpc_measure_imad_peak",
 ]
 
 
@@ -70,6 +70,7 @@ def load_library():
     lib.hbmpc_batch_recover.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp, vp]
     lib.hbmpc_batch_recover_secrets.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp]
     lib.hbmpc_robust_interpolate_batch.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp, vp, vp]
+    lib.hbmpc_nonrobust_recover_batch.argtypes = [vp, sz, sz, sz, vp, sz, vp, ci, vp, vp, vp]
     lib.hbmpc_elementwise.argtypes = [vp, ci, sz, vp, vp, vp]
     lib.hbmpc_measure_imad_peak.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = lib
@@ -228,6 +229,21 @@ class Context:
                                                      _ptr(path), _ptr(flags) if flags is not None else None)
         self._check(rc, ok=(0, DECODING_ERROR))
         return rc, coeffs, secrets, path, flags
+
+    # -- a10
+    def nonrobust_recover_batch(self, ids, shares, n: int, deg: int, sender_major: bool = False, out=None):
+        """shares[B][S] (or [S][B] when sender_major) -> (coeffs[B][deg+1][4], secrets[B][4], status[B])
+        (NonRobustShare::recover_secret, common/share/shamir.rs:199-239, batched; status = degree or -DegreeMismatch)."""
+        s = _Buf(shares)
+        S, B = (s.shape[0], s.shape[1]) if sender_major else (s.shape[1], s.shape[0])
+        idv = np.ascontiguousarray(ids, dtype=np.uint64)
+        if out is None:
+            coeffs, secrets, status = s.like((B, deg + 1, 4)), s.like((B, 4)), s.like((B,), "i32")
+        else:
+            coeffs, secrets, status = out
+        self._check(self.lib.hbmpc_nonrobust_recover_batch(self.h, n, deg, len(idv), idv.ctypes.data, B, s.ptr, int(sender_major),
+                                                            _ptr(coeffs), _ptr(secrets), _ptr(status)))
+        return coeffs, secrets, status
 
     # -- K5
     def elementwise(self, op: int, a, b, out=None):

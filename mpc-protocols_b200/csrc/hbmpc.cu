@@ -54,6 +54,26 @@ __global__ void gather_first_kernel(long long B, long long stride, const uint4 *
     }
 }
 
+// NonRobustShare::recover_secret epilogue: status[b] = degree of the interpolant (highest non-zero coefficient, 0 for the zero
+// polynomial like DensePolynomial::degree) or -DegreeMismatch when a coefficient above `deg` was non-zero; failing items are zeroed.
+__global__ void degree_status_kernel(long long B, int m, uint4 *coeffs, const unsigned char *fail, int *status, uint4 *secrets) {
+    for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        uint4 *c = coeffs + b * m * 2;
+        int st = 0;
+        if (fail[b]) {
+            st = -HBMPC_DEGREE_MISMATCH;
+            for (int k = 0; k < 2 * m; ++k) c[k] = make_uint4(0, 0, 0, 0);
+        } else {
+            for (int k = m - 1; k > 0; --k) {
+                uint4 lo = c[2 * k], hi = c[2 * k + 1];
+                if (lo.x | lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w) { st = k; break; }
+            }
+        }
+        status[b] = st;
+        if (secrets) { secrets[2 * b] = c[0]; secrets[2 * b + 1] = c[1]; }
+    }
+}
+
 // Integer-pipe roofline probes (register-only, multiplicands depend on the running values so nothing is hoisted):
 //   0: mad.lo.u32 (IMAD)            -- the "IMAD peak" of the north star: 64 lanes/clk/SM
 //   1: IMAD.WIDE.U32(.X) 4-lane carry chains, the product kernels' instruction (32x32->64 multiply-add)
@@ -157,6 +177,7 @@ struct hbmpc_ctx {
     cudaEvent_t ev_main = nullptr;
     std::map<std::string, uint4 *> matrices;          // Vandermonde / twiddle tables keyed by "V n cols" / "W N"
     std::map<std::string, RecoverTables> recover;     // keyed by (n, d, t, ids, variant)
+    std::map<std::string, struct NonRobustTables> *nonrobust = nullptr;
     std::vector<void *> owned;                        // device allocations freed at destroy
     cudaStream_t main_stream() const { return lanes[0].stream; }
 };
@@ -275,6 +296,7 @@ extern "C" void hbmpc_ctx_destroy(hbmpc_ctx *ctx) {
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
+    delete ctx->nonrobust;
     for (int i = 0; i < NLANES; ++i)
         if (ctx->lanes[i].stream && (i > 0 || ctx->own_stream)) cudaStreamDestroy(ctx->lanes[i].stream);
     delete ctx;
@@ -845,6 +867,99 @@ extern "C" int hbmpc_robust_interpolate_batch(hbmpc_ctx *ctx, size_t n, size_t d
                                               const uint64_t *shares, uint64_t *coeffs, uint64_t *secrets, int32_t *path, uint64_t *flags) {
     if (!ctx) return HBMPC_INVALID_INPUT;
     return recover_impl(ctx, n, d, t, S, ids, B, shares, false, coeffs, false, secrets, path, flags);
+}
+
+// ------------------------------------------------------------------------------------------------ a10: NonRobustShare::recover_secret, batched
+struct NonRobustTables {
+    uint4 *M = nullptr;
+    int *chk_map = nullptr;
+    int R = 0, n_chk = 0;
+};
+static std::map<std::string, NonRobustTables> &nr_cache(hbmpc_ctx *ctx) {
+    if (!ctx->nonrobust) ctx->nonrobust = new std::map<std::string, NonRobustTables>();
+    return *ctx->nonrobust;
+}
+
+extern "C" int hbmpc_nonrobust_recover_batch(hbmpc_ctx *ctx, size_t n, size_t deg, size_t S, const size_t *ids, size_t B, const uint64_t *shares,
+                                             int sender_major, uint64_t *coeffs, uint64_t *secrets, int32_t *status) {
+    if (!ctx) return HBMPC_INVALID_INPUT;
+    // validation order of common/share/shamir.rs:204-232
+    if (S == 0 || !ids) return HBMPC_INVALID_INPUT;
+    if (S > 256) return HBMPC_INVALID_INPUT;
+    {
+        std::vector<size_t> srt(ids, ids + S);
+        std::sort(srt.begin(), srt.end());
+        for (size_t i = 1; i < S; ++i)
+            if (srt[i] == srt[i - 1]) return HBMPC_INVALID_INPUT;
+    }
+    if (S < deg + 1) return HBMPC_INSUFFICIENT_SHARES;
+    if (!domain_size(n)) return HBMPC_NO_SUITABLE_DOMAIN;
+    for (size_t i = 0; i < S; ++i)
+        if (ids[i] >= n) return HBMPC_INVALID_INPUT;
+    if (B == 0) return HBMPC_SUCCESS;
+    if (!shares || !coeffs || !status) return HBMPC_INVALID_INPUT;
+    cudaSetDevice(ctx->device);
+    const size_t m = deg + 1;
+    std::string key = "N " + std::to_string(n) + " " + std::to_string(deg);
+    for (size_t i = 0; i < S; ++i) key += " " + std::to_string(ids[i]);
+    auto &cache = nr_cache(ctx);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        std::vector<HFr> dom = domain_elements(n, n), xs(S);
+        for (size_t i = 0; i < S; ++i) xs[i] = dom[ids[i]];
+        Lagrange L = lagrange_basis(xs);  // Lc[k][i]: coefficient k of the basis polynomial of arrival i
+        // rows: coefficients deg+1 .. S-1 (must vanish: the DegreeMismatch check of shamir.rs:234-237), then 0 .. deg
+        std::vector<HFr> M(L.Lc.begin() + m * S, L.Lc.end());
+        M.insert(M.end(), L.Lc.begin(), L.Lc.begin() + m * S);
+        NonRobustTables T;
+        T.n_chk = (int)(S - m);
+        T.R = (int)S;
+        std::vector<int> chk(std::max<size_t>(S - m, 1), -1);
+        int rc;
+        if ((rc = upload_fr(ctx, M, &T.M))) return rc;
+        if ((rc = upload(ctx, chk, &T.chk_map))) return rc;
+        it = cache.emplace(key, T).first;
+    }
+    const NonRobustTables &T = it->second;
+    BatchBuf bi = make_buf(shares, B, (long long)S, sender_major != 0), bc = make_buf(coeffs, B, (long long)m, false);
+    BatchBuf bs = make_buf(secrets, B, 1, false), bst = make_buf(status, B, 1, false, 4);
+    auto body = [&](Lane &ln, size_t b0, size_t Bc) -> int {
+        ChunkView vi, vc, vs, vst;
+        int rc;
+        if ((rc = chunk_prepare(ctx, ln, 0, bi, b0, Bc, true, vi))) return rc;
+        if ((rc = chunk_prepare(ctx, ln, 1, bc, b0, Bc, false, vc))) return rc;
+        if ((rc = chunk_prepare(ctx, ln, 2, bst, b0, Bc, false, vst))) return rc;
+        if (secrets && (rc = chunk_prepare(ctx, ln, 4, bs, b0, Bc, false, vs))) return rc;
+        void *aux = nullptr;
+        const size_t fail_bytes = ((Bc + 15) / 16) * 16;
+        if ((rc = scratch_get(ctx, ln, 5, fail_bytes, &aux))) return rc;
+        CK(cudaMemsetAsync(aux, 0, fail_bytes, ln.stream));
+        MatvecArgs a{};
+        a.M = T.M;
+        a.in = (const uint4 *)vi.dev;
+        a.out = (uint4 *)vc.dev;
+        a.R = T.R;
+        a.C = (int)S;
+        a.B = (long long)Bc;
+        a.in_sb = vi.sb; a.in_sc = vi.sj;
+        a.in_chunk_major = sender_major ? 0 : 1;
+        a.out_sb = (long long)m;
+        a.out_sr = 1;
+        a.n_chk = T.n_chk;
+        a.n_gate = T.n_chk;
+        a.chk_map = T.chk_map;
+        a.fail = (unsigned char *)aux;
+        if ((rc = launch_matvec(ctx, ln.stream, a, 0))) return rc;
+        degree_status_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>((long long)Bc, (int)m, (uint4 *)vc.dev, (const unsigned char *)aux, (int *)vst.dev,
+                                                                     secrets ? (uint4 *)vs.dev : nullptr);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        if ((rc = chunk_commit(ctx, ln, bc, b0, Bc, vc))) return rc;
+        if ((rc = chunk_commit(ctx, ln, bst, b0, Bc, vst))) return rc;
+        if (secrets && (rc = chunk_commit(ctx, ln, bs, b0, Bc, vs))) return rc;
+        return 0;
+    };
+    return run_batched(ctx, B, bi.host || bc.host || bst.host || (secrets && bs.host), S * 32, body);
 }
 
 // ------------------------------------------------------------------------------------------------ K5

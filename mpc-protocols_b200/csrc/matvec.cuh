@@ -33,7 +33,7 @@ struct MatvecArgs {
     long long in_sb, in_sc, out_sb, out_sr;  // strides in 32-byte elements
     const int *col_map;                     // [C] input index of column c, or nullptr (identity)
     int n_chk, n_gate;
-    const int *chk_map;        // [n_chk] input index checked by check row r
+    const int *chk_map;        // [n_chk] input index checked by check row r (< 0: compare with zero)
     unsigned char *fail;       // [B] set to 1 when a gate row mismatches (may be nullptr when n_gate == 0)
     unsigned long long *flags; // [B][flag_words] or nullptr
     int flag_words;
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
             uint4 y_lo = make_uint4(0, 0, 0, 0), y_hi = y_lo;
             int chk_j = 0;
             if (is_chk) {
-                chk_j = a.chk_map[r];
-                if (b < a.B) {
+                chk_j = a.chk_map[r];  // < 0: the row must evaluate to zero (degree check)
+                if (chk_j >= 0 && b < a.B) {
                     const uint4 *p = a.in + (b * a.in_sb + (long long)chk_j * a.in_sc) * 2;
                     y_lo = ldg_stream(p);
                     y_hi = ldg_stream(p + 1);
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
                 bad |= geq_mod(y) ? 1u : 0u;
                 if (b < a.B && !fr_eq(res, y)) {
                     if (r < a.n_gate) sFail[sub * 32 + lane] = 1u;
-                    if (a.flags) atomicOr(&sFlags[(size_t)(sub * 32 + lane) * a.flag_words + (chk_j >> 6)], 1ull << (chk_j & 63));
+                    if (a.flags && chk_j >= 0) atomicOr(&sFlags[(size_t)(sub * 32 + lane) * a.flag_words + (chk_j >> 6)], 1ull << (chk_j & 63));
                 }
             } else if (b < a.B) {
                 uint4 *o = a.out + (b * a.out_sb + (long long)(r - a.n_chk) * a.out_sr) * 2;

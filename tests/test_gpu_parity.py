@@ -382,3 +382,40 @@ def test_pipelined_host_chunks(hb, orc, monkeypatch):
         assert np.array_equal(c.elementwise(2, a, b), w)
     finally:
         c.close()
+
+
+# ------------------------------------------------------------------ a10: NonRobustShare::recover_secret (RanDouSha checker)
+@pytest.mark.parametrize("n,t", [(4, 1), (7, 2), (10, 3), (16, 5), (64, 21)])
+def test_nonrobust_recover_batch(ctx, orc, hb, n, t):
+    B = 40
+    rng = np.random.default_rng(n)
+    for deg in (t, 2 * t):
+        coeffs, shares = _codewords(orc, n, deg, B, 0x5EED0500 + n + deg)
+        # item 1: top coefficient zero (degree deg-1); item 2: zero polynomial; item 3..5: not a codeword (degree mismatch)
+        coeffs[1, deg] = 0
+        coeffs[2] = 0
+        rc, shares = orc.compute_shares(coeffs, n)
+        for S, ids in ((n, np.arange(n)), (max(deg + 1, n - 2), rng.permutation(n)[: max(deg + 1, n - 2)])):
+            vals = shares[:, ids].copy()
+            for b in (3, 4, 5):
+                vals[b, rng.integers(0, S), 0] ^= np.uint64(77)
+            co, sec, st = ctx.nonrobust_recover_batch(ids, vals, n, deg)
+            co2, sec2, st2 = ctx.nonrobust_recover_batch(ids, np.ascontiguousarray(vals.transpose(1, 0, 2)), n, deg, sender_major=True)
+            assert np.array_equal(co, co2) and np.array_equal(sec, sec2) and np.array_equal(st, st2)
+            for b in range(B):
+                ref = orc.nonrobust_recover_secret(ids, vals[b], n, deg)
+                if ref["rc"] == 0:
+                    assert st[b] == max(ref["coeff_len"] - 1, 0), (b, st[b], ref["coeff_len"])
+                    assert np.array_equal(co[b], ref["coeffs"]) and np.array_equal(sec[b], ref["secret"])
+                else:
+                    assert ref["rc"] == hb.DEGREE_MISMATCH and st[b] == -hb.DEGREE_MISMATCH
+                    assert not co[b].any() and not sec[b].any()
+            if S > deg + 1:
+                assert (st[3:6] == -hb.DEGREE_MISMATCH).all()
+            assert st[0] == deg and st[1] == deg - 1 and st[2] == 0
+    with pytest.raises(hb.HbmpcError) as e:
+        ctx.nonrobust_recover_batch(np.arange(t), shares[:, :t], n, t)
+    assert e.value.code == hb.INSUFFICIENT_SHARES
+    with pytest.raises(hb.HbmpcError) as e:
+        ctx.nonrobust_recover_batch(np.zeros(t + 1, dtype=np.uint64), shares[:, : t + 1], n, t)
+    assert e.value.code == hb.INVALID_INPUT
