@@ -1,0 +1,31 @@
+"""Builds and runs the C++ host-side mirror tests (tests/host/mirror_test.cpp: the reference's unit tests re-stated against
+include/hbmpc_b200.hpp and the C ABI) on the GPU box."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _compile(tmp_path):
+    exe = tmp_path / "mirror_test"
+    lib_dir = os.path.join(ROOT, "mpc-protocols_b200")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "host", "mirror_test.cpp"),
+           "-L", lib_dir, "-lhbmpc_b200", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def test_mirror_compiles_and_links(tmp_path):
+    """CPU: the C++ mirror compiles against the header and links against the built library."""
+    assert os.path.exists(os.path.join(ROOT, "mpc-protocols_b200", "libhbmpc_b200.so")), "build the library first"
+    _compile(tmp_path)
+
+
+@pytest.mark.gpu
+def test_reference_unit_tests_through_cpp_mirror(tmp_path):
+    exe = _compile(tmp_path)
+    res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "all reference-shaped tests passed" in res.stdout
