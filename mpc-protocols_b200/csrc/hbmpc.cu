@@ -158,6 +158,10 @@ struct RecoverTables {
     int *att_P = nullptr, *att_nsyn = nullptr, *att_maxL = nullptr, *order = nullptr;
     long long *att_Hoff = nullptr, *att_uoff = nullptr;
     uint4 *H = nullptr, *uinv = nullptr, *xs = nullptr, *xinv = nullptr, *Lc = nullptr, *Veval = nullptr;
+    // all-shares-present fast path (S == n == N): inverse NTT + degree check
+    int fast_logn = 0;
+    int *in_map = nullptr;
+    uint4 *itw = nullptr, *iscale = nullptr;
 };
 
 struct hbmpc_ctx {
@@ -169,7 +173,8 @@ struct hbmpc_ctx {
     std::string err;
     int num_sms = 148;
     int matvec_regs = 0;
-    int ntt_ctas[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // resident CTAs per SM of ntt_kernel<LOGN>
+    int ntt_ctas[2][9] = {};                        // resident CTAs per SM of ntt_kernel<LOGN, MODE>
+    bool no_fastpath = false;                       // HBMPC_NO_FASTPATH=1: K3 never takes the all-shares-present inverse-NTT path
     bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
     size_t chunk_bytes = 24u << 20;                 // HBMPC_CHUNK_MB: target bytes per pipelined host copy
     unsigned int *d_status = nullptr;  // [0] non-canonical input seen, [2] some item failed to decode
@@ -255,6 +260,8 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
     {
         const char *fd = getenv("HBMPC_FORCE_DENSE");
         ctx->force_dense = fd && fd[0] == '1';
+        const char *nf = getenv("HBMPC_NO_FASTPATH");
+        ctx->no_fastpath = nf && nf[0] == '1';
         const char *cm = getenv("HBMPC_CHUNK_MB");
         if (cm && atoi(cm) > 0) ctx->chunk_bytes = (size_t)atoi(cm) << 20;
     }
@@ -455,38 +462,39 @@ static int launch_matvec(hbmpc_ctx *ctx, cudaStream_t st, MatvecArgs a, int flag
     return 0;
 }
 
-template <int LOGN>
+template <int LOGN, int MODE>
 static int launch_ntt_t(hbmpc_ctx *ctx, cudaStream_t st, const NttArgs &a) {
     const size_t smem = ntt_smem_bytes<LOGN>();
-    if (ctx->ntt_ctas[LOGN] == 0) {
-        CK(cudaFuncSetAttribute(ntt_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int &ctas = ctx->ntt_ctas[MODE][LOGN];
+    if (ctas == 0) {
+        CK(cudaFuncSetAttribute(ntt_kernel<LOGN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ntt_kernel<LOGN>, 256, smem));
-        ctx->ntt_ctas[LOGN] = nb > 0 ? nb : 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ntt_kernel<LOGN, MODE>, 256, smem));
+        ctas = nb > 0 ? nb : 1;
     }
     const int ipc = ntt_items_per_cta<LOGN>();
     long long ntiles = (a.B + ipc - 1) / ipc;
-    long long grid = std::min<long long>(ntiles, (long long)ctx->num_sms * ctx->ntt_ctas[LOGN]);
-    ntt_kernel<LOGN><<<(unsigned)grid, 256, smem, st>>>(a);
+    long long grid = std::min<long long>(ntiles, (long long)ctx->num_sms * ctas);
+    ntt_kernel<LOGN, MODE><<<(unsigned)grid, 256, smem, st>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
 }
+template <int MODE>
 static int launch_ntt(hbmpc_ctx *ctx, cudaStream_t st, int logn, const NttArgs &a) {
     switch (logn) {
-        case 1: return launch_ntt_t<1>(ctx, st, a);
-        case 2: return launch_ntt_t<2>(ctx, st, a);
-        case 3: return launch_ntt_t<3>(ctx, st, a);
-        case 4: return launch_ntt_t<4>(ctx, st, a);
-        case 5: return launch_ntt_t<5>(ctx, st, a);
-        case 6: return launch_ntt_t<6>(ctx, st, a);
-        case 7: return launch_ntt_t<7>(ctx, st, a);
-        case 8: return launch_ntt_t<8>(ctx, st, a);
+        case 1: return launch_ntt_t<1, MODE>(ctx, st, a);
+        case 2: return launch_ntt_t<2, MODE>(ctx, st, a);
+        case 3: return launch_ntt_t<3, MODE>(ctx, st, a);
+        case 4: return launch_ntt_t<4, MODE>(ctx, st, a);
+        case 5: return launch_ntt_t<5, MODE>(ctx, st, a);
+        case 6: return launch_ntt_t<6, MODE>(ctx, st, a);
+        case 7: return launch_ntt_t<7, MODE>(ctx, st, a);
+        case 8: return launch_ntt_t<8, MODE>(ctx, st, a);
     }
     ctx->err = "ntt: unsupported domain size";
     return HBMPC_NO_SUITABLE_DOMAIN;
 }
-
 
 static int get_twiddles(hbmpc_ctx *ctx, int N, uint4 **out) {
     char key[64];
@@ -502,6 +510,27 @@ static int get_twiddles(hbmpc_ctx *ctx, int N, uint4 **out) {
     if (rc) return rc;
     ctx->matrices[key] = d;
     *out = d;
+    return 0;
+}
+
+// inverse transform tables: w_N^{-k} (k < N/2) followed by N^{-1}, all in Montgomery form
+static int get_inverse_twiddles(hbmpc_ctx *ctx, int N, uint4 **tw, uint4 **scale) {
+    char key[64];
+    snprintf(key, sizeof key, "WI %d", N);
+    auto it = ctx->matrices.find(key);
+    if (it == ctx->matrices.end()) {
+        std::vector<HFr> d = domain_elements((size_t)N, (size_t)N);
+        std::vector<HFr> t((size_t)std::max(N / 2, 1) + 1);
+        t[0] = hfr::ONE;
+        for (int k = 1; k < N / 2; ++k) t[k] = d[N - k];  // w^{-k} = w^{N-k}
+        t[std::max(N / 2, 1)] = hfr::inv(hfr::from_u64((uint64_t)N));
+        uint4 *dev = nullptr;
+        int rc = upload_fr(ctx, t, &dev);
+        if (rc) return rc;
+        it = ctx->matrices.emplace(key, dev).first;
+    }
+    *tw = it->second;
+    *scale = it->second + (size_t)std::max(N / 2, 1) * 2;
     return 0;
 }
 
@@ -555,7 +584,7 @@ static int apply_map(hbmpc_ctx *ctx, const uint4 *M, const uint4 *tw, int logn, 
             a.cols = (int)cols;
             a.n = (int)rows;
             a.err = ctx->d_status;
-            if ((rc = launch_ntt(ctx, ln.stream, logn, a))) return rc;
+            if ((rc = launch_ntt<0>(ctx, ln.stream, logn, a))) return rc;
         }
         return chunk_commit(ctx, ln, bo, b0, Bc, vo);
     };
@@ -718,6 +747,15 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
     if ((rc = upload_fr(ctx, xinv, &T.xinv))) return rc;
     if ((rc = upload_fr(ctx, L.Lc, &T.Lc))) return rc;
     if ((rc = upload_fr(ctx, Veval, &T.Veval))) return rc;
+    // every point of the power-of-two domain supplied: coefficients by one inverse NTT, checked by "top coefficients vanish"
+    const int N = domain_size(n);
+    if (!ctx->no_fastpath && S == n && (size_t)N == n && N >= 2) {
+        std::vector<int> in_map(N);
+        for (size_t i = 0; i < S; ++i) in_map[sorted_ids[i]] = order[i];
+        if ((rc = upload(ctx, in_map, &T.in_map))) return rc;
+        if ((rc = get_inverse_twiddles(ctx, N, &T.itw, &T.iscale))) return rc;
+        while ((1 << T.fast_logn) < N) ++T.fast_logn;
+    }
     return 0;
 }
 
@@ -778,16 +816,47 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         // scratch: fail bytes + list + counter
         void *aux = nullptr;
         const size_t fail_bytes = ((Bc + 15) / 16) * 16;
-        if ((rc = scratch_get(ctx, ln, 5, fail_bytes + Bc * 4 + 16, &aux))) return rc;
+        if ((rc = scratch_get(ctx, ln, 5, 2 * (fail_bytes + Bc * 4 + 16), &aux))) return rc;
         unsigned char *fail = (unsigned char *)aux;
         unsigned int *list = (unsigned int *)((char *)aux + fail_bytes);
         unsigned int *count = list + Bc;
+        unsigned char *fail1 = (unsigned char *)(count + 4);
+        unsigned int *list1 = (unsigned int *)(fail1 + fail_bytes);
+        unsigned int *count1 = list1 + Bc;
         CK(cudaMemsetAsync(fail, 0, fail_bytes, ln.stream));
         CK(cudaMemsetAsync(count, 0, 16, ln.stream));
         CK(cudaMemsetAsync(vp.dev, 0, Bc * 4, ln.stream));
         if (want_flags) CK(cudaMemsetAsync(vf.dev, 0, Bc * fw * 8, ln.stream));
 
+        const bool fastN = T.fast_logn > 0;
+        if (fastN) {
+            // optimistic-optimistic: all n = N shares on one degree-d polynomial <=> the top N-m coefficients of the inverse
+            // NTT vanish; then the lowest d+t+1 agree as well (path 0, no flags).  Items that fail go to the dense check.
+            CK(cudaMemsetAsync(fail1, 0, fail_bytes, ln.stream));
+            CK(cudaMemsetAsync(count1, 0, 16, ln.stream));
+            NttArgs na{};
+            na.in = (const uint4 *)vi.dev;
+            na.out = (uint4 *)vc.dev;
+            na.tw = T.itw;
+            na.B = (long long)Bc;
+            na.in_sb = vi.sb; na.in_sc = vi.sj;
+            na.out_sb = T.mout; na.out_sr = 1;
+            na.cols = (int)S;
+            na.n = (int)S;
+            na.err = ctx->d_status;
+            na.in_map = T.in_map;
+            na.scale = T.iscale;
+            na.m = (int)m;
+            na.mout = T.mout;
+            na.fail = fail1;
+            if ((rc = launch_ntt<1>(ctx, ln.stream, T.fast_logn, na))) return rc;
+            compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail1, (long long)Bc, list1, count1);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+
         MatvecArgs a{};
+        if (fastN) { a.item_list = list1; a.item_count = count1; }
         a.M = T.M;
         a.in = (const uint4 *)vi.dev;
         a.out = (uint4 *)vc.dev;

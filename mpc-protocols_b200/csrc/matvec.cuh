@@ -40,6 +40,8 @@ struct MatvecArgs {
     unsigned int *err;         // device word: bit0 set when a non-canonical (>= r) input is seen
     int rows_per_slice;        // rows handled by one blockIdx.y slice
     int in_chunk_major;        // 1: in_sc == 1 (tile is contiguous), 0: in_sb == 1 (sender-major)
+    const unsigned int *item_list;   // optional indirection: process items item_list[0 .. *item_count) instead of 0 .. B
+    const unsigned int *item_count;
 };
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
@@ -67,7 +69,8 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
     for (int i = tid; i < nrows * C * 2; i += blockDim.x) sM[i] = a.M[(size_t)r0 * C * 2 + i];
 
     const long long TILE = TBT * 32;
-    const long long ntiles = (a.B + TILE - 1) / TILE;
+    const long long NB = a.item_list ? (long long)*a.item_count : a.B;  // items to process
+    const long long ntiles = (NB + TILE - 1) / TILE;
     const int nitems = nrows * TBT;
     const bool checks_here = r0 < a.n_chk;
 
@@ -82,7 +85,8 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
             else { bl = (i >> 1) % (TBT * 32); c = (i >> 1) / (TBT * 32); }
             long long b = b0 + bl;
             uint4 v = make_uint4(0, 0, 0, 0);
-            if (b < a.B) {
+            if (b < NB) {
+                if (a.item_list) b = a.item_list[b];
                 int j = a.col_map ? a.col_map[c] : c;
                 v = ldg_stream(a.in + (b * a.in_sb + (long long)j * a.in_sc) * 2 + half);
             }
@@ -97,7 +101,9 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
         for (int item = warp; item < nitems; item += W) {
             const int rl = item / TBT, sub = item - rl * TBT;
             const int r = r0 + rl;
-            const long long b = b0 + sub * 32 + lane;
+            long long b = b0 + sub * 32 + lane;
+            const bool live = b < NB;
+            if (live && a.item_list) b = a.item_list[b];
             const uint4 *Mrow = sM + (size_t)rl * C * 2;
             const uint4 *Dsub = sD + (size_t)sub * C * 64 + lane;
             const bool is_chk = r < a.n_chk;
@@ -106,7 +112,7 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
             int chk_j = 0;
             if (is_chk) {
                 chk_j = a.chk_map[r];  // < 0: the row must evaluate to zero (degree check)
-                if (chk_j >= 0 && b < a.B) {
+                if (chk_j >= 0 && live) {
                     const uint4 *p = a.in + (b * a.in_sb + (long long)chk_j * a.in_sc) * 2;
                     y_lo = ldg_stream(p);
                     y_hi = ldg_stream(p + 1);
@@ -152,11 +158,11 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
                 uint32_t y[8];
                 load_fr(y, y_lo, y_hi);
                 bad |= geq_mod(y) ? 1u : 0u;
-                if (b < a.B && !fr_eq(res, y)) {
+                if (live && !fr_eq(res, y)) {
                     if (r < a.n_gate) sFail[sub * 32 + lane] = 1u;
                     if (a.flags && chk_j >= 0) atomicOr(&sFlags[(size_t)(sub * 32 + lane) * a.flag_words + (chk_j >> 6)], 1ull << (chk_j & 63));
                 }
-            } else if (b < a.B) {
+            } else if (live) {
                 uint4 *o = a.out + (b * a.out_sb + (long long)(r - a.n_chk) * a.out_sr) * 2;
                 stg_stream(o, make_uint4(res[0], res[1], res[2], res[3]));
                 stg_stream(o + 1, make_uint4(res[4], res[5], res[6], res[7]));
@@ -167,7 +173,8 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
             __syncthreads();
             for (int i = tid; i < TBT * 32; i += blockDim.x) {
                 long long b = b0 + i;
-                if (b < a.B) {
+                if (b < NB) {
+                    if (a.item_list) b = a.item_list[b];
                     if (a.fail && sFail[i]) a.fail[b] = 1;  // slices only ever raise the flag (buffer pre-zeroed by the host side)
                     if (a.flags)
                         for (int w = 0; w < a.flag_words; ++w) {

@@ -27,6 +27,11 @@ struct NttArgs {
     long long B, in_sb, in_sc, out_sb, out_sr;
     int cols, n;
     unsigned int *err;
+    // MODE 1 (inverse transform + degree check, the all-shares-present fast path of K3):
+    const int *in_map;     // domain index j -> record index of the share with id j (nullptr: identity)
+    const uint4 *scale;    // N^{-1} in Montgomery form
+    int m, mout;           // coefficients k < mout are stored (scaled), coefficients k >= m must vanish
+    unsigned char *fail;   // fail[b] = 1 when some coefficient k >= m is non-zero
 };
 
 __device__ __forceinline__ void ntt_butterfly(uint32_t (&u)[8], uint32_t (&v)[8], const uint4 *tw, int twidx) {
@@ -64,7 +69,29 @@ __device__ __forceinline__ void ntt_stages(uint32_t (&x)[E][8], const uint4 *tw,
 template <int LOGN>
 __host__ __device__ constexpr int ntt_g() { return LOGN < 3 ? LOGN : 3; }
 
-template <int LOGN>
+// one transformed value at natural-order position `pos` of item b
+template <int MODE>
+__device__ __forceinline__ void ntt_emit(const NttArgs &a, long long b, int pos, const uint32_t (&v)[8], const uint32_t (&sc)[8]) {
+    if (MODE == 0) {
+        if (pos < a.n) {
+            uint4 *o = a.out + (b * a.out_sb + (long long)pos * a.out_sr) * 2;
+            stg_stream(o, make_uint4(v[0], v[1], v[2], v[3]));
+            stg_stream(o + 1, make_uint4(v[4], v[5], v[6], v[7]));
+        }
+    } else {
+        if (pos < a.mout) {
+            uint32_t c[8];
+            mont_mul(c, v, sc);
+            uint4 *o = a.out + (b * a.out_sb + (long long)pos * a.out_sr) * 2;
+            stg_stream(o, make_uint4(c[0], c[1], c[2], c[3]));
+            stg_stream(o + 1, make_uint4(c[4], c[5], c[6], c[7]));
+        } else if (pos >= a.m) {
+            if (!fr_is_zero(v)) a.fail[b] = 1;
+        }
+    }
+}
+
+template <int LOGN, int MODE>
 __global__ void __launch_bounds__(256, 2) ntt_kernel(const NttArgs a) {
     constexpr int N = 1 << LOGN;
     constexpr int G = ntt_g<LOGN>();
@@ -84,6 +111,8 @@ __global__ void __launch_bounds__(256, 2) ntt_kernel(const NttArgs a) {
     uint4 *myD = sD + (size_t)item_l * 2 * PADN;
     const long long ntiles = (a.B + IPC - 1) / IPC;
     unsigned bad = 0;
+    uint32_t sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (MODE == 1) load_fr(sc, a.scale[0], a.scale[1]);
 
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long b = tile * IPC + item_l;
@@ -95,7 +124,8 @@ __global__ void __launch_bounds__(256, 2) ntt_kernel(const NttArgs a) {
             const int pos = tid_i * E + e;
             const int k = (int)(__brev((unsigned)pos) >> (32 - LOGN));
             if (active && k < a.cols) {
-                const uint4 *p = a.in + (b * a.in_sb + (long long)k * a.in_sc) * 2;
+                const int rec = (MODE == 1 && a.in_map) ? a.in_map[k] : k;
+                const uint4 *p = a.in + (b * a.in_sb + (long long)rec * a.in_sc) * 2;
                 load_fr(x[e], ldg_stream(p), ldg_stream(p + 1));
                 bad |= geq_mod(x[e]) ? 1u : 0u;
             } else {
@@ -108,11 +138,7 @@ __global__ void __launch_bounds__(256, 2) ntt_kernel(const NttArgs a) {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int pos = tid_i * E + e;
-                if (active && pos < a.n) {
-                    uint4 *o = a.out + (b * a.out_sb + (long long)pos * a.out_sr) * 2;
-                    stg_stream(o, make_uint4(x[e][0], x[e][1], x[e][2], x[e][3]));
-                    stg_stream(o + 1, make_uint4(x[e][4], x[e][5], x[e][6], x[e][7]));
-                }
+                if (active) ntt_emit<MODE>(a, b, pos, x[e], sc);
             }
         } else {
 #pragma unroll
@@ -157,11 +183,7 @@ __global__ void __launch_bounds__(256, 2) ntt_kernel(const NttArgs a) {
 #pragma unroll
                 for (int e = 0; e < EL; ++e) {
                     const int pos = base + e * h0;
-                    if (active && pos < a.n) {
-                        uint4 *o = a.out + (b * a.out_sb + (long long)pos * a.out_sr) * 2;
-                        stg_stream(o, make_uint4(y[e][0], y[e][1], y[e][2], y[e][3]));
-                        stg_stream(o + 1, make_uint4(y[e][4], y[e][5], y[e][6], y[e][7]));
-                    }
+                    if (active) ntt_emit<MODE>(a, b, pos, y[e], sc);
                 }
             }
             __syncwarp();  // the tile's buffer is reused by the next tile's pass 0 writes
