@@ -325,12 +325,153 @@ HB_DEV void acc_reduce(const acc_t &A, uint32_t (&out)[8]) {
     cond_sub_mod(out);
 }
 
-// Montgomery product: a*b*R^{-1} mod r (fully reduced)
-HB_DEV void mont_mul(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+// Montgomery product through the lazy accumulator (kept for the unit test of acc_mac / acc_reduce)
+HB_DEV void mont_mul_acc(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
     acc_t A;
     acc_zero(A);
     acc_mac(A, a, b);
     acc_reduce(A, d);
+}
+
+// ----------------------------------------------------------------------------------------------
+// mont_mul: a*b*R^{-1} mod r for ONE product (butterflies, decoder), interleaved multiply/reduce rows.
+// The running value T is kept as an even-aligned and an odd-aligned array of four 64-bit lanes (T = E + O*2^32); each row
+// adds a*b_i with two IMAD.WIDE carry chains, cancels the low limb with m = -T_0 (again two chains with the modulus)
+// and shifts by one limb by swapping the roles of the two arrays.  ~30 live registers instead of the ~50 of the lazy
+// 512-bit accumulator, so kernels built on it keep twice as many warps resident.  Inputs < 2^256 with a*b < r*2^256.
+// ----------------------------------------------------------------------------------------------
+// modulus limbs as PTX immediates (PTX does not accept the C "u" suffix)
+#define HB_PR0 "0x00000001"
+#define HB_PR1 "0xffffffff"
+#define HB_PR2 "0xfffe5bfe"
+#define HB_PR3 "0x53bda402"
+#define HB_PR4 "0x09a1d805"
+#define HB_PR5 "0x3339d808"
+#define HB_PR6 "0x299d7d48"
+#define HB_PR7 "0x73eda753"
+// row i >= 1:  (E: current even lanes with E0 == 0, O: current odd lanes)  ->  roles swapped (E holds the new odd lanes)
+HB_DEV void cios_row(unsigned long long &e0, unsigned long long &e1, unsigned long long &e2, unsigned long long &e3,
+                     unsigned long long &o0, unsigned long long &o1, unsigned long long &o2, unsigned long long &o3,
+                     const uint32_t (&a)[8], uint32_t bi) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t"
+        ".reg .u32 E0, E1, E2, E3, E4, E5, E6, E7, O0, O1, O2, O3, O4, O5, O6, O7, mi;\n\t"
+        "mov.b64 {E0, E1}, %0;\n\t"
+        "mov.b64 {E2, E3}, %1;\n\t"
+        "mov.b64 {E4, E5}, %2;\n\t"
+        "mov.b64 {E6, E7}, %3;\n\t"
+        "mov.b64 {O0, O1}, %4;\n\t"
+        "mov.b64 {O2, O3}, %5;\n\t"
+        "mov.b64 {O4, O5}, %6;\n\t"
+        "mov.b64 {O6, O7}, %7;\n\t"
+        // shift by one limb: new even = old odd (+ old E1 at position 0), new odd[j] = old E[j+2] + a[2j+1]*bi
+        "add.cc.u32 O0, O0, E1;\n\t"
+        "madc.lo.cc.u32 E0, %9, %16, E2;\n\t"
+        "madc.hi.cc.u32 E1, %9, %16, E3;\n\t"
+        "madc.lo.cc.u32 E2, %11, %16, E4;\n\t"
+        "madc.hi.cc.u32 E3, %11, %16, E5;\n\t"
+        "madc.lo.cc.u32 E4, %13, %16, E6;\n\t"
+        "madc.hi.cc.u32 E5, %13, %16, E7;\n\t"
+        "madc.lo.cc.u32 E6, %15, %16, 0;\n\t"
+        "madc.hi.u32 E7, %15, %16, 0;\n\t"
+        "mad.lo.cc.u32 O0, %8, %16, O0;\n\t"
+        "madc.hi.cc.u32 O1, %8, %16, O1;\n\t"
+        "madc.lo.cc.u32 O2, %10, %16, O2;\n\t"
+        "madc.hi.cc.u32 O3, %10, %16, O3;\n\t"
+        "madc.lo.cc.u32 O4, %12, %16, O4;\n\t"
+        "madc.hi.cc.u32 O5, %12, %16, O5;\n\t"
+        "madc.lo.cc.u32 O6, %14, %16, O6;\n\t"
+        "madc.hi.cc.u32 O7, %14, %16, O7;\n\t"
+        "addc.u32 E7, E7, 0;\n\t"
+        // Montgomery step: m = -T_0, T += m * r
+        "sub.u32 mi, 0, O0;\n\t"
+        "mad.lo.cc.u32 E0, mi, " HB_PR1 ", E0;\n\t"
+        "madc.hi.cc.u32 E1, mi, " HB_PR1 ", E1;\n\t"
+        "madc.lo.cc.u32 E2, mi, " HB_PR3 ", E2;\n\t"
+        "madc.hi.cc.u32 E3, mi, " HB_PR3 ", E3;\n\t"
+        "madc.lo.cc.u32 E4, mi, " HB_PR5 ", E4;\n\t"
+        "madc.hi.cc.u32 E5, mi, " HB_PR5 ", E5;\n\t"
+        "madc.lo.cc.u32 E6, mi, " HB_PR7 ", E6;\n\t"
+        "madc.hi.u32 E7, mi, " HB_PR7 ", E7;\n\t"
+        "mad.lo.cc.u32 O0, mi, " HB_PR0 ", O0;\n\t"
+        "madc.hi.cc.u32 O1, mi, " HB_PR0 ", O1;\n\t"
+        "madc.lo.cc.u32 O2, mi, " HB_PR2 ", O2;\n\t"
+        "madc.hi.cc.u32 O3, mi, " HB_PR2 ", O3;\n\t"
+        "madc.lo.cc.u32 O4, mi, " HB_PR4 ", O4;\n\t"
+        "madc.hi.cc.u32 O5, mi, " HB_PR4 ", O5;\n\t"
+        "madc.lo.cc.u32 O6, mi, " HB_PR6 ", O6;\n\t"
+        "madc.hi.cc.u32 O7, mi, " HB_PR6 ", O7;\n\t"
+        "addc.u32 E7, E7, 0;\n\t"
+        "mov.b64 %0, {E0, E1};\n\t"
+        "mov.b64 %1, {E2, E3};\n\t"
+        "mov.b64 %2, {E4, E5};\n\t"
+        "mov.b64 %3, {E6, E7};\n\t"
+        "mov.b64 %4, {O0, O1};\n\t"
+        "mov.b64 %5, {O2, O3};\n\t"
+        "mov.b64 %6, {O4, O5};\n\t"
+        "mov.b64 %7, {O6, O7};\n\t"
+        "}"
+        : "+l"(e0), "+l"(e1), "+l"(e2), "+l"(e3), "+l"(o0), "+l"(o1), "+l"(o2), "+l"(o3)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(bi));
+#else
+    // literal emulation of the instruction sequence above (32-bit limbs, explicit carry flag)
+    uint32_t E[8] = {(uint32_t)e0, (uint32_t)(e0 >> 32), (uint32_t)e1, (uint32_t)(e1 >> 32), (uint32_t)e2, (uint32_t)(e2 >> 32), (uint32_t)e3, (uint32_t)(e3 >> 32)};
+    uint32_t O[8] = {(uint32_t)o0, (uint32_t)(o0 >> 32), (uint32_t)o1, (uint32_t)(o1 >> 32), (uint32_t)o2, (uint32_t)(o2 >> 32), (uint32_t)o3, (uint32_t)(o3 >> 32)};
+    const uint32_t rl[8] = {HB_R0, HB_R1, HB_R2, HB_R3, HB_R4, HB_R5, HB_R6, HB_R7};
+    unsigned cf = 0;
+    auto addc = [&](uint32_t x, uint64_t y, bool use_cf) { uint64_t t = (uint64_t)x + y + (use_cf ? cf : 0); cf = (unsigned)(t >> 32); return (uint32_t)t; };
+    auto lo = [](uint32_t x, uint32_t y) { return (uint64_t)(uint32_t)((uint64_t)x * y); };
+    auto hi = [](uint32_t x, uint32_t y) { return (uint64_t)(((uint64_t)x * y) >> 32); };
+    O[0] = addc(O[0], E[1], false);
+    for (int j = 0; j < 3; ++j) { uint32_t x = a[2 * j + 1]; E[2 * j] = addc(E[2 * j + 2], lo(x, bi), true); E[2 * j + 1] = addc(E[2 * j + 3], hi(x, bi), true); }
+    E[6] = addc(0, lo(a[7], bi), true);
+    E[7] = addc(0, hi(a[7], bi), true);
+    for (int j = 0; j < 4; ++j) { uint32_t x = a[2 * j]; O[2 * j] = addc(O[2 * j], lo(x, bi), j > 0); O[2 * j + 1] = addc(O[2 * j + 1], hi(x, bi), true); }
+    E[7] = addc(E[7], 0, true);
+    uint32_t mi = 0u - O[0];
+    for (int j = 0; j < 4; ++j) { uint32_t x = rl[2 * j + 1]; E[2 * j] = addc(E[2 * j], lo(mi, x), j > 0); E[2 * j + 1] = addc(E[2 * j + 1], hi(mi, x), true); }
+    for (int j = 0; j < 4; ++j) { uint32_t x = rl[2 * j]; O[2 * j] = addc(O[2 * j], lo(mi, x), j > 0); O[2 * j + 1] = addc(O[2 * j + 1], hi(mi, x), true); }
+    E[7] = addc(E[7], 0, true);
+    e0 = E[0] | ((unsigned long long)E[1] << 32); e1 = E[2] | ((unsigned long long)E[3] << 32);
+    e2 = E[4] | ((unsigned long long)E[5] << 32); e3 = E[6] | ((unsigned long long)E[7] << 32);
+    o0 = O[0] | ((unsigned long long)O[1] << 32); o1 = O[2] | ((unsigned long long)O[3] << 32);
+    o2 = O[4] | ((unsigned long long)O[5] << 32); o3 = O[6] | ((unsigned long long)O[7] << 32);
+#endif
+}
+
+HB_DEV void mont_mul(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    unsigned long long E[4], O[4];
+    // row 0: E = a[0,2,4,6]*b0, O = a[1,3,5,7]*b0, then the Montgomery step
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        E[j] = (unsigned long long)a[2 * j] * b[0];
+        O[j] = (unsigned long long)a[2 * j + 1] * b[0];
+    }
+    {
+        const uint32_t mi = 0u - (uint32_t)E[0];
+        uint32_t k0 = 0, k1 = 0;
+        chain4w(O[0], O[1], O[2], O[3], k0, HB_R1, HB_R3, HB_R5, HB_R7, mi);
+        chain4w(E[0], E[1], E[2], E[3], k1, HB_R0, HB_R2, HB_R4, HB_R6, mi);
+        O[3] += (unsigned long long)k1 << 32;  // carry out of position 7 enters position 8 (k0 cannot occur: T < 2^257)
+        (void)k0;
+    }
+    cios_row(E[0], E[1], E[2], E[3], O[0], O[1], O[2], O[3], a, b[1]);  // now O = even, E = odd
+    cios_row(O[0], O[1], O[2], O[3], E[0], E[1], E[2], E[3], a, b[2]);  // E = even
+    cios_row(E[0], E[1], E[2], E[3], O[0], O[1], O[2], O[3], a, b[3]);
+    cios_row(O[0], O[1], O[2], O[3], E[0], E[1], E[2], E[3], a, b[4]);
+    cios_row(E[0], E[1], E[2], E[3], O[0], O[1], O[2], O[3], a, b[5]);
+    cios_row(O[0], O[1], O[2], O[3], E[0], E[1], E[2], E[3], a, b[6]);
+    cios_row(E[0], E[1], E[2], E[3], O[0], O[1], O[2], O[3], a, b[7]);  // O = even (O0 low limb == 0), E = odd
+    // result = (even >> 32) + odd  (< 2r), then one conditional subtraction
+    uint32_t x[8], y[8], sres[8];
+    x[0] = (uint32_t)(O[0] >> 32); x[1] = (uint32_t)O[1]; x[2] = (uint32_t)(O[1] >> 32); x[3] = (uint32_t)O[2];
+    x[4] = (uint32_t)(O[2] >> 32); x[5] = (uint32_t)O[3]; x[6] = (uint32_t)(O[3] >> 32); x[7] = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { y[2 * j] = (uint32_t)E[j]; y[2 * j + 1] = (uint32_t)(E[j] >> 32); }
+    add8(sres, x, y);
+    cond_sub_mod(sres);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = sres[i];
 }
 
 // R^2 mod r (to Montgomery form: mont_mul(x, R2)); 1 (from Montgomery form: mont_mul(x, 1))

@@ -42,11 +42,12 @@ int main(int argc, char **argv) {
         printf(" "); print(out); printf("\n");
     }
     // mont_mul / add / sub
-    for (int t = 0; t < 8; ++t) {
+    for (int t = 0; t < 64; ++t) {
         uint32_t a[8], b[8], m[8], s[8], d[8];
         rnd(a, t == 0 ? 1 : 0); rnd(b, t == 1 ? 2 : (t == 0 ? 1 : 0));
-        hb::mont_mul(m, a, b); hb::fr_add(s, a, b); hb::fr_sub(d, a, b);
-        printf("ops "); print(a); printf(" "); print(b); printf(" "); print(m); printf(" "); print(s); printf(" "); print(d); printf("\n");
+        hb::mont_mul_acc(m, a, b); hb::fr_add(s, a, b); hb::fr_sub(d, a, b);
+        uint32_t mc[8]; hb::mont_mul(mc, a, b);
+        printf("ops "); print(a); printf(" "); print(b); printf(" "); print(m); printf(" "); print(s); printf(" "); print(d); printf(" "); print(mc); printf("\n");
     }
     return 0;
 }

@@ -17,8 +17,9 @@ def test_fr_cuh_limb_logic(tmp_path):
         for ln in out:
             p = ln.split()
             if p[0] == "ops":
-                a, b, m, s, d = (int(x, 16) for x in p[1:6])
+                a, b, m, s, d, mc = (int(x, 16) for x in p[1:7])
                 assert m == a * b * RINV % R and s == (a + b) % R and d == (a - b) % R
+                assert mc == m, "mont_mul_cios differs"
                 n_ops += 1
             else:
                 terms = int(p[0])
@@ -26,4 +27,4 @@ def test_fr_cuh_limb_logic(tmp_path):
                 acc = sum(vals[2 * k] * vals[2 * k + 1] for k in range(terms))
                 assert vals[-1] == acc * RINV % R, f"terms={terms}"
                 n_acc += 1
-        assert n_acc == 10 and n_ops == 8
+        assert n_acc == 10 and n_ops == 64
