@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhbmpc_b200.so")
+LIB_PATH = os.environ.get("HBMPC_LIB") or os.path.join(_HERE, "libhbmpc_b200.so")  # HBMPC_LIB: tuning builds only
 
 # ShareErrorCode (ffi/c_bindings/share/mod.rs:18-37) + library codes
 SUCCESS, INSUFFICIENT_SHARES, DEGREE_MISMATCH, ID_MISMATCH, INVALID_INPUT = 0, 1, 2, 3, 4

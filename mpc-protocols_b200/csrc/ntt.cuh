@@ -66,8 +66,16 @@ __device__ __forceinline__ void ntt_stages(uint32_t (&x)[E][8], const uint4 *tw,
     }
 }
 
+// butterfly stages per pass (2^G register-resident elements per thread).  G = 2 keeps the kernel at <= 80 registers so
+// three CTAs (24 warps) stay resident per SM; N = 256 needs G = 3 to keep one item inside one warp.
+#ifndef HB_NTT_G
+#define HB_NTT_G 2
+#endif
+#ifndef HB_NTT_MINB
+#define HB_NTT_MINB 3
+#endif
 template <int LOGN>
-__host__ __device__ constexpr int ntt_g() { return LOGN < 3 ? LOGN : 3; }
+__host__ __device__ constexpr int ntt_g() { return LOGN < HB_NTT_G ? LOGN : (LOGN >= 8 ? 3 : HB_NTT_G); }
 
 // one transformed value at natural-order position `pos` of item b
 template <int MODE>
@@ -92,7 +100,7 @@ __device__ __forceinline__ void ntt_emit(const NttArgs &a, long long b, int pos,
 }
 
 template <int LOGN, int MODE>
-__global__ void __launch_bounds__(256, 2) ntt_kernel(const NttArgs a) {
+__global__ void __launch_bounds__(256, HB_NTT_MINB) ntt_kernel(const NttArgs a) {
     constexpr int N = 1 << LOGN;
     constexpr int G = ntt_g<LOGN>();
     constexpr int E = 1 << G;
