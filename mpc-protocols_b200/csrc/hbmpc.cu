@@ -156,8 +156,9 @@ struct RecoverTables {
     // robust
     int rmax = 0, fast = 0, nsyn_max = 0;
     int *att_P = nullptr, *att_nsyn = nullptr, *att_maxL = nullptr, *order = nullptr;
-    long long *att_Hoff = nullptr, *att_uoff = nullptr;
-    uint4 *H = nullptr, *uinv = nullptr, *xs = nullptr, *xinv = nullptr, *Lc = nullptr, *Veval = nullptr;
+    long long *att_uoff = nullptr;
+    int *sid = nullptr;
+    uint4 *u2 = nullptr, *tw = nullptr, *ritw = nullptr, *uinv = nullptr, *xs = nullptr, *xinv = nullptr, *Lc = nullptr, *Veval = nullptr;
     // all-shares-present fast path (S == n == N): inverse NTT + degree check
     int fast_logn = 0;
     int *in_map = nullptr;
@@ -685,8 +686,8 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
     T.fast = T.rmax >= 1 ? 1 : 0;
     const int natt = 1 + T.rmax;
     std::vector<int> att_P(natt), att_nsyn(natt), att_maxL(natt);
-    std::vector<long long> att_Hoff(natt), att_uoff(natt);
-    std::vector<HFr> H, U;
+    std::vector<long long> att_uoff(natt);
+    std::vector<HFr> U2, U;
     // uinv_i^{(P)} = prod_{l<P, l != i} (x_i - x_l), built incrementally over P
     std::vector<HFr> uinv;
     auto extend_to = [&](size_t P) {
@@ -705,21 +706,12 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
         att_P[a] = (int)P;
         att_nsyn[a] = (int)nsyn;
         att_maxL[a] = (int)maxL;
-        att_Hoff[a] = (long long)H.size();
         att_uoff[a] = (long long)U.size();
         std::vector<HFr> u(uinv.begin(), uinv.begin() + P);
         HFr one_c = {{1, 0, 0, 0}};
         for (size_t i = 0; i < P; ++i) U.push_back(hfr::mul(u[i], one_c));  // canonical
         hfr::batch_inv(u);
-        size_t base = H.size();
-        H.resize(base + nsyn * P);
-        for (size_t i = 0; i < P; ++i) {
-            HFr p = hfr::mul(u[i], hfr::R2);  // u_i * R^2
-            for (size_t j = 0; j < nsyn; ++j) {
-                H[base + j * P + i] = p;
-                p = hfr::mul(p, xs[i]);
-            }
-        }
+        for (size_t i = 0; i < P; ++i) U2.push_back(hfr::mul(u[i], hfr::R2));  // u_i * R^2
         T.nsyn_max = std::max(T.nsyn_max, (int)nsyn);
     };
     if (T.rmax >= 1) {
@@ -731,7 +723,7 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
         extend_to(S);
         emit(0, S, S - m, std::min(t, (S - m) / 2));
     } else {
-        att_P[0] = (int)S; att_nsyn[0] = 0; att_maxL[0] = 0; att_Hoff[0] = 0; att_uoff[0] = 0;
+        att_P[0] = (int)S; att_nsyn[0] = 0; att_maxL[0] = 0; att_uoff[0] = 0;
     }
     std::vector<HFr> xinv(xs);
     hfr::batch_inv(xinv);
@@ -739,9 +731,16 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
     if ((rc = upload(ctx, att_P, &T.att_P))) return rc;
     if ((rc = upload(ctx, att_nsyn, &T.att_nsyn))) return rc;
     if ((rc = upload(ctx, att_maxL, &T.att_maxL))) return rc;
-    if ((rc = upload(ctx, att_Hoff, &T.att_Hoff))) return rc;
     if ((rc = upload(ctx, att_uoff, &T.att_uoff))) return rc;
-    if ((rc = upload_fr(ctx, H, &T.H))) return rc;
+    if ((rc = upload_fr(ctx, U2, &T.u2))) return rc;
+    {
+        std::vector<int> sid(S);
+        for (size_t i = 0; i < S; ++i) sid[i] = (int)sorted_ids[i];
+        if ((rc = upload(ctx, sid, &T.sid))) return rc;
+        uint4 *sc = nullptr;
+        if ((rc = get_twiddles(ctx, domain_size(n), &T.tw))) return rc;
+        if ((rc = get_inverse_twiddles(ctx, domain_size(n), &T.ritw, &sc))) return rc;
+    }
     if ((rc = upload_fr(ctx, U, &T.uinv))) return rc;
     if ((rc = upload_fr(ctx, xs, &T.xs))) return rc;
     if ((rc = upload_fr(ctx, xinv, &T.xinv))) return rc;
@@ -803,7 +802,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
     BatchBuf bp = make_buf(path, B, 1, false, 4);
     BatchBuf bf = make_buf(flags, B, fw > 0 ? fw : 1, false, 8);
     BatchBuf bs = make_buf(want_secrets ? secrets : nullptr, B, 1, false);
-    const WsLayout lay(T.nsyn_max, (int)t);
+    const WsLayout lay(T.nsyn_max, (int)t, domain_size(n));
 
     auto body = [&](Lane &ln, size_t b0, size_t Bc) -> int {
         ChunkView vi, vc, vp, vf, vs;
@@ -886,8 +885,9 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         r.list = list;
         r.count = count;
         r.S = (int)S; r.m = (int)m; r.t = (int)t; r.needed = (int)needed; r.rmax = T.rmax; r.fast = T.fast;
-        r.att_P = T.att_P; r.att_nsyn = T.att_nsyn; r.att_maxL = T.att_maxL; r.att_Hoff = T.att_Hoff; r.att_uoff = T.att_uoff;
-        r.H = T.H; r.uinv = T.uinv; r.xs = T.xs; r.xinv = T.xinv; r.Lc = T.Lc; r.Veval = T.Veval; r.order = T.order;
+        r.att_P = T.att_P; r.att_nsyn = T.att_nsyn; r.att_maxL = T.att_maxL; r.att_uoff = T.att_uoff;
+        r.u2 = T.u2; r.sid = T.sid; r.tw = T.tw; r.itw = T.ritw; r.uinv = T.uinv;
+        { int lg = 0; while ((1 << lg) < domain_size(n)) ++lg; r.logn = lg; } r.xs = T.xs; r.xinv = T.xinv; r.Lc = T.Lc; r.Veval = T.Veval; r.order = T.order;
         r.coeffs = (uint4 *)vc.dev;
         r.mout = T.mout;
         r.path = (int *)vp.dev;

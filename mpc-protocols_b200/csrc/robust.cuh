@@ -18,6 +18,11 @@
 //   exact path : if the fast attempt fails (more than maxL errors overall), attempts r = 1..rmax on the prefixes
 //                P_r with maxL = r -- the literal OEC loop.
 //
+// All evaluation points are N-th roots of unity, so the three "evaluate at every point" steps are size-N transforms:
+//   syndromes  S_j = sum_i (u_i y_i) w^(id_i j)        = forward NTT of the weighted word (first nsyn outputs),
+//   Chien      Lambda(w^(-id))                          = inverse-direction NTT of Lambda's coefficients,
+//   Forney     Omega(w^(-id)), Lambda'(w^(-id))         = two more (when the locator is long enough to pay off),
+// ~N/2*log2(N) products each instead of nsyn*P, P*L and 2*L^2.
 // One thread decodes one codeword; per-thread polynomials live in a strided global workspace (coalesced across the
 // warp).  The corrected coefficients are obtained by linearity from what the optimistic kernel already wrote:
 //   coeffs(f) = Lc * y[0..m) - sum_{i in E, i<m} e_i * Lc[:, i].
@@ -39,10 +44,13 @@ struct RobustArgs {
     const int *att_P;           // [1 + rmax] prefix size per attempt (index 0 = fast path)
     const int *att_nsyn;        // [1 + rmax]
     const int *att_maxL;        // [1 + rmax]
-    const long long *att_Hoff;  // [1 + rmax] offset (in elements) of the attempt's H matrix [nsyn][P]
-    const long long *att_uoff;  // [1 + rmax] offset of the attempt's uinv vector [P]
-    const uint4 *H;             // (u_i x_i^j) * R^2: canonical y times this gives a Montgomery-form syndrome
+    const long long *att_uoff;  // [1 + rmax] offset of the attempt's u2 / uinv vectors [P]
+    const uint4 *u2;            // u_i * R^2: canonical y_i times this is the Montgomery form of u_i*y_i
     const uint4 *uinv;          // prod_{l != i, l < P} (x_i - x_l), canonical (Montgomery c times this is canonical e)
+    const int *sid;             // [S] domain index (share id) of sorted position i
+    const uint4 *tw;            // [N/2] w^k   (Montgomery)
+    const uint4 *itw;           // [N/2] w^-k  (Montgomery)
+    int logn;                   // N = 1 << logn
     const uint4 *xs;            // [S] x_i (Montgomery), sorted by id
     const uint4 *xinv;          // [S] x_i^{-1} (Montgomery)
     const uint4 *Lc;            // [m][m] Lagrange coefficient matrix of the lowest m ids (Montgomery)
@@ -105,9 +113,9 @@ __device__ __noinline__ void fr_inv_mont(uint32_t (&out)[8], const uint32_t (&a)
 // workspace slots (element offsets) -- sized by the host with the same formulae
 struct WsLayout {
     int syn, lam, bp, om, num, den, pre, ev, total;
-    __host__ __device__ WsLayout(int nsyn_max, int t) {
-        syn = 0;
-        lam = syn + nsyn_max;
+    __host__ __device__ WsLayout(int nsyn_max, int t, int N) {
+        syn = 0;  // transform buffer of N elements; the syndromes are its first nsyn entries
+        lam = syn + (nsyn_max > N ? nsyn_max : N);
         bp = lam + (t + 2);
         om = bp + (t + 2);
         num = om + (t + 1);
@@ -118,30 +126,58 @@ struct WsLayout {
     }
 };
 
+// In-place radix-2 decimation-in-time transform of the N workspace elements at `slot0` (input in bit-reversed order,
+// output in natural order), twiddles tw[k] = g^k in Montgomery form: out[j] = sum_p in_natural[p] * g^(p j).
+__device__ __noinline__ void ntt_serial(const FrWs &ws, int slot0, int logn, const uint4 *tw) {
+    const int N = 1 << logn;
+#pragma unroll 1
+    for (int s = 0; s < logn; ++s) {
+        const int half = 1 << s, tws = logn - 1 - s;
+#pragma unroll 1
+        for (int i = 0; i < (N >> 1); ++i) {
+            const int j = i & (half - 1);
+            const int pos = ((i >> s) << (s + 1)) | j;
+            uint32_t u[8], v[8], t[8], sm[8], df[8];
+            ws.ld(u, slot0 + pos);
+            ws.ld(v, slot0 + pos + half);
+            if (j) {
+                uint32_t w[8];
+                ldg_fr(w, tw + ((size_t)(j << tws)) * 2);
+                mont_mul(t, v, w);
+            } else {
+                copy8(t, v);
+            }
+            fr_add(sm, u, t);
+            fr_sub(df, u, t);
+            ws.st(slot0 + pos, sm);
+            ws.st(slot0 + pos + half, df);
+        }
+    }
+}
+__device__ __forceinline__ int bitrev_n(int x, int logn) { return (int)(__brev((unsigned)x) >> (32 - logn)); }
+
 // One bounded-distance decoding attempt.  Returns the number of errors L (positions in rootpos[0..L), ascending sorted
 // position; canonical error values in ws[ev + q]) or -1.
 __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b, const FrWs &ws, const WsLayout &lay, int *rootpos) {
     const int P = a.att_P[att], nsyn = a.att_nsyn[att], maxL = a.att_maxL[att];
-    const uint4 *H = a.H + a.att_Hoff[att] * 2;
+    const int N = 1 << a.logn;
+    const uint4 *U2 = a.u2 + a.att_uoff[att] * 2;
     const uint4 *ybase = a.in + b * a.in_sb * 2;
+    uint32_t zero[8];
+    set_zero(zero);
 
-    // ---- syndromes (Montgomery form)
+    // ---- syndromes (Montgomery form): forward transform of the weighted word, S_j = sum_i (u_i y_i) w^(id_i j)
 #pragma unroll 1
-    for (int j = 0; j < nsyn; ++j) {
-        acc_t A;
-        acc_zero(A);
-        const uint4 *Hrow = H + (size_t)j * P * 2;
+    for (int p = 0; p < N; ++p) ws.st(lay.syn + p, zero);
 #pragma unroll 1
-        for (int i = 0; i < P; ++i) {
-            uint32_t y[8], h[8];
-            ldg_fr(y, ybase + (long long)a.order[i] * a.in_sc * 2);
-            ldg_fr(h, Hrow + i * 2);
-            acc_mac(A, y, h);
-        }
-        uint32_t s[8];
-        acc_reduce(A, s);
-        ws.st(lay.syn + j, s);
+    for (int i = 0; i < P; ++i) {
+        uint32_t y[8], u[8], w[8];
+        ldg_fr(y, ybase + (long long)a.order[i] * a.in_sc * 2);
+        ldg_fr(u, U2 + i * 2);
+        mont_mul(w, y, u);
+        ws.st(lay.syn + bitrev_n(a.sid[i], a.logn), w);
     }
+    ntt_serial(ws, lay.syn, a.logn, a.tw);
 
     // ---- inversion-free Berlekamp-Massey:  Lambda <- bdis*Lambda - delta * z^shift * Bp
     uint32_t one[8], bdis[8];
@@ -198,19 +234,54 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
     }
     if (L == 0) return 0;
 
+    // ---- Forney numerator polynomial first (it needs the syndromes, which share the transform buffer):
+    //      Omega = S*Lambda mod z^L
+#pragma unroll 1
+    for (int l = 0; l < L; ++l) {
+        acc_t A;
+        acc_zero(A);
+#pragma unroll 1
+        for (int k = 0; k <= l; ++k) {
+            uint32_t x[8], sy[8];
+            ws.ld(x, lay.lam + k);
+            ws.ld(sy, lay.syn + l - k);
+            acc_mac(A, x, sy);
+        }
+        uint32_t o[8];
+        acc_reduce(A, o);
+        ws.st(lay.om + l, o);
+    }
+
     // ---- Chien search over the prefix points: Lambda(x_i^{-1}) == 0  <=>  position i is in error
     int nroots = 0;
+    const bool chien_ntt = L >= 4;
+    if (chien_ntt) {  // all N values Lambda(w^-j) with one inverse-direction transform
+#pragma unroll 1
+        for (int p = 0; p < N; ++p) ws.st(lay.syn + p, zero);
+#pragma unroll 1
+        for (int l = 0; l <= L; ++l) {
+            uint32_t c[8];
+            ws.ld(c, lay.lam + l);
+            ws.st(lay.syn + bitrev_n(l, a.logn), c);
+        }
+        ntt_serial(ws, lay.syn, a.logn, a.itw);
+    }
 #pragma unroll 1
     for (int i = 0; i < P; ++i) {
-        uint32_t z[8], v[8];
-        ldg_fr(z, a.xinv + i * 2);
-        ws.ld(v, lay.lam + L);
+        uint32_t v[8];
+        if (chien_ntt) {
+            ws.ld(v, lay.syn + a.sid[i]);
+        } else {
+            uint32_t z[8];
+            ldg_fr(z, a.xinv + i * 2);
+            ws.ld(v, lay.lam + L);
 #pragma unroll 1
-        for (int l = L - 1; l >= 0; --l) {
-            uint32_t c[8], p[8];
-            mont_mul(p, v, z);
-            ws.ld(c, lay.lam + l);
-            fr_add(v, p, c);
+            for (int l = L - 1; l >= 0; --l) {
+                uint32_t c[8], p[8];
+                mont_mul(p, v, z);
+                ws.ld(c, lay.lam + l);
+                fr_add(v, p, c);
+            }
         }
         if (fr_is_zero(v)) {
             if (nroots < L) rootpos[nroots] = i;
@@ -219,28 +290,59 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
     }
     if (nroots != L) return -1;
 
-    // ---- Forney.  Omega = S*Lambda mod z^L;  c_i = -x_i Omega(x_i^{-1}) / Lambda'(x_i^{-1});  e_i = c_i * uinv_i
-#pragma unroll 1
-    for (int l = 0; l < L; ++l) {
-        acc_t A;
-        acc_zero(A);
-#pragma unroll 1
-        for (int k = 0; k <= l; ++k) {
-            uint32_t x[8], s[8];
-            ws.ld(x, lay.lam + k);
-            ws.ld(s, lay.syn + l - k);
-            acc_mac(A, x, s);
-        }
-        uint32_t o[8];
-        acc_reduce(A, o);
-        ws.st(lay.om + l, o);
-    }
+    // ---- Forney:  c_i = -x_i Omega(x_i^{-1}) / Lambda'(x_i^{-1});  e_i = c_i * uinv_i
     uint32_t Lm[8];  // Montgomery form of the integer L
     set_zero(Lm);
 #pragma unroll 1
     for (int l = 0; l < L; ++l) { uint32_t tsum[8]; fr_add(tsum, Lm, one); copy8(Lm, tsum); }
     uint32_t run[8];
     copy8(run, one);
+    const bool forney_ntt = L > 24;
+    if (forney_ntt) {
+        // numerators: Omega at every w^-j
+#pragma unroll 1
+        for (int p = 0; p < N; ++p) ws.st(lay.syn + p, zero);
+#pragma unroll 1
+        for (int l = 0; l < L; ++l) {
+            uint32_t c[8];
+            ws.ld(c, lay.om + l);
+            ws.st(lay.syn + bitrev_n(l, a.logn), c);
+        }
+        ntt_serial(ws, lay.syn, a.logn, a.itw);
+#pragma unroll 1
+        for (int q = 0; q < L; ++q) {
+            uint32_t v[8], x[8], numv[8];
+            ws.ld(v, lay.syn + a.sid[rootpos[q]]);
+            ldg_fr(x, a.xs + rootpos[q] * 2);
+            mont_mul(numv, v, x);
+            ws.st(lay.num + q, numv);
+        }
+        // denominators: Lambda'(z) = sum_{l>=1} l * Lambda_l z^(l-1) at every w^-j
+#pragma unroll 1
+        for (int p = 0; p < N; ++p) ws.st(lay.syn + p, zero);
+        uint32_t lm[8];
+        copy8(lm, one);
+#pragma unroll 1
+        for (int l = 1; l <= L; ++l) {
+            uint32_t c[8], lc[8], nl[8];
+            ws.ld(c, lay.lam + l);
+            mont_mul(lc, c, lm);
+            ws.st(lay.syn + bitrev_n(l - 1, a.logn), lc);
+            fr_add(nl, lm, one);
+            copy8(lm, nl);
+        }
+        ntt_serial(ws, lay.syn, a.logn, a.itw);
+#pragma unroll 1
+        for (int q = 0; q < L; ++q) {
+            uint32_t dv[8], nr[8];
+            ws.ld(dv, lay.syn + a.sid[rootpos[q]]);
+            if (fr_is_zero(dv)) return -1;
+            ws.st(lay.den + q, dv);
+            ws.st(lay.pre + q, run);
+            mont_mul(nr, run, dv);
+            copy8(run, nr);
+        }
+    } else {
 #pragma unroll 1
     for (int q = 0; q < L; ++q) {
         const int i = rootpos[q];
@@ -279,6 +381,7 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
         mont_mul(nr, run, dv);
         copy8(run, nr);
     }
+    }
     uint32_t inv[8];
     fr_inv_mont(inv, run);
     const uint4 *U = a.uinv + a.att_uoff[att] * 2;
@@ -310,7 +413,7 @@ __global__ void __launch_bounds__(128) robust_kernel(const RobustArgs a) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int nsyn_max = 0;
     for (int i = a.fast ? 0 : 1; i <= a.rmax; ++i) nsyn_max = max(nsyn_max, a.att_nsyn[i]);
-    const WsLayout lay(nsyn_max, a.t);
+    const WsLayout lay(nsyn_max, a.t, 1 << a.logn);
     FrWs ws{a.ws + g * 2, T};
     int rootpos[HB_ROBUST_MAXT];
 
