@@ -287,7 +287,7 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     t_e2e = te.item()
-    h2d = Be * M * 32 + Be * N_PARTIES * 32
+    h2d = Be * M * 32 + Be * needed * 32  # coefficients in; of the 64 sender vectors the library uploads only the 43 it examines
     d2h = Be * N_PARTIES * 32 + Be * M * 32 + Be * 4
 
     # ---- NCCL gather of the reconstructed secrets (the only collective; outside the hot path)
@@ -325,12 +325,24 @@ def run_b200(args):
         shares_per_step = 2 * B * N_PARTIES
         value = n_gpus * args.steps * shares_per_step / t_tot
         gen_launch_s = t_gen / args.steps
-        rec_launch_s = t_dense  # the dense matvec launch (43 senders); the 64-sender call runs ntt_kernel<6,1> instead
+        rec_launch_s = t_rec / args.steps
         hbm = measured_hbm()
-        # dominant kernel of the step: matvec_kernel (the recon launch: 43 check/coefficient rows x 22 terms per chunk)
         rec_alg_imad = B * ALG_MODMUL_REC * IMAD_PER_MODMUL
-        rec_exec_wide = B * ((T_FAULTS + M) * M + (T_FAULTS + M)) * 64  # IMAD.WIDE issued: 64 per term + 64 per reduction
         gen_alg_imad = B * ALG_MODMUL_GEN * IMAD_PER_MODMUL
+        # executed IMAD.WIDE (32x32->64 multiply-add) counts per secret: one Montgomery product = 8 rows x 16 = 128 wide;
+        # 64-point radix-2 NTT: 129 non-trivial twiddle products (+22 scalings by 1/N in the inverse); dense: 64 per term + 64 per reduction
+        NTT_MULS = 129
+        gen_exec_wide = B * NTT_MULS * 128
+        rec_exec_wide = B * (NTT_MULS + M) * 128
+        dense_exec_wide = B * ((T_FAULTS + M) * M + (T_FAULTS + M)) * 64
+        traffic = ncu_traffic()
+        def roof(kernel, alg_imad, exec_wide, secs, nbytes, note, tkey):
+            return {"kernel": kernel, "bound": "int32-imad", "achieved": alg_imad / secs / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
+                    "frac": alg_imad / secs / imad_peak, "how": note,
+                    "executed_wide_tinst": exec_wide / secs / 1e12, "imad_wide_peak_tinst": imad_wide_peak / 1e12,
+                    "executed_frac_of_imad_wide_peak": exec_wide / secs / imad_wide_peak,
+                    "hbm_gbs": nbytes / secs / 1e9, "hbm_frac": nbytes / secs / 1e9 / hbm, "algorithmic_bytes": nbytes,
+                    "traffic": (traffic[tkey] * B / (1 << 20)) if tkey in traffic else None}
         line = {
             "metric": "Fr shares generated+reconstructed per second (n=64,t=21)", "value": value, "unit": "shares/s",
             "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
@@ -341,18 +353,14 @@ def run_b200(args):
                           "alg_modmul_per_s": n_gpus * args.steps * B * (ALG_MODMUL_GEN + ALG_MODMUL_REC) / t_tot, "gather_ms": gather_ms,
                           "recon_43_senders_dense_ms": 1e3 * t_dense,
                           "recon_note": "recon_ms: all 64 senders supplied -> inverse-NTT + degree check (bit-identical; items that fail fall back to the dense check); recon_43_senders_dense_ms: only d+t+1 senders supplied -> dense matvec_kernel"},
-            "roofline": {"kernel": "matvec_kernel<4> (K3 batch_recover launch: 43x22 check+coefficient matrix per chunk)", "bound": "int32-imad",
-                         "achieved": rec_alg_imad / rec_launch_s / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
-                         "frac": rec_alg_imad / rec_launch_s / imad_peak,
-                         "how": "algorithmic IMAD = B * 1430 modmul * 256 IMAD (SURVEY 8d) / CUDA-event launch time; peak = mad.lo.u32 probe measured in this run on this GPU",
-                         "executed_wide_tinst": rec_exec_wide / rec_launch_s / 1e12, "imad_wide_peak_tinst": imad_wide_peak / 1e12,
-                         "executed_frac_of_imad_wide_peak": rec_exec_wide / rec_launch_s / imad_wide_peak,
-                         "hbm_gbs": B * BYTES_REC / rec_launch_s / 1e9, "hbm_frac": B * BYTES_REC / rec_launch_s / 1e9 / hbm, "traffic": None},
-            "roofline_gen": {"kernel": "ntt_kernel<6> (K1 compute_shares launch: zero-padded 64-point NTT per secret)", "bound": "int32-imad",
-                             "achieved": gen_alg_imad / gen_launch_s / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
-                             "frac": gen_alg_imad / gen_launch_s / imad_peak,
-                             "how": "algorithmic IMAD = B * 1344 modmul * 256 IMAD (dense Horner count of SURVEY 8d; the NTT executes ~130 modmul per secret)",
-                             "hbm_gbs": B * BYTES_GEN / gen_launch_s / 1e9, "hbm_frac": B * BYTES_GEN / gen_launch_s / 1e9 / hbm, "traffic": None},
+            "roofline": roof("ntt_kernel<6,1> (K3 batch_recover launch, all 64 senders: inverse 64-point NTT + degree check per chunk)", rec_alg_imad, rec_exec_wide,
+                             rec_launch_s, B * (N_PARTIES * 32 + M * 32 + 5),
+                             "achieved = algorithmic IMAD (B * 1430 modmul * 256, SURVEY 8d dense count) / CUDA-event launch time; peak = mad.lo.u32 probe measured in this run; executed_* = IMAD.WIDE actually issued vs the IMAD.WIDE probe",
+                             "ntt_inv"),
+            "roofline_gen": roof("ntt_kernel<6,0> (K1 compute_shares launch: zero-padded 64-point NTT per secret)", gen_alg_imad, gen_exec_wide, gen_launch_s, B * BYTES_GEN,
+                                 "algorithmic IMAD = B * 1344 modmul * 256 (dense Horner count of SURVEY 8d)", "ntt_fwd"),
+            "roofline_dense": roof("matvec_kernel<4> (K3 batch_recover launch, 43 senders: 43x22 check+coefficient matrix per chunk)", rec_alg_imad, dense_exec_wide, t_dense,
+                                   B * BYTES_REC, "same algorithmic count, general dense path", "matvec"),
             "cpu_baseline": cpu,
             "e2e": {"value": n_gpus * e2e_steps * 2 * Be * N_PARTIES / t_e2e, "unit": "shares/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps, "host_buffers": "pinned"},
@@ -363,6 +371,14 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 2^20 from the committed ncu --set full capture (profiles/)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_per_2p20.json")))
+    except Exception:
+        return {}
 
 
 def measured_hbm():

@@ -177,10 +177,12 @@ struct hbmpc_ctx {
     int ntt_ctas[2][9] = {};                        // resident CTAs per SM of ntt_kernel<LOGN, MODE>
     bool no_fastpath = false;                       // HBMPC_NO_FASTPATH=1: K3 never takes the all-shares-present inverse-NTT path
     bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
-    size_t chunk_bytes = 24u << 20;                 // HBMPC_CHUNK_MB: target bytes per pipelined host copy
+    size_t chunk_bytes = 16u << 20;                 // HBMPC_CHUNK_MB: target bytes per pipelined host copy
     unsigned int *d_status = nullptr;  // [0] non-canonical input seen, [2] some item failed to decode
     unsigned int *h_status = nullptr;  // pinned
     cudaEvent_t ev_main = nullptr;
+    unsigned int *h_counts = nullptr;  // pinned: per-chunk count of items that failed the optimistic check (lean host path)
+    size_t h_counts_cap = 0;
     std::map<std::string, uint4 *> matrices;          // Vandermonde / twiddle tables keyed by "V n cols" / "W N"
     std::map<std::string, RecoverTables> recover;     // keyed by (n, d, t, ids, variant)
     std::map<std::string, struct NonRobustTables> *nonrobust = nullptr;
@@ -303,6 +305,7 @@ extern "C" void hbmpc_ctx_destroy(hbmpc_ctx *ctx) {
             if (b.p) cudaFree(b.p);
     if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
     delete ctx->nonrobust;
     for (int i = 0; i < NLANES; ++i)
@@ -355,6 +358,7 @@ struct BatchBuf {
     long long J = 0;
     size_t esz = 32;
     size_t B = 0;
+    const std::vector<int> *rows = nullptr;  // record-major host buffers: copy only these records (ascending); others stay stale
 };
 static BatchBuf make_buf(const void *p, size_t B, long long J, bool record_major, size_t esz = 32) {
     BatchBuf b;
@@ -385,8 +389,18 @@ static int chunk_prepare(hbmpc_ctx *ctx, Lane &ln, int slot, const BatchBuf &bb,
     if (bb.record_major) {
         v.sb = 1;
         v.sj = (long long)Bc;
-        if (copy_in)
+        if (copy_in && !bb.rows)
             CK(cudaMemcpy2DAsync(v.dev, Bc * bb.esz, (char *)bb.user + b0 * bb.esz, bb.B * bb.esz, Bc * bb.esz, (size_t)bb.J, cudaMemcpyHostToDevice, ln.stream));
+        if (copy_in && bb.rows) {
+            const std::vector<int> &r = *bb.rows;
+            for (size_t i = 0; i < r.size();) {  // one 2D copy per run of consecutive records
+                size_t k = i + 1;
+                while (k < r.size() && r[k] == r[k - 1] + 1) ++k;
+                CK(cudaMemcpy2DAsync((char *)v.dev + (size_t)r[i] * Bc * bb.esz, Bc * bb.esz, (char *)bb.user + ((size_t)r[i] * bb.B + b0) * bb.esz,
+                                     bb.B * bb.esz, Bc * bb.esz, k - i, cudaMemcpyHostToDevice, ln.stream));
+                i = k;
+            }
+        }
     } else {
         v.sb = bb.J;
         v.sj = 1;
@@ -407,16 +421,20 @@ static int chunk_commit(hbmpc_ctx *ctx, Lane &ln, const BatchBuf &bb, size_t b0,
 // Runs `body(lane, b0, Bc)` over the batch: one pass on lane 0 when every buffer is a device pointer, otherwise chunk by
 // chunk round-robin over lanes 1..3 so that host->device copies, kernels and device->host copies of neighbouring chunks
 // overlap.  Returns after the host buffers are complete (or, all-device in async mode, after enqueueing).
+static size_t pick_chunk(const hbmpc_ctx *ctx, size_t B, size_t max_item_bytes) {
+    size_t Bc = ctx->chunk_bytes / std::max<size_t>(max_item_bytes, 32);
+    Bc = std::max<size_t>(Bc & ~(size_t)255, 1024);
+    if (Bc >= B || B <= 4096) Bc = B;
+    return Bc;
+}
 template <typename Body>
-static int run_batched(hbmpc_ctx *ctx, size_t B, bool any_host, size_t max_item_bytes, Body body) {
+static int run_batched(hbmpc_ctx *ctx, size_t B, bool any_host, size_t max_item_bytes, Body body, bool collect = true) {
     if (!any_host) {
         int rc = body(ctx->lanes[0], (size_t)0, B);
         if (rc) return rc;
         return ctx->async ? HBMPC_SUCCESS : collect_status(ctx);
     }
-    size_t Bc = ctx->chunk_bytes / std::max<size_t>(max_item_bytes, 32);
-    Bc = std::max<size_t>(Bc & ~(size_t)255, 1024);
-    if (Bc >= B || B <= 4096) Bc = B;
+    const size_t Bc = pick_chunk(ctx, B, max_item_bytes);
     CK(cudaEventRecord(ctx->ev_main, ctx->main_stream()));
     for (int i = 1; i < NLANES; ++i) CK(cudaStreamWaitEvent(ctx->lanes[i].stream, ctx->ev_main, 0));
     int li = 0, rc = 0;
@@ -433,7 +451,7 @@ static int run_batched(hbmpc_ctx *ctx, size_t B, bool any_host, size_t max_item_
         }
     }
     if (rc) return rc;
-    return collect_status(ctx);
+    return collect ? collect_status(ctx) : HBMPC_SUCCESS;
 }
 
 // ------------------------------------------------------------------------------------------------ kernel launches
@@ -804,10 +822,31 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
     BatchBuf bs = make_buf(want_secrets ? secrets : nullptr, B, 1, false);
     const WsLayout lay(T.nsyn_max, (int)t, domain_size(n));
 
+    // Lean host path: when the shares arrive in host memory sender-major and no flags are wanted, only the d+t+1 examined
+    // sender vectors are uploaded and the dense optimistic check runs (PCIe, not the SMs, bounds such calls); chunks in which
+    // some item fails are re-run afterwards with every sender vector uploaded (robust decoding needs them all).
+    std::vector<int> lean_rows;
+    BatchBuf bi_lean = bi;
+    const bool lean = bi.host && sender_major && !want_flags && S > needed;
+    size_t chunk_full = 0;
+    if (lean) {
+        for (size_t i = 0; i < needed; ++i) lean_rows.push_back(order[i]);
+        std::sort(lean_rows.begin(), lean_rows.end());
+        bi_lean.rows = &lean_rows;
+        chunk_full = pick_chunk(ctx, B, std::max<size_t>(S, T.mout) * 32);
+        const size_t nchunks = (B + chunk_full - 1) / chunk_full;
+        if (ctx->h_counts_cap < nchunks) {
+            if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+            ctx->h_counts = nullptr;
+            CK(cudaMallocHost((void **)&ctx->h_counts, (nchunks + 64) * sizeof(unsigned int)));
+            ctx->h_counts_cap = nchunks + 64;
+        }
+    }
+    bool lean_phase = lean;
     auto body = [&](Lane &ln, size_t b0, size_t Bc) -> int {
         ChunkView vi, vc, vp, vf, vs;
         int rc;
-        if ((rc = chunk_prepare(ctx, ln, 0, bi, b0, Bc, true, vi))) return rc;
+        if ((rc = chunk_prepare(ctx, ln, 0, lean_phase ? bi_lean : bi, b0, Bc, true, vi))) return rc;
         if ((rc = chunk_prepare(ctx, ln, 1, bc, b0, Bc, false, vc))) return rc;
         if ((rc = chunk_prepare(ctx, ln, 2, bp, b0, Bc, false, vp))) return rc;
         if (want_flags && (rc = chunk_prepare(ctx, ln, 3, bf, b0, Bc, false, vf))) return rc;
@@ -827,7 +866,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         CK(cudaMemsetAsync(vp.dev, 0, Bc * 4, ln.stream));
         if (want_flags) CK(cudaMemsetAsync(vf.dev, 0, Bc * fw * 8, ln.stream));
 
-        const bool fastN = T.fast_logn > 0;
+        const bool fastN = T.fast_logn > 0 && !lean_phase;
         if (fastN) {
             // optimistic-optimistic: all n = N shares on one degree-d polynomial <=> the top N-m coefficients of the inverse
             // NTT vanish; then the lowest d+t+1 agree as well (path 0, no flags).  Items that fail go to the dense check.
@@ -878,6 +917,11 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         ctx->launches++;
         CK(cudaGetLastError());
 
+        if (lean_phase) {
+            CK(cudaMemcpyAsync(ctx->h_counts + b0 / chunk_full, count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
+            if ((rc = chunk_commit(ctx, ln, bc, b0, Bc, vc))) return rc;
+            return chunk_commit(ctx, ln, bp, b0, Bc, vp);
+        }
         RobustArgs r{};
         r.in = (const uint4 *)vi.dev;
         r.in_sb = vi.sb; r.in_sc = vi.sj;
@@ -917,7 +961,16 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         return 0;
     };
     const bool any_host = bi.host || bc.host || bp.host || (want_flags && bf.host) || (want_secrets && bs.host);
-    return run_batched(ctx, B, any_host, std::max<size_t>(S, T.mout) * 32, body);
+    if (!lean) return run_batched(ctx, B, any_host, std::max<size_t>(S, T.mout) * 32, body);
+    int rc = run_batched(ctx, B, true, std::max<size_t>(S, T.mout) * 32, body, false);
+    if (rc) return rc;
+    lean_phase = false;
+    for (size_t b0 = 0, c = 0; b0 < B; b0 += chunk_full, ++c) {
+        if (!ctx->h_counts[c]) continue;
+        if ((rc = body(ctx->lanes[1], b0, std::min(chunk_full, B - b0)))) return rc;
+    }
+    CK(cudaStreamSynchronize(ctx->lanes[1].stream));
+    return collect_status(ctx);
 }
 
 extern "C" int hbmpc_batch_recover(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, const size_t *sender_ids, size_t B,

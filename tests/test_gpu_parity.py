@@ -377,6 +377,19 @@ def test_pipelined_host_chunks(hb, orc, monkeypatch):
         assert np.array_equal(got[1], coeffs)
         rc, co, sec, path, flags = c.robust_interpolate_batch(ids, bad, n, d, t, want_flags=True)
         assert np.array_equal(co, coeffs) and np.array_equal(sec, coeffs[:, 0]) and np.array_equal(path, ref["path"])
+        # lean host path (no flags): only the d+t+1 examined sender vectors are uploaded first; chunks with failing items
+        # are re-run with all senders.  Permuted arrival order makes the uploaded rows non-contiguous.
+        perm = rng.permutation(n)
+        ev_p = np.ascontiguousarray(evals[perm])
+        ref_p = orc.batch_recover_secret(ids[perm], ev_p, n, d, t, threads=orc.max_threads())
+        got_p = c.batch_recover(ids[perm], ev_p, n, d, t, want_flags=False)
+        _compare_recover(got_p, ref_p, B)
+        clean = np.ascontiguousarray(shares.transpose(1, 0, 2))
+        clean[50:, 4000:4100, 0] ^= np.uint64(3)          # errors only beyond the examined prefix, only in one chunk
+        got_c = c.batch_recover(ids, clean, n, d, t)
+        assert got_c[0] == 0 and np.array_equal(got_c[1], coeffs) and not got_c[2].any()
+        rc, secrets, path = c.batch_recover_secrets(ids, evals, n, d, t)
+        assert rc == 0 and np.array_equal(secrets, coeffs[:, 0]) and np.array_equal(path, ref["path"])
         a, b = _rand(orc, (B,), 1), _rand(orc, (B,), 2)
         rc, w = orc.elementwise(2, a, b)
         assert np.array_equal(c.elementwise(2, a, b), w)
