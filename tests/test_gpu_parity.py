@@ -432,3 +432,59 @@ def test_nonrobust_recover_batch(ctx, orc, hb, n, t):
     with pytest.raises(hb.HbmpcError) as e:
         ctx.nonrobust_recover_batch(np.zeros(t + 1, dtype=np.uint64), shares[:, : t + 1], n, t)
     assert e.value.code == hb.INVALID_INPUT
+
+
+# ------------------------------------------------------------------ edges
+def test_vandermonde_more_columns_than_domain(ctx, orc):
+    """cols > N (the exponent wraps, w^N = 1): the NTT does not apply, the dense kernel must take over."""
+    n, cols, B = 4, 7, 50
+    x = _rand(orc, (B, cols), 808)
+    rc, want = orc.apply_vandermonde(x, n)
+    assert rc == 0 and np.array_equal(ctx.apply_vandermonde_batch(x, n), want)
+
+
+def test_forced_dense_equals_ntt(hb, orc, monkeypatch):
+    """K1/K2 through the dense matvec kernel (HBMPC_FORCE_DENSE) and K3 without the inverse-NTT fast path
+    (HBMPC_NO_FASTPATH) give the same bytes as the default NTT paths."""
+    n, t, d, B = 64, 21, 21, 300
+    coeffs = _rand(orc, (B, d + 1), 909)
+    monkeypatch.setenv("HBMPC_FORCE_DENSE", "1")
+    monkeypatch.setenv("HBMPC_NO_FASTPATH", "1")
+    c1 = hb.Context(0)
+    monkeypatch.delenv("HBMPC_FORCE_DENSE")
+    monkeypatch.delenv("HBMPC_NO_FASTPATH")
+    c2 = hb.Context(0)
+    try:
+        s1, s2 = c1.compute_shares_batch(coeffs, n), c2.compute_shares_batch(coeffs, n)
+        assert np.array_equal(s1, s2)
+        bad = s1.copy()
+        bad[::5, 60, 0] ^= np.uint64(1)      # beyond the examined prefix: fast path rejects, dense check accepts (path 0)
+        bad[1::5, 3, 0] ^= np.uint64(1)      # inside: robust path
+        ev = np.ascontiguousarray(bad.transpose(1, 0, 2))
+        r1 = c1.batch_recover(np.arange(n), ev, n, d, t, want_flags=True)
+        r2 = c2.batch_recover(np.arange(n), ev, n, d, t, want_flags=True)
+        for a_, b_ in zip(r1, r2):
+            assert np.array_equal(a_, b_)
+        assert np.array_equal(r2[1], coeffs) and (r2[2][::5] == 0).all() and (r2[2][1::5] == 1).all()
+    finally:
+        c1.close()
+        c2.close()
+
+
+def test_large_party_count_recover(ctx, orc):
+    n, t, d, B = 255, 84, 84, 12
+    coeffs, shares = _codewords(orc, n, d, B, 777)
+    rng = np.random.default_rng(3)
+    nerr = np.array([0, 1, 5, 40, 84, 84, 0, 2, 3, 10, 20, 60])
+    bad = _corrupt(shares, rng, nerr)
+    ids = np.arange(n)
+    rc, co, sec, path, flags = ctx.robust_interpolate_batch(ids, bad, n, d, t, want_flags=True)
+    assert rc == 0 and np.array_equal(co, coeffs)
+    for b in range(B):
+        diff = np.nonzero((bad[b] != shares[b]).any(axis=1))[0]
+        got = [i for i in range(n) if (int(flags[b, i >> 6]) >> (i & 63)) & 1]
+        assert got == diff.tolist()
+        # reference round: smallest r with #errors among the lowest d+t+1+r ids <= r (0 if the lowest d+t+1 are clean)
+        pre = d + t + 1
+        want = 0 if not (diff < pre).any() else next(r for r in range(1, t + 1) if (diff < pre + r).sum() <= r)
+        assert path[b] == want
