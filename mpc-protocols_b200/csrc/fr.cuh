@@ -355,7 +355,7 @@ HB_DEV void cios_row(unsigned long long &e0, unsigned long long &e1, unsigned lo
                      const uint32_t (&a)[8], uint32_t bi) {
 #if defined(__CUDA_ARCH__)
     asm("{\n\t"
-        ".reg .u32 E0, E1, E2, E3, E4, E5, E6, E7, O0, O1, O2, O3, O4, O5, O6, O7, mi;\n\t"
+        ".reg .u32 E0, E1, E2, E3, E4, E5, E6, E7, O0, O1, O2, O3, O4, O5, O6, O7, mi, mh, t0;\n\t"
         "mov.b64 {E0, E1}, %0;\n\t"
         "mov.b64 {E2, E3}, %1;\n\t"
         "mov.b64 {E4, E5}, %2;\n\t"
@@ -383,18 +383,22 @@ HB_DEV void cios_row(unsigned long long &e0, unsigned long long &e1, unsigned lo
         "madc.lo.cc.u32 O6, %14, %16, O6;\n\t"
         "madc.hi.cc.u32 O7, %14, %16, O7;\n\t"
         "addc.u32 E7, E7, 0;\n\t"
-        // Montgomery step: m = -T_0, T += m * r
+        // Montgomery step: m = -T_0, T += m * r.  r_0 = 1 and r_1 = 2^32 - 1, so m*r_0 = m and
+        // m*r_1 = (m - [m != 0]) * 2^32 + T_0: those two products are plain additions (ALU pipe), 6 wide multiplies remain
+        "mov.u32 t0, O0;\n\t"
         "sub.u32 mi, 0, O0;\n\t"
-        "mad.lo.cc.u32 E0, mi, " HB_PR1 ", E0;\n\t"
-        "madc.hi.cc.u32 E1, mi, " HB_PR1 ", E1;\n\t"
+        "min.u32 mh, mi, 1;\n\t"
+        "sub.u32 mh, mi, mh;\n\t"
+        "add.cc.u32 E0, E0, t0;\n\t"
+        "addc.cc.u32 E1, E1, mh;\n\t"
         "madc.lo.cc.u32 E2, mi, " HB_PR3 ", E2;\n\t"
         "madc.hi.cc.u32 E3, mi, " HB_PR3 ", E3;\n\t"
         "madc.lo.cc.u32 E4, mi, " HB_PR5 ", E4;\n\t"
         "madc.hi.cc.u32 E5, mi, " HB_PR5 ", E5;\n\t"
         "madc.lo.cc.u32 E6, mi, " HB_PR7 ", E6;\n\t"
         "madc.hi.u32 E7, mi, " HB_PR7 ", E7;\n\t"
-        "mad.lo.cc.u32 O0, mi, " HB_PR0 ", O0;\n\t"
-        "madc.hi.cc.u32 O1, mi, " HB_PR0 ", O1;\n\t"
+        "add.cc.u32 O0, O0, mi;\n\t"
+        "addc.cc.u32 O1, O1, 0;\n\t"
         "madc.lo.cc.u32 O2, mi, " HB_PR2 ", O2;\n\t"
         "madc.hi.cc.u32 O3, mi, " HB_PR2 ", O3;\n\t"
         "madc.lo.cc.u32 O4, mi, " HB_PR4 ", O4;\n\t"
@@ -428,9 +432,13 @@ HB_DEV void cios_row(unsigned long long &e0, unsigned long long &e1, unsigned lo
     E[7] = addc(0, hi(a[7], bi), true);
     for (int j = 0; j < 4; ++j) { uint32_t x = a[2 * j]; O[2 * j] = addc(O[2 * j], lo(x, bi), j > 0); O[2 * j + 1] = addc(O[2 * j + 1], hi(x, bi), true); }
     E[7] = addc(E[7], 0, true);
-    uint32_t mi = 0u - O[0];
-    for (int j = 0; j < 4; ++j) { uint32_t x = rl[2 * j + 1]; E[2 * j] = addc(E[2 * j], lo(mi, x), j > 0); E[2 * j + 1] = addc(E[2 * j + 1], hi(mi, x), true); }
-    for (int j = 0; j < 4; ++j) { uint32_t x = rl[2 * j]; O[2 * j] = addc(O[2 * j], lo(mi, x), j > 0); O[2 * j + 1] = addc(O[2 * j + 1], hi(mi, x), true); }
+    const uint32_t t0 = O[0], mi = 0u - O[0], mh = mi - (mi < 1u ? mi : 1u);
+    E[0] = addc(E[0], t0, false);
+    E[1] = addc(E[1], mh, true);
+    for (int j = 1; j < 4; ++j) { uint32_t x = rl[2 * j + 1]; E[2 * j] = addc(E[2 * j], lo(mi, x), true); E[2 * j + 1] = addc(E[2 * j + 1], hi(mi, x), true); }
+    O[0] = addc(O[0], mi, false);
+    O[1] = addc(O[1], 0, true);
+    for (int j = 1; j < 4; ++j) { uint32_t x = rl[2 * j]; O[2 * j] = addc(O[2 * j], lo(mi, x), true); O[2 * j + 1] = addc(O[2 * j + 1], hi(mi, x), true); }
     E[7] = addc(E[7], 0, true);
     e0 = E[0] | ((unsigned long long)E[1] << 32); e1 = E[2] | ((unsigned long long)E[3] << 32);
     e2 = E[4] | ((unsigned long long)E[5] << 32); e3 = E[6] | ((unsigned long long)E[7] << 32);

@@ -488,13 +488,13 @@ static int launch_ntt_t(hbmpc_ctx *ctx, cudaStream_t st, const NttArgs &a) {
     if (ctas == 0) {
         CK(cudaFuncSetAttribute(ntt_kernel<LOGN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ntt_kernel<LOGN, MODE>, 256, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ntt_kernel<LOGN, MODE>, HB_NTT_BLOCK, smem));
         ctas = nb > 0 ? nb : 1;
     }
     const int ipc = ntt_items_per_cta<LOGN>();
     long long ntiles = (a.B + ipc - 1) / ipc;
     long long grid = std::min<long long>(ntiles, (long long)ctx->num_sms * ctas);
-    ntt_kernel<LOGN, MODE><<<(unsigned)grid, 256, smem, st>>>(a);
+    ntt_kernel<LOGN, MODE><<<(unsigned)grid, HB_NTT_BLOCK, smem, st>>>(a);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;

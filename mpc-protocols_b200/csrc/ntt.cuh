@@ -34,9 +34,12 @@ struct NttArgs {
     unsigned char *fail;   // fail[b] = 1 when some coefficient k >= m is non-zero
 };
 
+// SKIP_ONE: test for the trivial twiddle (only where the index is warp-uniform -- pass 0 -- so the test folds away or
+// never diverges); elsewhere always multiply (tw[0] is the Montgomery form of 1).
+template <bool SKIP_ONE>
 __device__ __forceinline__ void ntt_butterfly(uint32_t (&u)[8], uint32_t (&v)[8], const uint4 *tw, int twidx) {
     uint32_t t[8], s[8], d[8];
-    if (twidx != 0) {
+    if (!SKIP_ONE || twidx != 0) {
         uint32_t w[8];
         load_fr(w, tw[twidx * 2], tw[twidx * 2 + 1]);
         mont_mul(t, v, w);
@@ -51,7 +54,7 @@ __device__ __forceinline__ void ntt_butterfly(uint32_t (&u)[8], uint32_t (&v)[8]
 }
 
 // GG butterfly stages on the 2^GG register-resident elements x[e] that sit at positions base + e*h0
-template <int GG, int E>
+template <int GG, int E, bool SKIP_ONE>
 __device__ __forceinline__ void ntt_stages(uint32_t (&x)[E][8], const uint4 *tw, int low, int h0, int tw_shift0) {
 #pragma unroll
     for (int q = 0; q < GG; ++q) {
@@ -61,7 +64,7 @@ __device__ __forceinline__ void ntt_stages(uint32_t (&x)[E][8], const uint4 *tw,
         for (int e = 0; e < (1 << GG); ++e) {
             if (e & (1 << q)) continue;
             const int twidx = (low + (e & ((1 << q) - 1)) * h0) << tws;
-            ntt_butterfly(x[e], x[e | (1 << q)], tw, twidx);
+            ntt_butterfly<SKIP_ONE>(x[e], x[e | (1 << q)], tw, twidx);
         }
     }
 }
@@ -73,6 +76,9 @@ __device__ __forceinline__ void ntt_stages(uint32_t (&x)[E][8], const uint4 *tw,
 #endif
 #ifndef HB_NTT_MINB
 #define HB_NTT_MINB 3
+#endif
+#ifndef HB_NTT_BLOCK
+#define HB_NTT_BLOCK 256
 #endif
 template <int LOGN>
 __host__ __device__ constexpr int ntt_g() { return LOGN < HB_NTT_G ? LOGN : (LOGN >= 8 ? 3 : HB_NTT_G); }
@@ -100,12 +106,12 @@ __device__ __forceinline__ void ntt_emit(const NttArgs &a, long long b, int pos,
 }
 
 template <int LOGN, int MODE>
-__global__ void __launch_bounds__(256, HB_NTT_MINB) ntt_kernel(const NttArgs a) {
+__global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const NttArgs a) {
     constexpr int N = 1 << LOGN;
     constexpr int G = ntt_g<LOGN>();
     constexpr int E = 1 << G;
     constexpr int TPI = N / E;                  // threads per item (<= 32)
-    constexpr int IPC = 256 / TPI;              // items per CTA tile
+    constexpr int IPC = HB_NTT_BLOCK / TPI;     // items per CTA tile
     constexpr int NP = (LOGN + G - 1) / G;      // passes
     constexpr int GL = LOGN - G * (NP - 1);     // stages in the last pass
     constexpr int PADN = N + N / 8;
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(256, HB_NTT_MINB) ntt_kernel(const NttArgs a) 
                 for (int i = 0; i < 8; ++i) x[e][i] = 0;
             }
         }
-        ntt_stages<G, E>(x, sTw, 0, 1, LOGN - 1);
+        ntt_stages<G, E, true>(x, sTw, 0, 1, LOGN - 1);
         if constexpr (NP == 1) {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(256, HB_NTT_MINB) ntt_kernel(const NttArgs a) 
                 const int pos = base + e * h0, idx = pos + (pos >> 3);
                 load_fr(x[e], myD[idx], myD[PADN + idx]);
             }
-            ntt_stages<G, E>(x, sTw, low, h0, LOGN - 1 - sh);
+            ntt_stages<G, E, false>(x, sTw, low, h0, LOGN - 1 - sh);
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int pos = base + e * h0, idx = pos + (pos >> 3);
@@ -187,7 +193,7 @@ __global__ void __launch_bounds__(256, HB_NTT_MINB) ntt_kernel(const NttArgs a) 
                     const int pos = base + e * h0, idx = pos + (pos >> 3);
                     load_fr(y[e], myD[idx], myD[PADN + idx]);
                 }
-                ntt_stages<GL, EL>(y, sTw, low, h0, LOGN - 1 - sh);
+                ntt_stages<GL, EL, false>(y, sTw, low, h0, LOGN - 1 - sh);
 #pragma unroll
                 for (int e = 0; e < EL; ++e) {
                     const int pos = base + e * h0;
@@ -206,14 +212,14 @@ inline size_t ntt_smem_bytes() {
     constexpr int N = 1 << LOGN;
     constexpr int G = ntt_g<LOGN>();
     constexpr int TPI = N / (1 << G);
-    constexpr int IPC = 256 / TPI;
+    constexpr int IPC = HB_NTT_BLOCK / TPI;
     constexpr int NP = (LOGN + G - 1) / G;
     size_t tw = (size_t)(N > 1 ? N : 2) * 16;
     return tw + (NP > 1 ? (size_t)IPC * 2 * (N + N / 8) * 16 : 0) + 16;
 }
 template <int LOGN>
 inline int ntt_items_per_cta() {
-    return 256 / ((1 << LOGN) / (1 << ntt_g<LOGN>()));
+    return HB_NTT_BLOCK / ((1 << LOGN) / (1 << ntt_g<LOGN>()));
 }
 
 }  // namespace hb
