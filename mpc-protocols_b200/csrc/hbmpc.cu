@@ -996,6 +996,10 @@ struct NonRobustTables {
     uint4 *M = nullptr;
     int *chk_map = nullptr;
     int R = 0, n_chk = 0;
+    // every domain point supplied (S == n == N): interpolation through all points is one inverse NTT
+    int fast_logn = 0;
+    int *in_map = nullptr;
+    uint4 *itw = nullptr, *iscale = nullptr;
 };
 static std::map<std::string, NonRobustTables> &nr_cache(hbmpc_ctx *ctx) {
     if (!ctx->nonrobust) ctx->nonrobust = new std::map<std::string, NonRobustTables>();
@@ -1040,6 +1044,14 @@ extern "C" int hbmpc_nonrobust_recover_batch(hbmpc_ctx *ctx, size_t n, size_t de
         int rc;
         if ((rc = upload_fr(ctx, M, &T.M))) return rc;
         if ((rc = upload(ctx, chk, &T.chk_map))) return rc;
+        const int N = domain_size(n);
+        if (!ctx->no_fastpath && S == n && (size_t)N == n && N >= 2) {
+            std::vector<int> in_map(N);
+            for (size_t i = 0; i < S; ++i) in_map[ids[i]] = (int)i;
+            if ((rc = upload(ctx, in_map, &T.in_map))) return rc;
+            if ((rc = get_inverse_twiddles(ctx, N, &T.itw, &T.iscale))) return rc;
+            while ((1 << T.fast_logn) < N) ++T.fast_logn;
+        }
         it = cache.emplace(key, T).first;
     }
     const NonRobustTables &T = it->second;
@@ -1056,6 +1068,24 @@ extern "C" int hbmpc_nonrobust_recover_batch(hbmpc_ctx *ctx, size_t n, size_t de
         const size_t fail_bytes = ((Bc + 15) / 16) * 16;
         if ((rc = scratch_get(ctx, ln, 5, fail_bytes, &aux))) return rc;
         CK(cudaMemsetAsync(aux, 0, fail_bytes, ln.stream));
+        if (T.fast_logn > 0) {
+            NttArgs na{};
+            na.in = (const uint4 *)vi.dev;
+            na.out = (uint4 *)vc.dev;
+            na.tw = T.itw;
+            na.B = (long long)Bc;
+            na.in_sb = vi.sb; na.in_sc = vi.sj;
+            na.out_sb = (long long)m; na.out_sr = 1;
+            na.cols = (int)S;
+            na.n = (int)S;
+            na.err = ctx->d_status;
+            na.in_map = T.in_map;
+            na.scale = T.iscale;
+            na.m = (int)m;
+            na.mout = (int)m;
+            na.fail = (unsigned char *)aux;
+            if ((rc = launch_ntt<1>(ctx, ln.stream, T.fast_logn, na))) return rc;
+        } else {
         MatvecArgs a{};
         a.M = T.M;
         a.in = (const uint4 *)vi.dev;
@@ -1072,6 +1102,7 @@ extern "C" int hbmpc_nonrobust_recover_batch(hbmpc_ctx *ctx, size_t n, size_t de
         a.chk_map = T.chk_map;
         a.fail = (unsigned char *)aux;
         if ((rc = launch_matvec(ctx, ln.stream, a, 0))) return rc;
+        }
         degree_status_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>((long long)Bc, (int)m, (uint4 *)vc.dev, (const unsigned char *)aux, (int *)vst.dev,
                                                                      secrets ? (uint4 *)vs.dev : nullptr);
         ctx->launches++;
