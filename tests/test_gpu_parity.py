@@ -488,3 +488,54 @@ def test_large_party_count_recover(ctx, orc):
         pre = d + t + 1
         want = 0 if not (diff < pre).any() else next(r for r in range(1, t + 1) if (diff < pre + r).sum() <= r)
         assert path[b] == want
+
+
+def test_two_contexts_from_two_threads(hb, orc):
+    """The reference calls the share functions from several tokio worker threads (one node per task, many nodes per
+    process in its tests): one context per thread must work concurrently on the same GPU."""
+    import threading
+
+    n, t, d, B = 16, 5, 5, 20000
+    results, errors = {}, []
+
+    def worker(k):
+        try:
+            c = hb.Context(0)
+            coeffs = _rand(orc, (B, d + 1), 0xAB00 + k)
+            for _ in range(3):
+                shares = c.compute_shares_batch(coeffs, n)
+                ev = np.ascontiguousarray(shares.transpose(1, 0, 2))
+                rc, co, path, _ = c.batch_recover(np.arange(n), ev, n, d, t)
+                assert rc == 0 and np.array_equal(co, coeffs) and not path.any()
+            results[k] = shares
+            c.close()
+        except Exception as ex:  # pragma: no cover
+            errors.append(ex)
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(3)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errors, errors
+    for k in range(3):
+        rc, want = orc.compute_shares(_rand(orc, (B, d + 1), 0xAB00 + k), n, threads=orc.max_threads())
+        assert np.array_equal(results[k], want)
+
+
+def test_serialized_payload_pointer_offsets(ctx, orc):
+    """ark-serialize writes Vec<F> as a u64 length followed by 32-byte little-endian canonical elements
+    (batch_recon.rs:174-175): the element bytes are this library's format, only 8-byte aligned.  Host pointers at such
+    offsets must be accepted as they are (no unpacking pass)."""
+    n, t, d, B = 16, 5, 5, 1000
+    coeffs = _rand(orc, (B, d + 1), 0xF00D)
+    raw = np.zeros(8 + coeffs.nbytes, dtype=np.uint8)
+    raw[:8] = np.frombuffer(np.uint64(B * (d + 1)).tobytes(), dtype=np.uint8)   # the length prefix
+    raw[8:] = coeffs.view(np.uint8).reshape(-1)
+    payload = raw[8:].view(np.uint64).reshape(B, d + 1, 4)                       # 8-byte aligned view, not 16
+    assert payload.ctypes.data % 16 == 8 or payload.ctypes.data % 16 == 0
+    rc, want = orc.compute_shares(coeffs, n)
+    out_raw = np.zeros(8 + B * n * 32, dtype=np.uint8)
+    out = out_raw[8:].view(np.uint64).reshape(B, n, 4)
+    got = ctx.compute_shares_batch(payload, n, out=out)
+    assert np.array_equal(got, want)
