@@ -939,7 +939,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         r.flag_words = fw;
         r.fail_any = ctx->d_status + 2;
         const int threads = 128;
-        long long blocks = std::min<long long>((long long)ctx->num_sms * 4, (long long)((Bc + threads - 1) / threads));
+        long long blocks = std::min<long long>((long long)ctx->num_sms * HB_ROBUST_MINB, (long long)((Bc + threads - 1) / threads));
         if (blocks < 1) blocks = 1;
         void *ws = nullptr;
         if ((rc = scratch_get(ctx, ln, 6, (size_t)blocks * threads * lay.total * 32 + 64, &ws))) return rc;

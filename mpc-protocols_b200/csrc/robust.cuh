@@ -407,7 +407,10 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
 #define HB_ROBUST_MAXT 85  // t < n/3, n <= 256
 #endif
 
-__global__ void __launch_bounds__(128) robust_kernel(const RobustArgs a) {
+#ifndef HB_ROBUST_MINB
+#define HB_ROBUST_MINB 8
+#endif
+__global__ void __launch_bounds__(128, HB_ROBUST_MINB) robust_kernel(const RobustArgs a) {
     const unsigned int cnt = *a.count;
     const size_t T = (size_t)gridDim.x * blockDim.x;
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
