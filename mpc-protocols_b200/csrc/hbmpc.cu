@@ -163,6 +163,10 @@ struct RecoverTables {
     int fast_logn = 0;
     int *in_map = nullptr;
     uint4 *itw = nullptr, *iscale = nullptr;
+    // general optimistic check without flags: erasure-weighted inverse NTT + triangular coefficient recovery
+    int er_logn = 0, er_zero_from = 0;
+    int *er_in_map = nullptr, *er_row_len = nullptr;
+    uint4 *er_wt = nullptr, *er_tri = nullptr;
 };
 
 struct hbmpc_ctx {
@@ -174,7 +178,7 @@ struct hbmpc_ctx {
     std::string err;
     int num_sms = 148;
     int matvec_regs = 0;
-    int ntt_ctas[2][9] = {};                        // resident CTAs per SM of ntt_kernel<LOGN, MODE>
+    int ntt_ctas[3][9] = {};                        // resident CTAs per SM of ntt_kernel<LOGN, MODE>
     bool no_fastpath = false;                       // HBMPC_NO_FASTPATH=1: K3 never takes the all-shares-present inverse-NTT path
     bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
     size_t chunk_bytes = 16u << 20;                 // HBMPC_CHUNK_MB: target bytes per pipelined host copy
@@ -773,6 +777,55 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
         if ((rc = get_inverse_twiddles(ctx, N, &T.itw, &T.iscale))) return rc;
         while ((1 << T.fast_logn) < N) ++T.fast_logn;
     }
+    // Erasure-weighted transform for the general case (any id subset, no flags): with X = the d+t+1 examined ids and
+    // Zc(x) = prod_{k < N, k not in X} (x - w^k), the word y'_k = y_k*Zc(w^k) (k in X, zero elsewhere) is the evaluation
+    // vector of Q = P_X*Zc where P_X interpolates the examined shares; deg P_X <= d  <=>  the coefficients N-t .. N-1 of
+    // Q = INTT(y') vanish, and then P = Q*(N*Zc)^{-1} mod x^(d+1): a (d+1) x (d+1) triangular matrix.
+    if (!ctx->no_fastpath && !want_flags && T.fast_logn == 0 && N >= 2) {
+        std::vector<char> inX(N, 0);
+        std::vector<int> er_map(N, -1);
+        for (size_t i = 0; i < needed; ++i) { inX[sorted_ids[i]] = 1; er_map[sorted_ids[i]] = order[i]; }
+        std::vector<HFr> domN = domain_elements((size_t)N, (size_t)N);
+        std::vector<HFr> Z(1, hfr::ONE);  // coefficients of Zc, low degree first
+        for (int k = 0; k < N; ++k) {
+            if (inX[k]) continue;
+            HFr nx = hfr::neg(domN[k]);
+            Z.push_back(hfr::ZERO);
+            for (size_t i = Z.size() - 1; i >= 1; --i) Z[i] = hfr::add(Z[i - 1], hfr::mul(Z[i], nx));
+            Z[0] = hfr::mul(Z[0], nx);
+        }
+        std::vector<HFr> wt(N, hfr::ZERO);
+        for (int k = 0; k < N; ++k) {
+            if (!inX[k]) continue;
+            HFr acc = hfr::ZERO;
+            for (size_t i = Z.size(); i-- > 0;) acc = hfr::add(hfr::mul(acc, domN[k]), Z[i]);
+            wt[k] = acc;
+        }
+        // W = (N*Zc)^{-1} mod x^m
+        HFr Nf = hfr::from_u64((uint64_t)N);
+        std::vector<HFr> Zs(m, hfr::ZERO), W(m, hfr::ZERO);
+        for (size_t i = 0; i < m && i < Z.size(); ++i) Zs[i] = hfr::mul(Z[i], Nf);
+        W[0] = hfr::inv(Zs[0]);
+        HFr nW0 = hfr::neg(W[0]);
+        for (size_t k = 1; k < m; ++k) {
+            HFr acc = hfr::ZERO;
+            for (size_t i = 1; i <= k; ++i) acc = hfr::add(acc, hfr::mul(Zs[i], W[k - i]));
+            W[k] = hfr::mul(nW0, acc);
+        }
+        std::vector<HFr> tri(mout * mout, hfr::ZERO);
+        std::vector<int> row_len(mout);
+        for (size_t k = 0; k < mout; ++k) {
+            row_len[k] = (int)k + 1;
+            for (size_t i = 0; i <= k; ++i) tri[k * mout + i] = W[k - i];
+        }
+        if ((rc = upload(ctx, er_map, &T.er_in_map))) return rc;
+        if ((rc = upload(ctx, row_len, &T.er_row_len))) return rc;
+        if ((rc = upload_fr(ctx, wt, &T.er_wt))) return rc;
+        if ((rc = upload_fr(ctx, tri, &T.er_tri))) return rc;
+        if (!T.itw && (rc = get_inverse_twiddles(ctx, N, &T.itw, &T.iscale))) return rc;
+        T.er_zero_from = N - (int)t;
+        while ((1 << T.er_logn) < N) ++T.er_logn;
+    }
     return 0;
 }
 
@@ -893,6 +946,38 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             CK(cudaGetLastError());
         }
 
+        const bool erasure = T.er_logn > 0 && !fastN;
+        if (erasure) {
+            void *tmp = nullptr;
+            if ((rc = scratch_get(ctx, ln, 7, Bc * (size_t)T.mout * 32, &tmp))) return rc;
+            NttArgs na{};
+            na.in = (const uint4 *)vi.dev;
+            na.out = (uint4 *)tmp;
+            na.tw = T.itw;
+            na.B = (long long)Bc;
+            na.in_sb = vi.sb; na.in_sc = vi.sj;
+            na.out_sb = T.mout; na.out_sr = 1;
+            na.cols = 1 << T.er_logn;
+            na.n = 1 << T.er_logn;
+            na.err = ctx->d_status;
+            na.in_map = T.er_in_map;
+            na.wt = T.er_wt;
+            na.m = T.er_zero_from;
+            na.mout = T.mout;
+            na.fail = fail;
+            if ((rc = launch_ntt<2>(ctx, ln.stream, T.er_logn, na))) return rc;
+            MatvecArgs tr{};
+            tr.M = T.er_tri;
+            tr.in = (const uint4 *)tmp;
+            tr.out = (uint4 *)vc.dev;
+            tr.R = T.mout;
+            tr.C = T.mout;
+            tr.B = (long long)Bc;
+            tr.in_sb = T.mout; tr.in_sc = 1; tr.in_chunk_major = 1;
+            tr.out_sb = T.mout; tr.out_sr = 1;
+            tr.row_len = T.er_row_len;
+            if ((rc = launch_matvec(ctx, ln.stream, tr, 0))) return rc;
+        }
         MatvecArgs a{};
         if (fastN) { a.item_list = list1; a.item_count = count1; }
         a.M = T.M;
@@ -911,11 +996,27 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         a.chk_map = T.chk_map;
         a.fail = fail;
         a.flags = want_flags ? (unsigned long long *)vf.dev : nullptr;
-        if ((rc = launch_matvec(ctx, ln.stream, a, fw))) return rc;
+        if (!erasure && (rc = launch_matvec(ctx, ln.stream, a, fw))) return rc;
 
         compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail, (long long)Bc, list, count);
         ctx->launches++;
         CK(cudaGetLastError());
+        if (erasure && !lean_phase) {
+            // the robust decoder corrects Lc*y[lowest d+1] by linearity: provide it for the failing items
+            MatvecArgs lc{};
+            lc.M = T.Lc;
+            lc.in = (const uint4 *)vi.dev;
+            lc.out = (uint4 *)vc.dev;
+            lc.R = T.mout;
+            lc.C = (int)m;
+            lc.B = (long long)Bc;
+            lc.in_sb = vi.sb; lc.in_sc = vi.sj;
+            lc.in_chunk_major = sender_major ? 0 : 1;
+            lc.out_sb = T.mout; lc.out_sr = 1;
+            lc.col_map = T.col_map;
+            lc.item_list = list; lc.item_count = count;
+            if ((rc = launch_matvec(ctx, ln.stream, lc, 0))) return rc;
+        }
 
         if (lean_phase) {
             CK(cudaMemcpyAsync(ctx->h_counts + b0 / chunk_full, count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));

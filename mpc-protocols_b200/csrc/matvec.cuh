@@ -42,6 +42,7 @@ struct MatvecArgs {
     int in_chunk_major;        // 1: in_sc == 1 (tile is contiguous), 0: in_sb == 1 (sender-major)
     const unsigned int *item_list;   // optional indirection: process items item_list[0 .. *item_count) instead of 0 .. B
     const unsigned int *item_count;
+    const int *row_len;        // optional [R]: row r uses only its first row_len[r] columns (triangular matrices)
 };
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
@@ -121,13 +122,14 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
             acc_t A;
             acc_zero(A);
             unsigned bad = 0;
+            const int Cr = a.row_len ? a.row_len[r] : C;  // terms of this row
             const bool validate = (rl == 0);  // one row per slice validates the tile's inputs (each input exactly once per slice)
             // two register sets, loads issued one term ahead, no register moves (loop unrolled by two)
             uint4 a0 = Dsub[0], a1 = Dsub[32], b0 = Mrow[0], b1 = Mrow[1];
             uint4 c0 = a0, c1 = a1, d0 = b0, d1 = b1;
 #pragma unroll 1
-            for (int c = 0; c < C; c += 2) {
-                if (c + 1 < C) {
+            for (int c = 0; c < Cr; c += 2) {
+                if (c + 1 < Cr) {
                     c0 = Dsub[(c + 1) * 64];
                     c1 = Dsub[(c + 1) * 64 + 32];
                     d0 = Mrow[(c + 1) * 2];
@@ -139,13 +141,13 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
                     if (validate) bad |= geq_mod(x) ? 1u : 0u;
                     acc_mac(A, x, m);
                 }
-                if (c + 2 < C) {
+                if (c + 2 < Cr) {
                     a0 = Dsub[(c + 2) * 64];
                     a1 = Dsub[(c + 2) * 64 + 32];
                     b0 = Mrow[(c + 2) * 2];
                     b1 = Mrow[(c + 2) * 2 + 1];
                 }
-                if (c + 1 < C) {
+                if (c + 1 < Cr) {
                     const uint32_t x[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
                     const uint32_t m[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
                     if (validate) bad |= geq_mod(x) ? 1u : 0u;

@@ -32,6 +32,10 @@ struct NttArgs {
     const uint4 *scale;    // N^{-1} in Montgomery form
     int m, mout;           // coefficients k < mout are stored (scaled), coefficients k >= m must vanish
     unsigned char *fail;   // fail[b] = 1 when some coefficient k >= m is non-zero
+    // MODE 2 (inverse transform of an erasure-weighted word, the general optimistic check of K3): the share with id k is
+    // multiplied by wt[k] = Zc(w^k) (Zc = product over the ids outside the examined set; Montgomery form) while it is
+    // loaded, ids outside the examined set contribute zero (in_map[k] < 0); outputs are left unscaled.
+    const uint4 *wt;       // [N][2]
 };
 
 // SKIP_ONE: test for the trivial twiddle (only where the index is warp-uniform -- pass 0 -- so the test folds away or
@@ -95,7 +99,11 @@ __device__ __forceinline__ void ntt_emit(const NttArgs &a, long long b, int pos,
     } else {
         if (pos < a.mout) {
             uint32_t c[8];
-            mont_mul(c, v, sc);
+            if (MODE == 1) mont_mul(c, v, sc);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) c[i] = v[i];
+            }
             uint4 *o = a.out + (b * a.out_sb + (long long)pos * a.out_sr) * 2;
             stg_stream(o, make_uint4(c[0], c[1], c[2], c[3]));
             stg_stream(o + 1, make_uint4(c[4], c[5], c[6], c[7]));
@@ -138,10 +146,22 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
             const int pos = tid_i * E + e;
             const int k = (int)(__brev((unsigned)pos) >> (32 - LOGN));
             if (active && k < a.cols) {
-                const int rec = (MODE == 1 && a.in_map) ? a.in_map[k] : k;
+                const int rec = (MODE != 0 && a.in_map) ? a.in_map[k] : k;
+                if (MODE == 2 && rec < 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[e][i] = 0;
+                    continue;
+                }
                 const uint4 *p = a.in + (b * a.in_sb + (long long)rec * a.in_sc) * 2;
                 load_fr(x[e], ldg_stream(p), ldg_stream(p + 1));
                 bad |= geq_mod(x[e]) ? 1u : 0u;
+                if (MODE == 2) {
+                    uint32_t w[8], y[8];
+                    load_fr(w, __ldg(a.wt + k * 2), __ldg(a.wt + k * 2 + 1));
+                    mont_mul(y, x[e], w);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[e][i] = y[i];
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[e][i] = 0;
