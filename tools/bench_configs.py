@@ -21,7 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--log2", type=int, default=20)
     ap.add_argument("--log2-c4", type=int, default=16)
-    ap.add_argument("--which", default="c2,c4,c5")
+    ap.add_argument("--which", default="c2,c3r,c4,c5")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     ctx = hb.Context(0)
@@ -56,6 +56,19 @@ def main():
         t_mul = timed(lambda: ctx.elementwise(2, a_, b_, out=o_))
         out["c5_n64_t21"] = {"B": B, "vandermonde_64x64_ms": t_nn, "vandermonde_64x43_ms": t_43, "vandermonde_64x43_recipient_major_ms": t_43t,
                              "recover_d2t_ms": t_r2t, "elementwise_mul_ms": t_mul, "elementwise_GBs": B * 8 * 96 / (t_mul * 1e-3) / 1e9}
+    if "c3r" in which:   # batch reconstruction under attack at n=64,t=21: every chunk carries errors from the t corrupted senders
+        n, t, d, B = 64, 21, 21, 1 << a.log2
+        coeffs = random_fr_device(torch, (B, d + 1), 14, dev)
+        shares = torch.empty((B, n, 4), dtype=torch.int64, device=dev)
+        ctx.compute_shares_batch(coeffs, n, out=shares)
+        ev = shares.permute(1, 0, 2).contiguous()
+        bad_senders = torch.randperm(n, device=dev)[:t]
+        ev[bad_senders, :, 0] ^= 0x77
+        rec = torch.empty((B, d + 1, 4), dtype=torch.int64, device=dev); path = torch.empty((B,), dtype=torch.int32, device=dev)
+        ms = timed(lambda: ctx.batch_recover(np.arange(n), ev, n, d, t, out=(rec, path, None)), reps=2)
+        rc = ctx.synchronize()
+        out["c3_under_attack_n64_t21"] = {"B": B, "corrupted_senders": t, "ms": ms, "chunks_per_s": B / (ms * 1e-3), "rc": rc,
+                                          "all_recovered": bool(torch.equal(rec, coeffs)), "max_path": int(path.max())}
     if "c4" in which:
         n, t, d, B = 128, 42, 42, 1 << a.log2_c4
         coeffs = random_fr_device(torch, (B, d + 1), 4, dev)
