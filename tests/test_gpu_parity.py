@@ -224,7 +224,7 @@ def test_robust_all_error_subsets(ctx, orc, hb, n, t):
         assert int(flags[b, 0]) == sum(1 << p for p in sub)
 
 
-@pytest.mark.parametrize("n,t,S", [(10, 3, 7), (10, 3, 8), (10, 3, 9), (16, 5, 11), (16, 5, 13), (64, 21, 50), (64, 21, 43)])
+@pytest.mark.parametrize("n,t,S", [(10, 3, 7), (10, 3, 8), (10, 3, 9), (10, 3, 10), (13, 4, 11), (16, 5, 11), (16, 5, 13), (64, 21, 50), (64, 21, 43), (128, 42, 100)])
 def test_robust_subset_of_senders(ctx, orc, n, t, S):
     """S < n supplied shares, ids not starting at 0, error counts up to and beyond what the prefix rounds can absorb:
     the GPU must reproduce the oracle's path / DecodingError pattern exactly."""
@@ -248,6 +248,13 @@ def test_robust_subset_of_senders(ctx, orc, n, t, S):
     want_b = orc.batch_recover_secret(ids[arrival], evals, n, d, t, threads=orc.max_threads())
     got_b = ctx.batch_recover(ids[arrival], evals, n, d, t, want_flags=True)
     _compare_recover(got_b, want_b, B)
+    # same calls without flags: the optimistic check runs as an erasure-weighted inverse NTT + triangular recovery
+    got_nf = ctx.batch_recover(ids[arrival], evals, n, d, t, want_flags=False)
+    _compare_recover(got_nf, want_b, B)
+    rc2, co2, sec2, path2, _ = ctx.robust_interpolate_batch(ids[arrival], bad, n, d, t, want_flags=False)
+    assert rc2 == want["rc"] and np.array_equal(path2, want["path"]) and np.array_equal(co2, want["coeffs"]) and np.array_equal(sec2, want["secrets"])
+    rc3, sec3, path3 = ctx.batch_recover_secrets(ids[arrival], evals, n, d, t)
+    assert rc3 == want["rc"] and np.array_equal(path3, want["path"]) and np.array_equal(sec3, want["secrets"])
 
 
 def test_robust_more_than_t_errors(ctx, orc):
