@@ -1,17 +1,18 @@
-// matvec.cuh -- the one hot kernel: a small constant Fr matrix applied to a huge batch of Fr vectors.
+// matvec.cuh -- the dense kernel: a small constant Fr matrix applied to a huge batch of Fr vectors.
 //
-//   out[b][r] = sum_c  M[r][c] * in[b][col_map[c]]   (mod r),   b < B, r < R, c < C
+//   out[b][r] = sum_c  M[r][c] * in[b][col_map[c]]   (mod r),   b < B, r < R, c < C (or c < row_len[r])
 //
-// This single shape covers every dense site of the reference's hot path:
-//   K1  RobustShare/NonRobustShare::compute_shares      M = V[n x (d+1)], V[j][k] = w^(jk)
-//       (robust_interpolate.rs:52-82, shamir.rs:158-196: poly evaluated at the first n domain points)
-//   K2  apply_vandermonde                               M = V[n x cols]          (common/share/mod.rs:50-76)
-//   K3  batch_recover_secret                            M = [check rows L_i(x_s); coefficient rows L_i[k]]
-//       (robust_interpolate.rs:392-428: verify_matrix + basis_coeffs, identity rows dropped)
+// It serves every dense site of the hot path that the NTT kernels (ntt.cuh) do not take:
+//   K3/K4  optimistic check with flags          M = [check rows L_i(x_s); coefficient rows L_i[k]]
+//          (robust_interpolate.rs:392-428: verify_matrix + basis_coeffs, identity rows dropped), also restricted to the
+//          items an NTT check rejected (item_list) and as plain Lc*y for the items handed to the robust decoder
+//   K3     triangular coefficient recovery P = Q*(N*Zc)^-1 mod x^(d+1) after the erasure-weighted inverse NTT
+//   a10    NonRobustShare::recover_secret on id subsets: coefficient rows above `deg` are zero-check rows (shamir.rs:234-237)
+//   K1/K2  Vandermonde with more columns than domain points, caller-supplied matrices (apply_vandermonde, share/mod.rs:50-76)
 //
-// Rows [0, n_chk) are "check rows": the result is compared with the supplied share in[b][chk_map[r]] instead of being
-// written; a mismatch in rows [0, n_gate) marks the item as failing the optimistic path (-> robust decode),
-// any mismatch sets the item's flag bit chk_map[r].
+// Rows [0, n_chk) are "check rows": the result is compared with the supplied share in[b][chk_map[r]] (or with zero when
+// chk_map[r] < 0) instead of being written; a mismatch in rows [0, n_gate) marks the item as failing (-> robust decode /
+// DegreeMismatch), any mismatch sets the item's flag bit chk_map[r].
 //
 // Mapping: M lives in shared memory in Montgomery form (warp-uniform broadcast reads), a tile of TBT*32 batch items is
 // staged in shared memory as [c][half][lane] uint4 (conflict-free 128-bit reads); work items (row, 32-lane sub-tile)

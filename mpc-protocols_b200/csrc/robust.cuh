@@ -9,7 +9,7 @@
 // independent of Gao's internals.  Any bounded-distance decoder with radius >= r therefore returns bit-identical
 // (coefficients, path, flags).  This file uses syndromes + inversion-free Berlekamp-Massey + Chien + Forney:
 //
-//   attempt(P, nsyn, maxL):   S_j = sum_{i<P} u_i x_i^j y_i  (constant matrix H, j < nsyn = P-(d+1));
+//   attempt(P, nsyn, maxL):   S_j = sum_{i<P} u_i x_i^j y_i  (u_i = 1/prod_{l != i}(x_i - x_l), j < nsyn = P-(d+1));
 //                             BM -> locator Lambda (degree L); accept iff L <= maxL and Lambda has L roots among
 //                             the prefix points; Forney -> error values.
 //   fast path  : ONE attempt on all S supplied shares (maxL = min(t, floor((S-d-1)/2))).  If it succeeds the true
@@ -24,8 +24,8 @@
 //   Forney     Omega(w^(-id)), Lambda'(w^(-id))         = two more (when the locator is long enough to pay off),
 // ~N/2*log2(N) products each instead of nsyn*P, P*L and 2*L^2.
 // One thread decodes one codeword; per-thread polynomials live in a strided global workspace (coalesced across the
-// warp).  The corrected coefficients are obtained by linearity from what the optimistic kernel already wrote:
-//   coeffs(f) = Lc * y[0..m) - sum_{i in E, i<m} e_i * Lc[:, i].
+// warp).  The corrected coefficients are obtained by linearity from Lc * y[0..m), which the dense kernel wrote for the
+// failing items:   coeffs(f) = Lc * y[0..m) - sum_{i in E, i<m} e_i * Lc[:, i].
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -69,6 +69,31 @@ def main():
         rc = ctx.synchronize()
         out["c3_under_attack_n64_t21"] = {"B": B, "corrupted_senders": t, "ms": ms, "chunks_per_s": B / (ms * 1e-3), "rc": rc,
                                           "all_recovered": bool(torch.equal(rec, coeffs)), "max_path": int(path.max())}
+    if "lat" in which:   # per-call latency at session-sized batches (device pointers, synchronous mode, wall clock)
+        import time
+        n, t, d = 64, 21, 21
+        ctx.set_async(False)
+        lat = {}
+        for B in (64, 1024, 4096, 16384):
+            coeffs = random_fr_device(torch, (B, d + 1), 24, dev)
+            shares = torch.empty((B, n, 4), dtype=torch.int64, device=dev)
+            ctx.compute_shares_batch(coeffs, n, out=shares)
+            evs = shares.permute(1, 0, 2).contiguous()
+            ev43 = evs[:43].contiguous()
+            rec = torch.empty((B, d + 1, 4), dtype=torch.int64, device=dev); path = torch.empty((B,), dtype=torch.int32, device=dev)
+            sec = torch.empty((B, 4), dtype=torch.int64, device=dev)
+            def wall(fn, reps=50):
+                fn(); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(reps): fn()
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t0) / reps * 1e6
+            lat[B] = {"compute_shares_us": wall(lambda: ctx.compute_shares_batch(coeffs, n, out=shares)),
+                      "batch_recover_64_senders_us": wall(lambda: ctx.batch_recover(np.arange(n), evs, n, d, t, out=(rec, path, None))),
+                      "batch_recover_43_senders_us": wall(lambda: ctx.batch_recover(np.arange(43), ev43, n, d, t, out=(rec, path, None))),
+                      "batch_recover_secrets_43_us": wall(lambda: ctx.batch_recover_secrets(np.arange(43), ev43, n, d, t, out=(sec, path)))}
+        ctx.set_async(True)
+        out["latency_n64_t21"] = lat
     if "c4" in which:
         n, t, d, B = 128, 42, 42, 1 << a.log2_c4
         coeffs = random_fr_device(torch, (B, d + 1), 4, dev)
