@@ -546,3 +546,43 @@ def test_serialized_payload_pointer_offsets(ctx, orc):
     out = out_raw[8:].view(np.uint64).reshape(B, n, 4)
     got = ctx.compute_shares_batch(payload, n, out=out)
     assert np.array_equal(got, want)
+
+
+def test_randomized_configurations(ctx, orc):
+    """Seeded sweep over random (n, t, degree, sender subset, arrival order, error pattern, flags on/off): every output of
+    K1/K2/K3/K4/a10 must equal the oracle's, byte for byte."""
+    rng = np.random.default_rng(20261018)
+    for trial in range(40):
+        n = int(rng.integers(4, 41))
+        t = int(rng.integers(1, (n - 1) // 3 + 1))
+        d = int(rng.choice([t, 2 * t])) if 2 * t + t + 1 <= n else t
+        needed = d + t + 1
+        S = int(rng.integers(needed, n + 1))
+        B = int(rng.integers(1, 70))
+        coeffs, shares = _codewords(orc, n, d, B, 0x5EED1000 + trial)
+        cols = int(rng.integers(1, n + 1))
+        x = _rand(orc, (B, cols), 0x5EED2000 + trial)
+        rm = bool(rng.integers(0, 2))
+        rc, want = orc.apply_vandermonde(x, n, rm)
+        assert np.array_equal(ctx.apply_vandermonde_batch(x, n, rm), want), (trial, n, cols)
+        ids = rng.permutation(n)[:S]
+        words = shares[:, ids]
+        nerr = rng.integers(0, t + 2, size=B)
+        nerr[rng.integers(0, B)] = 0
+        bad = _corrupt(words, rng, np.minimum(nerr, S))
+        flags_on = bool(rng.integers(0, 2))
+        want = orc.robust_interpolate_batch(ids, bad, n, d, t, threads=orc.max_threads())
+        rc, co, sec, path, fl = ctx.robust_interpolate_batch(ids, bad, n, d, t, want_flags=flags_on)
+        key = (trial, n, t, d, S, B, flags_on)
+        assert rc == want["rc"], key
+        assert np.array_equal(path, want["path"]), key
+        assert np.array_equal(co, want["coeffs"]) and np.array_equal(sec, want["secrets"]), key
+        if flags_on:
+            assert np.array_equal(fl, want["flags"][:, : fl.shape[1]]), key
+        ev = np.ascontiguousarray(bad.transpose(1, 0, 2))
+        wb = orc.batch_recover_secret(ids, ev, n, d, t, threads=orc.max_threads())
+        gb = ctx.batch_recover(ids, ev, n, d, t, want_flags=flags_on)
+        _compare_recover(gb, wb, B)
+        # a10 on the clean word: degree d interpolant through all S points
+        co10, sec10, st10 = ctx.nonrobust_recover_batch(ids, words, n, d)
+        assert np.array_equal(co10, coeffs) and np.array_equal(sec10, coeffs[:, 0]), key
