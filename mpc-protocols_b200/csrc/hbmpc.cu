@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) elementwise_kernel(int op, long long coun
         stg_stream(out + i * 2, make_uint4(z[0], z[1], z[2], z[3]));
         stg_stream(out + i * 2 + 1, make_uint4(z[4], z[5], z[6], z[7]));
     }
-    if (bad) atomicOr(err, 1u);
+    if (bad) *(volatile unsigned int *)err = 1u;  // status words live in mapped host memory: plain store, every writer stores 1
 }
 
 // out[b] = in[b*stride]  (secret = coefficient 0)
@@ -182,8 +182,10 @@ struct hbmpc_ctx {
     bool no_fastpath = false;                       // HBMPC_NO_FASTPATH=1: K3 never takes the all-shares-present inverse-NTT path
     bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
     size_t chunk_bytes = 16u << 20;                 // HBMPC_CHUNK_MB: target bytes per pipelined host copy
+    // status words in mapped pinned host memory (device view d_status, host view h_status): kernels store 1 on the rare
+    // error, the host reads them after a stream synchronize -- no copy, no memset on the call path
     unsigned int *d_status = nullptr;  // [0] non-canonical input seen, [2] some item failed to decode
-    unsigned int *h_status = nullptr;  // pinned
+    unsigned int *h_status = nullptr;
     cudaEvent_t ev_main = nullptr;
     unsigned int *h_counts = nullptr;  // pinned: per-chunk count of items that failed the optimistic check (lean host path)
     size_t h_counts_cap = 0;
@@ -274,10 +276,11 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
     }
     bool ok = true;
     for (int i = 0; i < NLANES && ok; ++i) ok = cudaStreamCreateWithFlags(&ctx->lanes[i].stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaMalloc((void **)&ctx->d_status, 16) == cudaSuccess && cudaMallocHost((void **)&ctx->h_status, 16) == cudaSuccess &&
+    ok = ok && cudaHostAlloc((void **)&ctx->h_status, 16, cudaHostAllocMapped) == cudaSuccess &&
+         cudaHostGetDevicePointer((void **)&ctx->d_status, ctx->h_status, 0) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming) == cudaSuccess;
     if (ok) {
-        cudaMemsetAsync(ctx->d_status, 0, 16, ctx->main_stream());
+        memset(ctx->h_status, 0, 16);
         cudaFuncAttributes fa;
         int regs = 0;
         if (cudaFuncGetAttributes(&fa, matvec_kernel<1>) == cudaSuccess) regs = std::max(regs, fa.numRegs);
@@ -307,7 +310,6 @@ extern "C" void hbmpc_ctx_destroy(hbmpc_ctx *ctx) {
     for (auto &ln : ctx->lanes)
         for (auto &b : ln.scratch)
             if (b.p) cudaFree(b.p);
-    if (ctx->d_status) cudaFree(ctx->d_status);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
@@ -336,11 +338,13 @@ extern "C" int hbmpc_ctx_set_async(hbmpc_ctx *ctx, int async) {
 // reads the device status words, folds them into a ShareErrorCode and clears them (all lanes must be quiescent or
 // ordered before the main stream)
 static int collect_status(hbmpc_ctx *ctx) {
-    CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, 16, cudaMemcpyDeviceToHost, ctx->main_stream()));
-    CK(cudaMemsetAsync(ctx->d_status, 0, 16, ctx->main_stream()));
     CK(cudaStreamSynchronize(ctx->main_stream()));
-    if (ctx->h_status[0]) return HBMPC_INVALID_INPUT;
-    if (ctx->h_status[2]) return HBMPC_DECODING_ERROR;
+    volatile unsigned int *hs = ctx->h_status;
+    const unsigned int bad = hs[0], undecodable = hs[2];
+    hs[0] = 0;
+    hs[2] = 0;
+    if (bad) return HBMPC_INVALID_INPUT;
+    if (undecodable) return HBMPC_DECODING_ERROR;
     return HBMPC_SUCCESS;
 }
 
@@ -914,8 +918,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         unsigned char *fail1 = (unsigned char *)(count + 4);
         unsigned int *list1 = (unsigned int *)(fail1 + fail_bytes);
         unsigned int *count1 = list1 + Bc;
-        CK(cudaMemsetAsync(fail, 0, fail_bytes, ln.stream));
-        CK(cudaMemsetAsync(count, 0, 16, ln.stream));
+        CK(cudaMemsetAsync(aux, 0, 2 * (fail_bytes + Bc * 4 + 16), ln.stream));  // fail bytes, lists and counters of both levels
         CK(cudaMemsetAsync(vp.dev, 0, Bc * 4, ln.stream));
         if (want_flags) CK(cudaMemsetAsync(vf.dev, 0, Bc * fw * 8, ln.stream));
 
@@ -923,8 +926,6 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         if (fastN) {
             // optimistic-optimistic: all n = N shares on one degree-d polynomial <=> the top N-m coefficients of the inverse
             // NTT vanish; then the lowest d+t+1 agree as well (path 0, no flags).  Items that fail go to the dense check.
-            CK(cudaMemsetAsync(fail1, 0, fail_bytes, ln.stream));
-            CK(cudaMemsetAsync(count1, 0, 16, ln.stream));
             NttArgs na{};
             na.in = (const uint4 *)vi.dev;
             na.out = (uint4 *)vc.dev;

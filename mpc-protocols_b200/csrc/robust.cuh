@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(128, HB_ROBUST_MINB) robust_kernel(const Robus
             for (int k = 0; k < a.mout; ++k) { co[k * 2] = make_uint4(0, 0, 0, 0); co[k * 2 + 1] = make_uint4(0, 0, 0, 0); }
             if (fl) for (int w = 0; w < a.flag_words; ++w) fl[w] = 0ull;
             a.path[b] = -8;
-            atomicOr(a.fail_any, 1u);
+            *(volatile unsigned int *)a.fail_any = 1u;
             continue;
         }
         // corrected coefficients by linearity
