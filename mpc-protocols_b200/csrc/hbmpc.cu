@@ -152,20 +152,18 @@ struct RecoverTables {
     // optimistic matvec
     int R = 0, C = 0, n_chk = 0, n_gate = 0, mout = 0;
     uint4 *M = nullptr;
-    int *col_map = nullptr, *chk_map = nullptr;
     // robust
     int rmax = 0, fast = 0, nsyn_max = 0;
-    int *att_P = nullptr, *att_nsyn = nullptr, *att_maxL = nullptr, *order = nullptr;
+    int *att_P = nullptr, *att_nsyn = nullptr, *att_maxL = nullptr;
     long long *att_uoff = nullptr;
     int *sid = nullptr;
     uint4 *u2 = nullptr, *tw = nullptr, *ritw = nullptr, *uinv = nullptr, *xs = nullptr, *xinv = nullptr, *Lc = nullptr, *Veval = nullptr;
     // all-shares-present fast path (S == n == N): inverse NTT + degree check
     int fast_logn = 0;
-    int *in_map = nullptr;
     uint4 *itw = nullptr, *iscale = nullptr;
     // general optimistic check without flags: erasure-weighted inverse NTT + triangular coefficient recovery
     int er_logn = 0, er_zero_from = 0;
-    int *er_in_map = nullptr, *er_row_len = nullptr;
+    int *er_row_len = nullptr;
     uint4 *er_wt = nullptr, *er_tri = nullptr;
 };
 
@@ -193,6 +191,7 @@ struct hbmpc_ctx {
     std::map<std::string, RecoverTables> recover;     // keyed by (n, d, t, ids, variant)
     std::map<std::string, struct NonRobustTables> *nonrobust = nullptr;
     std::vector<void *> owned;                        // device allocations freed at destroy
+    DevBuf maps;                                      // per-call arrival-order index maps (order, col_map, chk_map, in_map)
     cudaStream_t main_stream() const { return lanes[0].stream; }
 };
 
@@ -311,6 +310,7 @@ extern "C" void hbmpc_ctx_destroy(hbmpc_ctx *ctx) {
         for (auto &b : ln.scratch)
             if (b.p) cudaFree(b.p);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    if (ctx->maps.p) cudaFree(ctx->maps.p);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
     delete ctx->nonrobust;
@@ -678,7 +678,7 @@ extern "C" int hbmpc_apply_matrix_batch(hbmpc_ctx *ctx, size_t rows, size_t cols
 }
 
 // ------------------------------------------------------------------------------------------------ recovery tables
-static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, const std::vector<int> &order,
+static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S,
                                 const std::vector<size_t> &sorted_ids, bool want_flags, bool secrets_only, RecoverTables &T) {
     const size_t m = d + 1, needed = d + t + 1;
     std::vector<HFr> dom = domain_elements(n, n);
@@ -698,14 +698,8 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
     T.n_chk = (int)n_chk;
     T.n_gate = (int)t;
     T.mout = (int)mout;
-    std::vector<int> col_map(m), chk_map(std::max<size_t>(n_chk, 1));
-    for (size_t i = 0; i < m; ++i) col_map[i] = order[i];
-    for (size_t r = 0; r < n_chk; ++r) chk_map[r] = order[m + r];
     int rc;
     if ((rc = upload_fr(ctx, M, &T.M))) return rc;
-    if ((rc = upload(ctx, col_map, &T.col_map))) return rc;
-    if ((rc = upload(ctx, chk_map, &T.chk_map))) return rc;
-    if ((rc = upload(ctx, order, &T.order))) return rc;
 
     // robust tables
     T.rmax = (int)std::min(t, S - needed);
@@ -775,9 +769,6 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
     // every point of the power-of-two domain supplied: coefficients by one inverse NTT, checked by "top coefficients vanish"
     const int N = domain_size(n);
     if (!ctx->no_fastpath && S == n && (size_t)N == n && N >= 2) {
-        std::vector<int> in_map(N);
-        for (size_t i = 0; i < S; ++i) in_map[sorted_ids[i]] = order[i];
-        if ((rc = upload(ctx, in_map, &T.in_map))) return rc;
         if ((rc = get_inverse_twiddles(ctx, N, &T.itw, &T.iscale))) return rc;
         while ((1 << T.fast_logn) < N) ++T.fast_logn;
     }
@@ -787,8 +778,7 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
     // Q = INTT(y') vanish, and then P = Q*(N*Zc)^{-1} mod x^(d+1): a (d+1) x (d+1) triangular matrix.
     if (!ctx->no_fastpath && !want_flags && T.fast_logn == 0 && N >= 2) {
         std::vector<char> inX(N, 0);
-        std::vector<int> er_map(N, -1);
-        for (size_t i = 0; i < needed; ++i) { inX[sorted_ids[i]] = 1; er_map[sorted_ids[i]] = order[i]; }
+        for (size_t i = 0; i < needed; ++i) inX[sorted_ids[i]] = 1;
         std::vector<HFr> domN = domain_elements((size_t)N, (size_t)N);
         std::vector<HFr> Z(1, hfr::ONE);  // coefficients of Zc, low degree first
         for (int k = 0; k < N; ++k) {
@@ -822,7 +812,6 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
             row_len[k] = (int)k + 1;
             for (size_t i = 0; i <= k; ++i) tri[k * mout + i] = W[k - i];
         }
-        if ((rc = upload(ctx, er_map, &T.er_in_map))) return rc;
         if ((rc = upload(ctx, row_len, &T.er_row_len))) return rc;
         if ((rc = upload_fr(ctx, wt, &T.er_wt))) return rc;
         if ((rc = upload_fr(ctx, tri, &T.er_tri))) return rc;
@@ -860,15 +849,46 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
     const bool want_flags = flags != nullptr;
     std::string key = "R " + std::to_string(n) + " " + std::to_string(d) + " " + std::to_string(t) + (want_flags ? " f" : " -") +
                       (secrets_only ? " s" : " c");
-    for (size_t i = 0; i < S; ++i) key += " " + std::to_string(ids[i]);
+    for (size_t i = 0; i < S; ++i) key += " " + std::to_string(sorted_ids[i]);  // the field tables depend on the id SET only
     auto it = ctx->recover.find(key);
     if (it == ctx->recover.end()) {
         RecoverTables T;
-        int rc = build_recover_tables(ctx, n, d, t, S, order, sorted_ids, want_flags, secrets_only, T);
+        int rc = build_recover_tables(ctx, n, d, t, S, sorted_ids, want_flags, secrets_only, T);
         if (rc) return rc;
         it = ctx->recover.emplace(key, T).first;
     }
     const RecoverTables &T = it->second;
+    // arrival-order index maps, rebuilt per call (messages arrive in a different order every session): a few hundred ints
+    struct { const int *order, *col_map, *chk_map, *in_map, *er_in_map; } P{};
+    {
+        const int N = domain_size(n);
+        std::vector<int> blk;
+        blk.reserve(2 * S + 2 * (size_t)N + 8);
+        blk.insert(blk.end(), order.begin(), order.end());                               // [0, S): order; col_map = its first m entries
+        const size_t off_in = blk.size();
+        std::vector<int> in_map((size_t)N, -1), er_map((size_t)N, -1);
+        for (size_t i = 0; i < S; ++i) in_map[sorted_ids[i]] = order[i];
+        for (size_t i = 0; i < needed; ++i) er_map[sorted_ids[i]] = order[i];
+        blk.insert(blk.end(), in_map.begin(), in_map.end());
+        const size_t off_er = blk.size();
+        blk.insert(blk.end(), er_map.begin(), er_map.end());
+        const size_t bytes = blk.size() * sizeof(int);
+        if (ctx->maps.cap < bytes) {
+            CK(cudaStreamSynchronize(ctx->main_stream()));
+            if (ctx->maps.p) CK(cudaFree(ctx->maps.p));
+            ctx->maps.p = nullptr;
+            CK(cudaMalloc(&ctx->maps.p, bytes + 4096));
+            ctx->maps.cap = bytes + 4096;
+        }
+        // pageable source: the runtime stages the bytes before returning, stream order protects kernels of earlier calls
+        CK(cudaMemcpyAsync(ctx->maps.p, blk.data(), bytes, cudaMemcpyHostToDevice, ctx->main_stream()));
+        const int *base = (const int *)ctx->maps.p;
+        P.order = base;
+        P.col_map = base;            // column c of the optimistic matrix reads the share of sorted position c
+        P.chk_map = base + m;        // check row r compares with the share of sorted position m + r
+        P.in_map = base + off_in;
+        P.er_in_map = base + off_er;
+    }
     const int fw = want_flags ? (int)((S + 63) / 64) : 0;
     const bool want_secrets = !secrets_only && secrets != nullptr;
 
@@ -880,8 +900,8 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
     const WsLayout lay(T.nsyn_max, (int)t, domain_size(n));
 
     // Lean host path: when the shares arrive in host memory sender-major and no flags are wanted, only the d+t+1 examined
-    // sender vectors are uploaded and the dense optimistic check runs (PCIe, not the SMs, bounds such calls); chunks in which
-    // some item fails are re-run afterwards with every sender vector uploaded (robust decoding needs them all).
+    // sender vectors are uploaded and the optimistic check runs on them (PCIe, not the SMs, bounds such calls); chunks in
+    // which some item fails are re-run afterwards with every sender vector uploaded (robust decoding needs them all).
     std::vector<int> lean_rows;
     BatchBuf bi_lean = bi;
     const bool lean = bi.host && sender_major && !want_flags && S > needed;
@@ -936,7 +956,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             na.cols = (int)S;
             na.n = (int)S;
             na.err = ctx->d_status;
-            na.in_map = T.in_map;
+            na.in_map = P.in_map;
             na.scale = T.iscale;
             na.m = (int)m;
             na.mout = T.mout;
@@ -961,7 +981,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             na.cols = 1 << T.er_logn;
             na.n = 1 << T.er_logn;
             na.err = ctx->d_status;
-            na.in_map = T.er_in_map;
+            na.in_map = P.er_in_map;
             na.wt = T.er_wt;
             na.m = T.er_zero_from;
             na.mout = T.mout;
@@ -991,10 +1011,10 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         a.in_chunk_major = sender_major ? 0 : 1;
         a.out_sb = T.mout;
         a.out_sr = 1;
-        a.col_map = T.col_map;
+        a.col_map = P.col_map;
         a.n_chk = T.n_chk;
         a.n_gate = T.n_gate;
-        a.chk_map = T.chk_map;
+        a.chk_map = P.chk_map;
         a.fail = fail;
         a.flags = want_flags ? (unsigned long long *)vf.dev : nullptr;
         if (!erasure && (rc = launch_matvec(ctx, ln.stream, a, fw))) return rc;
@@ -1014,7 +1034,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             lc.in_sb = vi.sb; lc.in_sc = vi.sj;
             lc.in_chunk_major = sender_major ? 0 : 1;
             lc.out_sb = T.mout; lc.out_sr = 1;
-            lc.col_map = T.col_map;
+            lc.col_map = P.col_map;
             lc.item_list = list; lc.item_count = count;
             if ((rc = launch_matvec(ctx, ln.stream, lc, 0))) return rc;
         }
@@ -1033,7 +1053,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         r.S = (int)S; r.m = (int)m; r.t = (int)t; r.needed = (int)needed; r.rmax = T.rmax; r.fast = T.fast;
         r.att_P = T.att_P; r.att_nsyn = T.att_nsyn; r.att_maxL = T.att_maxL; r.att_uoff = T.att_uoff;
         r.u2 = T.u2; r.sid = T.sid; r.tw = T.tw; r.itw = T.ritw; r.uinv = T.uinv;
-        { int lg = 0; while ((1 << lg) < domain_size(n)) ++lg; r.logn = lg; } r.xs = T.xs; r.xinv = T.xinv; r.Lc = T.Lc; r.Veval = T.Veval; r.order = T.order;
+        { int lg = 0; while ((1 << lg) < domain_size(n)) ++lg; r.logn = lg; } r.xs = T.xs; r.xinv = T.xinv; r.Lc = T.Lc; r.Veval = T.Veval; r.order = P.order;
         r.coeffs = (uint4 *)vc.dev;
         r.mout = T.mout;
         r.path = (int *)vp.dev;
