@@ -165,6 +165,7 @@ struct RecoverTables {
     int er_logn = 0, er_zero_from = 0;
     int *er_row_len = nullptr;
     uint4 *er_wt = nullptr, *er_tri = nullptr;
+    std::vector<void *> allocs;  // device memory of this entry (freed when the entry is evicted)
 };
 
 struct hbmpc_ctx {
@@ -232,21 +233,21 @@ static int scratch_get(hbmpc_ctx *ctx, Lane &ln, int slot, size_t bytes, void **
 }
 
 template <typename T>
-static int upload(hbmpc_ctx *ctx, const std::vector<T> &v, T **out) {
+static int upload(hbmpc_ctx *ctx, const std::vector<T> &v, T **out, std::vector<void *> *owner = nullptr) {
     void *p = nullptr;
     size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
     CK(cudaMalloc(&p, bytes));
-    ctx->owned.push_back(p);
+    (owner ? *owner : ctx->owned).push_back(p);
     if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     *out = (T *)p;
     return 0;
 }
 
-static int upload_fr(hbmpc_ctx *ctx, const std::vector<HFr> &v, uint4 **out) {
+static int upload_fr(hbmpc_ctx *ctx, const std::vector<HFr> &v, uint4 **out, std::vector<void *> *owner = nullptr) {
     std::vector<uint32_t> w;
     to_u32(v, w);
     uint32_t *p = nullptr;
-    int rc = upload(ctx, w, &p);
+    int rc = upload(ctx, w, &p, owner);
     *out = (uint4 *)p;
     return rc;
 }
@@ -306,6 +307,8 @@ extern "C" void hbmpc_ctx_destroy(hbmpc_ctx *ctx) {
     for (auto &ln : ctx->lanes)
         if (ln.stream) cudaStreamSynchronize(ln.stream);
     for (void *p : ctx->owned) cudaFree(p);
+    for (auto &e : ctx->recover)
+        for (void *q : e.second.allocs) cudaFree(q);
     for (auto &ln : ctx->lanes)
         for (auto &b : ln.scratch)
             if (b.p) cudaFree(b.p);
@@ -699,7 +702,7 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
     T.n_gate = (int)t;
     T.mout = (int)mout;
     int rc;
-    if ((rc = upload_fr(ctx, M, &T.M))) return rc;
+    if ((rc = upload_fr(ctx, M, &T.M, &T.allocs))) return rc;
 
     // robust tables
     T.rmax = (int)std::min(t, S - needed);
@@ -748,24 +751,24 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
     std::vector<HFr> xinv(xs);
     hfr::batch_inv(xinv);
     std::vector<HFr> Veval = vandermonde_on_points(xs, m);
-    if ((rc = upload(ctx, att_P, &T.att_P))) return rc;
-    if ((rc = upload(ctx, att_nsyn, &T.att_nsyn))) return rc;
-    if ((rc = upload(ctx, att_maxL, &T.att_maxL))) return rc;
-    if ((rc = upload(ctx, att_uoff, &T.att_uoff))) return rc;
-    if ((rc = upload_fr(ctx, U2, &T.u2))) return rc;
+    if ((rc = upload(ctx, att_P, &T.att_P, &T.allocs))) return rc;
+    if ((rc = upload(ctx, att_nsyn, &T.att_nsyn, &T.allocs))) return rc;
+    if ((rc = upload(ctx, att_maxL, &T.att_maxL, &T.allocs))) return rc;
+    if ((rc = upload(ctx, att_uoff, &T.att_uoff, &T.allocs))) return rc;
+    if ((rc = upload_fr(ctx, U2, &T.u2, &T.allocs))) return rc;
     {
         std::vector<int> sid(S);
         for (size_t i = 0; i < S; ++i) sid[i] = (int)sorted_ids[i];
-        if ((rc = upload(ctx, sid, &T.sid))) return rc;
+        if ((rc = upload(ctx, sid, &T.sid, &T.allocs))) return rc;
         uint4 *sc = nullptr;
         if ((rc = get_twiddles(ctx, domain_size(n), &T.tw))) return rc;
         if ((rc = get_inverse_twiddles(ctx, domain_size(n), &T.ritw, &sc))) return rc;
     }
-    if ((rc = upload_fr(ctx, U, &T.uinv))) return rc;
-    if ((rc = upload_fr(ctx, xs, &T.xs))) return rc;
-    if ((rc = upload_fr(ctx, xinv, &T.xinv))) return rc;
-    if ((rc = upload_fr(ctx, L.Lc, &T.Lc))) return rc;
-    if ((rc = upload_fr(ctx, Veval, &T.Veval))) return rc;
+    if ((rc = upload_fr(ctx, U, &T.uinv, &T.allocs))) return rc;
+    if ((rc = upload_fr(ctx, xs, &T.xs, &T.allocs))) return rc;
+    if ((rc = upload_fr(ctx, xinv, &T.xinv, &T.allocs))) return rc;
+    if ((rc = upload_fr(ctx, L.Lc, &T.Lc, &T.allocs))) return rc;
+    if ((rc = upload_fr(ctx, Veval, &T.Veval, &T.allocs))) return rc;
     // every point of the power-of-two domain supplied: coefficients by one inverse NTT, checked by "top coefficients vanish"
     const int N = domain_size(n);
     if (!ctx->no_fastpath && S == n && (size_t)N == n && N >= 2) {
@@ -812,9 +815,9 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
             row_len[k] = (int)k + 1;
             for (size_t i = 0; i <= k; ++i) tri[k * mout + i] = W[k - i];
         }
-        if ((rc = upload(ctx, row_len, &T.er_row_len))) return rc;
-        if ((rc = upload_fr(ctx, wt, &T.er_wt))) return rc;
-        if ((rc = upload_fr(ctx, tri, &T.er_tri))) return rc;
+        if ((rc = upload(ctx, row_len, &T.er_row_len, &T.allocs))) return rc;
+        if ((rc = upload_fr(ctx, wt, &T.er_wt, &T.allocs))) return rc;
+        if ((rc = upload_fr(ctx, tri, &T.er_tri, &T.allocs))) return rc;
         if (!T.itw && (rc = get_inverse_twiddles(ctx, N, &T.itw, &T.iscale))) return rc;
         T.er_zero_from = N - (int)t;
         while ((1 << T.er_logn) < N) ++T.er_logn;
@@ -852,6 +855,12 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
     for (size_t i = 0; i < S; ++i) key += " " + std::to_string(sorted_ids[i]);  // the field tables depend on the id SET only
     auto it = ctx->recover.find(key);
     if (it == ctx->recover.end()) {
+        if (ctx->recover.size() >= 256) {  // bounded cache: sender sets differ from session to session
+            for (auto &ln : ctx->lanes) CK(cudaStreamSynchronize(ln.stream));
+            for (auto &e : ctx->recover)
+                for (void *q : e.second.allocs) cudaFree(q);
+            ctx->recover.clear();
+        }
         RecoverTables T;
         int rc = build_recover_tables(ctx, n, d, t, S, sorted_ids, want_flags, secrets_only, T);
         if (rc) return rc;

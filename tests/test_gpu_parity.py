@@ -586,3 +586,27 @@ def test_randomized_configurations(ctx, orc):
         # a10 on the clean word: degree d interpolant through all S points
         co10, sec10, st10 = ctx.nonrobust_recover_batch(ids, words, n, d)
         assert np.array_equal(co10, coeffs) and np.array_equal(sec10, coeffs[:, 0]), key
+
+
+def test_table_cache_eviction(hb, orc):
+    """More distinct sender sets than the table cache holds (256): entries are evicted and rebuilt, results stay exact."""
+    n, t, d, B = 16, 5, 5, 8
+    c = hb.Context(0)
+    try:
+        coeffs, shares = _codewords(orc, n, d, B, 4711)
+        rng = np.random.default_rng(4711)
+        seen = set()
+        for k in range(500):
+            S = int(rng.integers(d + t + 1, n - 1))
+            ids = rng.permutation(n)[:S]
+            seen.add(tuple(sorted(ids.tolist())))
+            ev = np.ascontiguousarray(shares[:, ids].transpose(1, 0, 2))
+            if k % 3 == 0:
+                ev = ev.copy()
+                ev[0, 1, 0] ^= np.uint64(5)   # one error in item 1 -> robust path when S allows it
+            want = orc.batch_recover_secret(ids, ev, n, d, t)
+            got = c.batch_recover(ids, ev, n, d, t)
+            assert got[0] == want["rc"] and np.array_equal(got[2], want["path"]) and np.array_equal(got[1], want["coeffs"]), k
+        assert len(seen) > 256
+    finally:
+        c.close()
