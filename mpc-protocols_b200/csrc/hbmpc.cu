@@ -1302,3 +1302,10 @@ extern "C" int hbmpc_measure_imad_peak(hbmpc_ctx *ctx, int variant, double *giga
     if (elapsed_ms) *elapsed_ms = best;
     return HBMPC_SUCCESS;
 }
+
+#ifdef HB_ROBUST_PROF
+// profiling builds only (tools/robust_prof.py): per-phase cycle sums of robust_kernel
+extern "C" void hbmpc_debug_read_robust_prof(unsigned long long *out) {
+    cudaMemcpyFromSymbol(out, hb::g_robust_prof, sizeof(unsigned long long) * 8);
+}
+#endif

@@ -34,6 +34,13 @@
 
 namespace hb {
 
+#ifdef HB_ROBUST_PROF
+__device__ unsigned long long g_robust_prof[8];  // cycles: syndromes, BM, omega, chien, forney, inversion+values, finish, items
+#define HB_PROF_MARK(slot) do { long long t_ = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&g_robust_prof[slot], (unsigned long long)(t_ - prof_t)); prof_t = t_; } while (0)
+#else
+#define HB_PROF_MARK(slot) do { } while (0)
+#endif
+
 struct RobustArgs {
     const uint4 *in;            // supplied shares: element (b, arrival j) at in[(b*in_sb + j*in_sc)*2 ..]
     long long in_sb, in_sc, B;
@@ -165,6 +172,9 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
     const uint4 *ybase = a.in + b * a.in_sb * 2;
     uint32_t zero[8];
     set_zero(zero);
+#ifdef HB_ROBUST_PROF
+    long long prof_t = clock64();
+#endif
 
     // ---- syndromes (Montgomery form): forward transform of the weighted word, S_j = sum_i (u_i y_i) w^(id_i j)
 #pragma unroll 1
@@ -178,6 +188,7 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
         ws.st(lay.syn + bitrev_n(a.sid[i], a.logn), w);
     }
     ntt_serial(ws, lay.syn, a.logn, a.tw);
+    HB_PROF_MARK(0);
 
     // ---- inversion-free Berlekamp-Massey:  Lambda <- bdis*Lambda - delta * z^shift * Bp
     uint32_t one[8], bdis[8];
@@ -232,6 +243,7 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
             ++shift;
         }
     }
+    HB_PROF_MARK(1);
     if (L == 0) return 0;
 
     // ---- Forney numerator polynomial first (it needs the syndromes, which share the transform buffer):
@@ -252,9 +264,13 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
         ws.st(lay.om + l, o);
     }
 
+    HB_PROF_MARK(2);
     // ---- Chien search over the prefix points: Lambda(x_i^{-1}) == 0  <=>  position i is in error
     int nroots = 0;
-    const bool chien_ntt = L >= 4;
+    // warp-uniform choice (lanes hold different L): one transform for everybody beats paying for both code paths
+    const int Lmax = __reduce_max_sync(__activemask(), L);
+    const int nbfly = (N >> 1) * a.logn;          // products of one size-N transform
+    const bool chien_ntt = Lmax * P > nbfly;      // direct: L Horner steps at each of the P points
     if (chien_ntt) {  // all N values Lambda(w^-j) with one inverse-direction transform
 #pragma unroll 1
         for (int p = 0; p < N; ++p) ws.st(lay.syn + p, zero);
@@ -288,16 +304,13 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
             ++nroots;
         }
     }
+    HB_PROF_MARK(3);
     if (nroots != L) return -1;
 
     // ---- Forney:  c_i = -x_i Omega(x_i^{-1}) / Lambda'(x_i^{-1});  e_i = c_i * uinv_i
-    uint32_t Lm[8];  // Montgomery form of the integer L
-    set_zero(Lm);
-#pragma unroll 1
-    for (int l = 0; l < L; ++l) { uint32_t tsum[8]; fr_add(tsum, Lm, one); copy8(Lm, tsum); }
     uint32_t run[8];
     copy8(run, one);
-    const bool forney_ntt = L > 24;
+    const bool forney_ntt = 2 * Lmax * Lmax + Lmax > 2 * nbfly;  // direct: 2 L^2 + L products for Omega and Lambda' at the L roots
     if (forney_ntt) {
         // numerators: Omega at every w^-j
 #pragma unroll 1
@@ -343,36 +356,40 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
             copy8(run, nr);
         }
     } else {
+    // derivative coefficients dL_{l-1} = l * Lambda_l once (the B polynomial of Berlekamp-Massey is dead: reuse its slots)
+    {
+        uint32_t lm[8];
+        copy8(lm, one);
+#pragma unroll 1
+        for (int l = 1; l <= L; ++l) {
+            uint32_t c[8], lc[8], nl[8];
+            ws.ld(c, lay.lam + l);
+            mont_mul(lc, c, lm);
+            ws.st(lay.bp + l - 1, lc);
+            fr_add(nl, lm, one);
+            copy8(lm, nl);
+        }
+    }
 #pragma unroll 1
     for (int q = 0; q < L; ++q) {
         const int i = rootpos[q];
-        uint32_t z[8], x[8], v[8], dv[8], lm[8];
+        uint32_t z[8], x[8], v[8], dv[8];
         ldg_fr(z, a.xinv + i * 2);
         ldg_fr(x, a.xs + i * 2);
         ws.ld(v, lay.om + L - 1);
+        ws.ld(dv, lay.bp + L - 1);
 #pragma unroll 1
         for (int l = L - 2; l >= 0; --l) {
-            uint32_t c[8], p[8];
+            uint32_t c[8], p[8], c2[8], p2[8];
             mont_mul(p, v, z);
             ws.ld(c, lay.om + l);
             fr_add(v, p, c);
+            mont_mul(p2, dv, z);
+            ws.ld(c2, lay.bp + l);
+            fr_add(dv, p2, c2);
         }
         uint32_t numv[8];
         mont_mul(numv, v, x);
-        // Lambda'(z) = sum_{l=1..L} l * Lambda_l z^(l-1)
-        copy8(lm, Lm);
-        set_zero(dv);
-#pragma unroll 1
-        for (int l = L; l >= 1; --l) {
-            uint32_t c[8], p[8], lc[8];
-            mont_mul(p, dv, z);
-            ws.ld(c, lay.lam + l);
-            mont_mul(lc, c, lm);
-            fr_add(dv, p, lc);
-            uint32_t nl[8];
-            fr_sub(nl, lm, one);
-            copy8(lm, nl);
-        }
         if (fr_is_zero(dv)) return -1;
         ws.st(lay.num + q, numv);
         ws.st(lay.den + q, dv);
@@ -382,6 +399,7 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
         copy8(run, nr);
     }
     }
+    HB_PROF_MARK(4);
     uint32_t inv[8];
     fr_inv_mont(inv, run);
     const uint4 *U = a.uinv + a.att_uoff[att] * 2;
@@ -400,6 +418,7 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
         mont_mul(e, nc, u);  // Montgomery c times canonical uinv -> canonical error value
         ws.st(lay.ev + q, e);
     }
+    HB_PROF_MARK(5);
     return L;
 }
 
