@@ -117,6 +117,14 @@ int hbmpc_nonrobust_recover_batch(hbmpc_ctx *ctx, size_t n, size_t deg, size_t S
  * multiplication.rs:79-97,417-426): out[i] = a[i] (op) b[i], op: 0 add, 1 sub, 2 mul (share_mul / Mul<F>). */
 int hbmpc_elementwise(hbmpc_ctx *ctx, int op, size_t count, const uint64_t *a, const uint64_t *b, uint64_t *out);
 
+/* N1 (wire format).  ark-serialize writes a ShamirShare<F,1,_> record as 32-byte LE canonical value + u64 id + u64 degree
+ * (48 bytes; Vec<RobustShare> payloads of share_gen.rs:255-268, ran_dou_sha/messages.rs:40-46).  These helpers split such
+ * records into the value array the kernels consume (ids / degrees optional, may be NULL) and build records from values
+ * without a host-side repacking pass; `records` may be only 8-byte aligned (payload + 8 after the Vec length prefix).
+ * pack: record i gets id = i / per_id and the given degree. */
+int hbmpc_unpack_share_records(hbmpc_ctx *ctx, size_t count, const void *records, uint64_t *values, uint64_t *ids, uint64_t *degrees);
+int hbmpc_pack_share_records(hbmpc_ctx *ctx, size_t count, const uint64_t *values, size_t per_id, size_t degree, void *records);
+
 /* Integer-pipe roofline probe: runs a register-only dependent-chain microkernel on every SM and returns the sustained
  * rate in 1e9 thread-level instructions per second.  variant: 0 = mad.lo.u32 (IMAD, the north star's "IMAD peak"),
  * 1 = IMAD.WIDE.U32(.X) carry chains (the 32x32->64 multiply-add the product kernels issue), 2 = DFMA (FP64 pipe). */

@@ -32,7 +32,8 @@ EXPORTS = [
     "hbmpc_ctx_create", "hbmpc_ctx_destroy", "hbmpc_ctx_set_stream", "hbmpc_ctx_set_async", "hbmpc_ctx_synchronize",
     "hbmpc_ctx_launch_count", "hbmpc_last_error", "hbmpc_compute_shares_batch", "hbmpc_apply_vandermonde_batch",
     "hbmpc_apply_matrix_batch", "hbmpc_batch_recover", "hbmpc_batch_recover_secrets", "hbmpc_robust_interpolate_batch",
-    "hbmpc_nonrobust_recover_batch", "hbmpc_elementwise", "hbmpc_measure_imad_peak",
+    "hbmpc_nonrobust_recover_batch", "hbmpc_elementwise", "hbmpc_unpack_share_records", "hbmpc_pack_share_records",
+    "hbmpc_measure_imad_peak",
 ]
 
 
@@ -72,6 +73,8 @@ def load_library():
     lib.hbmpc_robust_interpolate_batch.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp, vp, vp]
     lib.hbmpc_nonrobust_recover_batch.argtypes = [vp, sz, sz, sz, vp, sz, vp, ci, vp, vp, vp]
     lib.hbmpc_elementwise.argtypes = [vp, ci, sz, vp, vp, vp]
+    lib.hbmpc_unpack_share_records.argtypes = [vp, sz, vp, vp, vp, vp]
+    lib.hbmpc_pack_share_records.argtypes = [vp, sz, vp, sz, sz, vp]
     lib.hbmpc_measure_imad_peak.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = lib
     return lib
@@ -251,6 +254,21 @@ class Context:
         count = int(np.prod(x.shape[:-1]))
         out = x.like(x.shape) if out is None else out
         self._check(self.lib.hbmpc_elementwise(self.h, op, count, x.ptr, y.ptr, _ptr(out)))
+        return out
+
+    # -- N1: 48-byte ark-serialize share records
+    def unpack_share_records(self, records: np.ndarray, count: int):
+        """records: uint8 buffer of count*48 bytes (host) -> (values uint64[count][4], ids uint64[count], degrees uint64[count])"""
+        rec = np.ascontiguousarray(records, dtype=np.uint8)
+        values = np.zeros((count, 4), dtype=np.uint64)
+        ids, degs = np.zeros(count, dtype=np.uint64), np.zeros(count, dtype=np.uint64)
+        self._check(self.lib.hbmpc_unpack_share_records(self.h, count, rec.ctypes.data, values.ctypes.data, ids.ctypes.data, degs.ctypes.data))
+        return values, ids, degs
+
+    def pack_share_records(self, values, per_id: int, degree: int) -> np.ndarray:
+        v = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1, 4)
+        out = np.zeros(v.shape[0] * 48, dtype=np.uint8)
+        self._check(self.lib.hbmpc_pack_share_records(self.h, v.shape[0], v.ctypes.data, per_id, degree, out.ctypes.data))
         return out
 
     def measure_imad_peak(self, variant: int = 0):

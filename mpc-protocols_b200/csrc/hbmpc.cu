@@ -74,6 +74,26 @@ __global__ void degree_status_kernel(long long B, int m, uint4 *coeffs, const un
     }
 }
 
+// N1 wire records: ark-serialize writes a ShamirShare<F,1,_> as 32-byte LE canonical value + u64 id + u64 degree (48 bytes,
+// 8-byte aligned inside a payload).  Split / join such records without a host-side repacking pass.
+__global__ void unpack_records_kernel(long long count, const unsigned long long *rec, unsigned long long *values, unsigned long long *ids,
+                                      unsigned long long *degrees) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long *r = rec + i * 6;
+        values[i * 4 + 0] = r[0]; values[i * 4 + 1] = r[1]; values[i * 4 + 2] = r[2]; values[i * 4 + 3] = r[3];
+        if (ids) ids[i] = r[4];
+        if (degrees) degrees[i] = r[5];
+    }
+}
+__global__ void pack_records_kernel(long long count, const unsigned long long *values, long long per_id, unsigned long long degree, unsigned long long *rec) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long *r = rec + i * 6;
+        r[0] = values[i * 4 + 0]; r[1] = values[i * 4 + 1]; r[2] = values[i * 4 + 2]; r[3] = values[i * 4 + 3];
+        r[4] = (unsigned long long)(i / per_id);
+        r[5] = degree;
+    }
+}
+
 // Integer-pipe roofline probes (register-only, multiplicands depend on the running values so nothing is hoisted):
 //   0: mad.lo.u32 (IMAD)            -- the "IMAD peak" of the north star: 64 lanes/clk/SM
 //   1: IMAD.WIDE.U32(.X) 4-lane carry chains, the product kernels' instruction (32x32->64 multiply-add)
@@ -1268,6 +1288,65 @@ extern "C" int hbmpc_elementwise(hbmpc_ctx *ctx, int op, size_t count, const uin
         return chunk_commit(ctx, ln, bo, b0, Bc, vo);
     };
     return run_batched(ctx, count, ba.host || bb.host || bo.host, 32, body);
+}
+
+// ------------------------------------------------------------------------------------------------ N1: 48-byte share records
+extern "C" int hbmpc_unpack_share_records(hbmpc_ctx *ctx, size_t count, const void *records, uint64_t *values, uint64_t *ids, uint64_t *degrees) {
+    if (!ctx) return HBMPC_INVALID_INPUT;
+    if (count == 0) return HBMPC_SUCCESS;
+    if (!records || !values) return HBMPC_INVALID_INPUT;
+    cudaSetDevice(ctx->device);
+    BatchBuf br = make_buf(records, count, 1, false, 48), bv = make_buf(values, count, 1, false, 32);
+    BatchBuf bi = make_buf(ids, count, 1, false, 8), bd = make_buf(degrees, count, 1, false, 8);
+    auto body = [&](Lane &ln, size_t b0, size_t Bc) -> int {
+        ChunkView vr, vv, vi, vd;
+        int rc;
+        if ((rc = chunk_prepare(ctx, ln, 0, br, b0, Bc, true, vr))) return rc;
+        if ((rc = chunk_prepare(ctx, ln, 1, bv, b0, Bc, false, vv))) return rc;
+        if ((rc = chunk_prepare(ctx, ln, 2, bi, b0, Bc, false, vi))) return rc;
+        if ((rc = chunk_prepare(ctx, ln, 3, bd, b0, Bc, false, vd))) return rc;
+        long long blocks = std::min<long long>((long long)ctx->num_sms * 8, (long long)((Bc + 255) / 256));
+        unpack_records_kernel<<<(unsigned)blocks, 256, 0, ln.stream>>>((long long)Bc, (const unsigned long long *)vr.dev, (unsigned long long *)vv.dev,
+                                                                     (unsigned long long *)vi.dev, (unsigned long long *)vd.dev);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        if ((rc = chunk_commit(ctx, ln, bv, b0, Bc, vv))) return rc;
+        if ((rc = chunk_commit(ctx, ln, bi, b0, Bc, vi))) return rc;
+        return chunk_commit(ctx, ln, bd, b0, Bc, vd);
+    };
+    return run_batched(ctx, count, br.host || bv.host || (ids && bi.host) || (degrees && bd.host), 48, body);
+}
+
+// records[i] = (values[i], id = i / per_id, degree): per_id consecutive values belong to the same share id
+// (per_id = 1: the n shares of one sharing, ids 0..n-1; per_id = B: recipient-major [n][B] batches)
+extern "C" int hbmpc_pack_share_records(hbmpc_ctx *ctx, size_t count, const uint64_t *values, size_t per_id, size_t degree, void *records) {
+    if (!ctx) return HBMPC_INVALID_INPUT;
+    if (count == 0) return HBMPC_SUCCESS;
+    if (!records || !values || per_id == 0) return HBMPC_INVALID_INPUT;
+    cudaSetDevice(ctx->device);
+    BatchBuf br = make_buf(records, count, 1, false, 48), bv = make_buf(values, count, 1, false, 32);
+    if (br.host || bv.host) {
+        // ids depend on the global index: keep host calls in one piece (these payloads are message sized)
+        Lane &ln = ctx->lanes[1];
+        CK(cudaEventRecord(ctx->ev_main, ctx->main_stream()));
+        CK(cudaStreamWaitEvent(ln.stream, ctx->ev_main, 0));
+        ChunkView vr, vv;
+        int rc;
+        if ((rc = chunk_prepare(ctx, ln, 0, bv, 0, count, true, vv))) return rc;
+        if ((rc = chunk_prepare(ctx, ln, 1, br, 0, count, false, vr))) return rc;
+        long long blocks = std::min<long long>((long long)ctx->num_sms * 8, (long long)((count + 255) / 256));
+        pack_records_kernel<<<(unsigned)blocks, 256, 0, ln.stream>>>((long long)count, (const unsigned long long *)vv.dev, (long long)per_id, degree, (unsigned long long *)vr.dev);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        if ((rc = chunk_commit(ctx, ln, br, 0, count, vr))) return rc;
+        CK(cudaStreamSynchronize(ln.stream));
+        return HBMPC_SUCCESS;
+    }
+    long long blocks = std::min<long long>((long long)ctx->num_sms * 8, (long long)((count + 255) / 256));
+    pack_records_kernel<<<(unsigned)blocks, 256, 0, ctx->main_stream()>>>((long long)count, (const unsigned long long *)values, (long long)per_id, degree, (unsigned long long *)records);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return ctx->async ? HBMPC_SUCCESS : collect_status(ctx);
 }
 
 extern "C" int hbmpc_measure_imad_peak(hbmpc_ctx *ctx, int variant, double *giga_inst_per_s, double *elapsed_ms) {

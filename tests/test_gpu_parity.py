@@ -610,3 +610,26 @@ def test_table_cache_eviction(hb, orc):
         assert len(seen) > 256
     finally:
         c.close()
+
+
+def test_share_record_pack_unpack(ctx, orc):
+    """N1: 48-byte ark-serialize ShamirShare records (value | u64 id | u64 degree) <-> value arrays, including an
+    8-byte-aligned payload offset and more records than one pipeline chunk."""
+    n, d, B = 16, 5, 3
+    coeffs = _rand(orc, (B, d + 1), 0xBEEF)
+    shares = ctx.compute_shares_batch(coeffs, n)                      # [B][n]
+    for b in range(B):
+        rec = ctx.pack_share_records(shares[b], per_id=1, degree=d)  # the n shares of one sharing: ids 0..n-1
+        raw = rec.reshape(n, 48)
+        assert np.array_equal(raw[:, :32].copy().view(np.uint64).reshape(n, 4), shares[b])
+        assert raw[:, 32:40].copy().view(np.uint64).reshape(-1).tolist() == list(range(n))
+        assert (raw[:, 40:48].copy().view(np.uint64).reshape(-1) == d).all()
+        payload = np.zeros(8 + rec.size, dtype=np.uint8)             # Vec length prefix + records
+        payload[:8] = np.frombuffer(np.uint64(n).tobytes(), dtype=np.uint8)
+        payload[8:] = rec
+        vals, ids, degs = ctx.unpack_share_records(payload[8:], n)
+        assert np.array_equal(vals, shares[b]) and ids.tolist() == list(range(n)) and (degs == d).all()
+    big = _rand(orc, (400000,), 5)                                   # > one 16 MB chunk of 48-byte records
+    rec = ctx.pack_share_records(big, per_id=100000, degree=7)
+    vals, ids, degs = ctx.unpack_share_records(rec, 400000)
+    assert np.array_equal(vals, big) and np.array_equal(ids, np.arange(400000, dtype=np.uint64) // 100000) and (degs == 7).all()
