@@ -633,3 +633,19 @@ def test_share_record_pack_unpack(ctx, orc):
     rec = ctx.pack_share_records(big, per_id=100000, degree=7)
     vals, ids, degs = ctx.unpack_share_records(rec, 400000)
     assert np.array_equal(vals, big) and np.array_equal(ids, np.arange(400000, dtype=np.uint64) // 100000) and (degs == 7).all()
+
+
+@pytest.mark.parametrize("n,t,d", [(1, 0, 0), (2, 0, 0), (2, 0, 1), (3, 0, 2), (4, 1, 1), (4, 1, 2), (5, 1, 3), (255, 84, 84)])
+def test_tiny_and_maximal_party_counts(ctx, orc, n, t, d):
+    B = 9
+    coeffs, shares = _codewords(orc, n, d, B, 0x5EED4000 + n + d)
+    assert np.array_equal(ctx.compute_shares_batch(coeffs, n), shares)
+    ids = np.arange(n)
+    ev = np.ascontiguousarray(shares.transpose(1, 0, 2))
+    want = orc.batch_recover_secret(ids, ev, n, d, t, threads=orc.max_threads())
+    for fl in (False, True):
+        got = ctx.batch_recover(ids, ev, n, d, t, want_flags=fl)
+        _compare_recover(got, want, B)
+    assert np.array_equal(want["coeffs"], coeffs)
+    co, sec, st = ctx.nonrobust_recover_batch(ids, shares, n, d)
+    assert np.array_equal(co, coeffs) and np.array_equal(sec, coeffs[:, 0])
