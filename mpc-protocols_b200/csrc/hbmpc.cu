@@ -486,12 +486,43 @@ static int run_batched(hbmpc_ctx *ctx, size_t B, bool any_host, size_t max_item_
 }
 
 // ------------------------------------------------------------------------------------------------ kernel launches
-static int launch_matvec(hbmpc_ctx *ctx, cudaStream_t st, MatvecArgs a, int flag_words) {
+static int launch_matvec(hbmpc_ctx *ctx, Lane &ln, MatvecArgs a, int flag_words) {
+    cudaStream_t st = ln.stream;
     if (a.B == 0) return 0;
     MatvecPlan p = matvec_plan(a.R, a.C, flag_words, ctx->matvec_regs > 0 ? ctx->matvec_regs : 112);
     if (p.tbt == 0) {
-        ctx->err = "matvec: no launch shape fits shared memory";
-        return HBMPC_INVALID_INPUT;
+        // too wide for one shared-memory tile: two column blocks into temporaries, then add + row semantics
+        if (a.C < 2 || a.row_len) {
+            ctx->err = "matvec: no launch shape fits shared memory";
+            return HBMPC_INVALID_INPUT;
+        }
+        void *tmp = nullptr;
+        const size_t tbytes = (size_t)a.B * a.R * 32;
+        int rc = scratch_get(ctx, ln, 8, 2 * tbytes, &tmp);
+        if (rc) return rc;
+        uint4 *T1 = (uint4 *)tmp, *T2 = (uint4 *)((char *)tmp + tbytes);
+        const int ld = a.M_ld ? a.M_ld : a.C, C1 = a.C / 2;
+        for (int h = 0; h < 2; ++h) {
+            MatvecArgs s = a;
+            s.M = a.M + (size_t)(h ? C1 : 0) * 2;
+            s.M_ld = ld;
+            s.C = h ? a.C - C1 : C1;
+            s.col0 = a.col0 + (h ? C1 : 0);
+            s.out = h ? T2 : T1;
+            s.out_sb = a.R;
+            s.out_sr = 1;
+            s.n_chk = 0;
+            s.n_gate = 0;
+            s.chk_map = nullptr;
+            s.fail = nullptr;
+            s.flags = nullptr;
+            if ((rc = launch_matvec(ctx, ln, s, 0))) return rc;
+        }
+        a.flag_words = flag_words;
+        matvec_combine_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(a, T1, T2);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return 0;
     }
     a.rows_per_slice = p.rows_per_slice;
     a.flag_words = flag_words;
@@ -622,7 +653,7 @@ static int apply_map(hbmpc_ctx *ctx, const uint4 *M, const uint4 *tw, int logn, 
             a.B = (long long)Bc;
             a.in_sb = vi.sb; a.in_sc = vi.sj; a.in_chunk_major = 1;
             a.out_sb = vo.sb; a.out_sr = vo.sj;
-            if ((rc = launch_matvec(ctx, ln.stream, a, 0))) return rc;
+            if ((rc = launch_matvec(ctx, ln, a, 0))) return rc;
         } else {
             NttArgs a{};
             a.in = (const uint4 *)vi.dev;
@@ -1026,7 +1057,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             tr.in_sb = T.mout; tr.in_sc = 1; tr.in_chunk_major = 1;
             tr.out_sb = T.mout; tr.out_sr = 1;
             tr.row_len = T.er_row_len;
-            if ((rc = launch_matvec(ctx, ln.stream, tr, 0))) return rc;
+            if ((rc = launch_matvec(ctx, ln, tr, 0))) return rc;
         }
         MatvecArgs a{};
         if (fastN) { a.item_list = list1; a.item_count = count1; }
@@ -1046,7 +1077,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         a.chk_map = P.chk_map;
         a.fail = fail;
         a.flags = want_flags ? (unsigned long long *)vf.dev : nullptr;
-        if (!erasure && (rc = launch_matvec(ctx, ln.stream, a, fw))) return rc;
+        if (!erasure && (rc = launch_matvec(ctx, ln, a, fw))) return rc;
 
         compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail, (long long)Bc, list, count);
         ctx->launches++;
@@ -1065,7 +1096,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             lc.out_sb = T.mout; lc.out_sr = 1;
             lc.col_map = P.col_map;
             lc.item_list = list; lc.item_count = count;
-            if ((rc = launch_matvec(ctx, ln.stream, lc, 0))) return rc;
+            if ((rc = launch_matvec(ctx, ln, lc, 0))) return rc;
         }
 
         if (lean_phase) {
@@ -1252,7 +1283,7 @@ extern "C" int hbmpc_nonrobust_recover_batch(hbmpc_ctx *ctx, size_t n, size_t de
         a.n_gate = T.n_chk;
         a.chk_map = T.chk_map;
         a.fail = (unsigned char *)aux;
-        if ((rc = launch_matvec(ctx, ln.stream, a, 0))) return rc;
+        if ((rc = launch_matvec(ctx, ln, a, 0))) return rc;
         }
         degree_status_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>((long long)Bc, (int)m, (uint4 *)vc.dev, (const unsigned char *)aux, (int *)vst.dev,
                                                                      secrets ? (uint4 *)vs.dev : nullptr);

@@ -44,6 +44,8 @@ struct MatvecArgs {
     const unsigned int *item_list;   // optional indirection: process items item_list[0 .. *item_count) instead of 0 .. B
     const unsigned int *item_count;
     const int *row_len;        // optional [R]: row r uses only its first row_len[r] columns (triangular matrices)
+    int M_ld;                  // leading dimension of M in elements (0: C) -- column blocks of a wider matrix
+    int col0;                  // first column of the block: column c reads input col_map[col0 + c] (or col0 + c)
 };
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
@@ -68,7 +70,10 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
     unsigned long long *sFlags = reinterpret_cast<unsigned long long *>(sFail + TBT * 32);  // [TBT*32][flag_words]
 
     // constant matrix slice -> shared memory (once per CTA; the CTA is persistent over batch tiles)
-    for (int i = tid; i < nrows * C * 2; i += blockDim.x) sM[i] = a.M[(size_t)r0 * C * 2 + i];
+    {
+        const int ld = a.M_ld ? a.M_ld : C;
+        for (int i = tid; i < nrows * C * 2; i += blockDim.x) sM[i] = a.M[((size_t)(r0 + i / (C * 2)) * ld) * 2 + i % (C * 2)];
+    }
 
     const long long TILE = TBT * 32;
     const long long NB = a.item_list ? (long long)*a.item_count : a.B;  // items to process
@@ -89,7 +94,7 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
             uint4 v = make_uint4(0, 0, 0, 0);
             if (b < NB) {
                 if (a.item_list) b = a.item_list[b];
-                int j = a.col_map ? a.col_map[c] : c;
+                int j = a.col_map ? a.col_map[a.col0 + c] : a.col0 + c;
                 v = ldg_stream(a.in + (b * a.in_sb + (long long)j * a.in_sc) * 2 + half);
             }
             sD[(((bl >> 5) * C + c) * 2 + half) * 32 + (bl & 31)] = v;
@@ -186,6 +191,38 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
                         }
                 }
             }
+        }
+    }
+}
+
+// Column-split fallback for matrices too wide for one shared-memory tile (C > ~200): the two column blocks are applied by
+// two plain launches into T1 / T2 [B][R]; this kernel adds them and applies the row semantics (check rows / outputs).
+__global__ void matvec_combine_kernel(const MatvecArgs a, const uint4 *T1, const uint4 *T2) {
+    const long long NB = a.item_list ? (long long)*a.item_count : a.B;
+    const long long total = NB * a.R;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long b = i / a.R;
+        const int r = (int)(i - b * a.R);
+        if (a.item_list) b = a.item_list[b];
+        uint32_t x[8], y[8], v[8];
+        load_fr(x, T1[(b * a.R + r) * 2], T1[(b * a.R + r) * 2 + 1]);
+        load_fr(y, T2[(b * a.R + r) * 2], T2[(b * a.R + r) * 2 + 1]);
+        fr_add(v, x, y);
+        if (r < a.n_chk) {
+            const int chk_j = a.chk_map[r];
+            uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (chk_j >= 0) {
+                const uint4 *p = a.in + (b * a.in_sb + (long long)chk_j * a.in_sc) * 2;
+                load_fr(w, ldg_stream(p), ldg_stream(p + 1));
+            }
+            if (!fr_eq(v, w)) {
+                if (r < a.n_gate && a.fail) a.fail[b] = 1;
+                if (a.flags && chk_j >= 0) atomicOr(&a.flags[b * a.flag_words + (chk_j >> 6)], 1ull << (chk_j & 63));
+            }
+        } else {
+            uint4 *o = a.out + (b * a.out_sb + (long long)(r - a.n_chk) * a.out_sr) * 2;
+            stg_stream(o, make_uint4(v[0], v[1], v[2], v[3]));
+            stg_stream(o + 1, make_uint4(v[4], v[5], v[6], v[7]));
         }
     }
 }
