@@ -635,7 +635,7 @@ def test_share_record_pack_unpack(ctx, orc):
     assert np.array_equal(vals, big) and np.array_equal(ids, np.arange(400000, dtype=np.uint64) // 100000) and (degs == 7).all()
 
 
-@pytest.mark.parametrize("n,t,d", [(1, 0, 0), (2, 0, 0), (2, 0, 1), (3, 0, 2), (4, 1, 1), (4, 1, 2), (5, 1, 3), (255, 84, 84)])
+@pytest.mark.parametrize("n,t,d", [(1, 0, 0), (2, 0, 0), (2, 0, 1), (3, 0, 2), (4, 1, 1), (4, 1, 2), (5, 1, 3), (255, 84, 84), (255, 84, 168), (200, 66, 132)])
 def test_tiny_and_maximal_party_counts(ctx, orc, n, t, d):
     B = 9
     coeffs, shares = _codewords(orc, n, d, B, 0x5EED4000 + n + d)
