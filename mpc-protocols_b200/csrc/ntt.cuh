@@ -57,6 +57,15 @@ __device__ __forceinline__ void ntt_butterfly(uint32_t (&u)[8], uint32_t (&v)[8]
     for (int i = 0; i < 8; ++i) { u[i] = s[i]; v[i] = d[i]; }
 }
 
+// 16-byte asynchronous global->shared copy (LDGSTS, L2 only): the next tile's inputs land in shared memory while the
+// current tile is being transformed
+__device__ __forceinline__ void cp_async16(uint4 *smem_dst, const uint4 *gmem_src) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // GG butterfly stages on the 2^GG register-resident elements x[e] that sit at positions base + e*h0
 template <int GG, int E, bool SKIP_ONE>
 __device__ __forceinline__ void ntt_stages(uint32_t (&x)[E][8], const uint4 *tw, int low, int h0, int tw_shift0) {
@@ -125,7 +134,8 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
     constexpr int PADN = N + N / 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4 *sTw = reinterpret_cast<uint4 *>(smem_raw);            // [N/2][2]
-    uint4 *sD = sTw + (N > 1 ? N : 2);                           // [IPC][2][PADN]
+    uint4 *sD = sTw + (N > 1 ? N : 2);                           // [IPC][2][PADN]   (NP > 1 only)
+    uint4 *sIn = sD + (NP > 1 ? (size_t)IPC * 2 * PADN : 0);     // [E][2][BLOCK] per-thread input staging (prefetch)
     for (int i = threadIdx.x; i < N; i += blockDim.x) sTw[i] = a.tw[i];  // N/2 entries * 2 halves
     __syncthreads();
 
@@ -136,24 +146,46 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
     uint32_t sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (MODE == 1) load_fr(sc, a.scale[0], a.scale[1]);
 
+    // Which record feeds each of this thread's E positions is the same for every tile: position pos holds the input with
+    // natural index k = bitrev(pos) (zero beyond `cols` / outside the examined id set).
+    int rec_of[E], k_of[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int pos = tid_i * E + e;
+        const int k = (int)(__brev((unsigned)pos) >> (32 - LOGN));
+        k_of[e] = k;
+        rec_of[e] = (k < a.cols) ? ((MODE != 0 && a.in_map) ? a.in_map[k] : k) : -1;
+    }
+    uint4 *myIn = sIn + threadIdx.x;
+    // `gate` carries a data dependence on the values just read from the staging slots, so the asynchronous copies that
+    // overwrite those slots cannot be issued before the reads have completed
+    const unsigned int never = (unsigned int)a.n + 0x7fff0000u;
+    auto prefetch = [&](long long t, unsigned int gate) {
+        const long long bb = t * IPC + item_l;
+        if (t < ntiles && bb < a.B && gate != never) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                if (rec_of[e] < 0) continue;
+                const uint4 *p = a.in + (bb * a.in_sb + (long long)rec_of[e] * a.in_sc) * 2;
+                cp_async16(myIn + (e * 2) * HB_NTT_BLOCK, p);
+                cp_async16(myIn + (e * 2 + 1) * HB_NTT_BLOCK, p + 1);
+            }
+        }
+        cp_async_commit();
+    };
+    prefetch(blockIdx.x, 0u);
+
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long b = tile * IPC + item_l;
         const bool active = b < a.B;
         uint32_t x[E][8];
-        // ---- pass 0: bit-reversed gather from global, stages with half = 1, 2, 4 (twiddles depend on e only)
+        // ---- pass 0: inputs from the prefetch staging (thread-private slots: no barrier), stages with half = 1, 2, 4
+        cp_async_wait_all();
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const int pos = tid_i * E + e;
-            const int k = (int)(__brev((unsigned)pos) >> (32 - LOGN));
-            if (active && k < a.cols) {
-                const int rec = (MODE != 0 && a.in_map) ? a.in_map[k] : k;
-                if (MODE == 2 && rec < 0) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) x[e][i] = 0;
-                    continue;
-                }
-                const uint4 *p = a.in + (b * a.in_sb + (long long)rec * a.in_sc) * 2;
-                load_fr(x[e], ldg_stream(p), ldg_stream(p + 1));
+            if (active && rec_of[e] >= 0) {
+                const int k = k_of[e];
+                load_fr(x[e], myIn[(e * 2) * HB_NTT_BLOCK], myIn[(e * 2 + 1) * HB_NTT_BLOCK]);
                 bad |= geq_mod(x[e]) ? 1u : 0u;
                 if (MODE == 2) {
                     uint32_t w[8], y[8];
@@ -167,6 +199,8 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
                 for (int i = 0; i < 8; ++i) x[e][i] = 0;
             }
         }
+        // the staged values are in registers (and were examined by geq_mod): the slots can take the next tile's inputs
+        prefetch(tile + gridDim.x, bad);
         ntt_stages<G, E, true>(x, sTw, 0, 1, LOGN - 1);
         if constexpr (NP == 1) {
 #pragma unroll
@@ -235,7 +269,7 @@ inline size_t ntt_smem_bytes() {
     constexpr int IPC = HB_NTT_BLOCK / TPI;
     constexpr int NP = (LOGN + G - 1) / G;
     size_t tw = (size_t)(N > 1 ? N : 2) * 16;
-    return tw + (NP > 1 ? (size_t)IPC * 2 * (N + N / 8) * 16 : 0) + 16;
+    return tw + (NP > 1 ? (size_t)IPC * 2 * (N + N / 8) * 16 : 0) + (size_t)(1 << G) * 2 * HB_NTT_BLOCK * 16 + 16;
 }
 template <int LOGN>
 inline int ntt_items_per_cta() {
