@@ -29,3 +29,25 @@ def test_reference_unit_tests_through_cpp_mirror(tmp_path):
     res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "all reference-shaped tests passed" in res.stdout
+
+
+def _compile_c(tmp_path):
+    exe = tmp_path / "secret_share_b200"
+    lib_dir = os.path.join(ROOT, "mpc-protocols_b200")
+    cmd = ["gcc", "-std=c99", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "host", "secret_share_b200.c"),
+           "-L", lib_dir, "-lhbmpc_b200", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def test_c99_consumer_compiles_and_links(tmp_path):
+    _compile_c(tmp_path)
+
+
+@pytest.mark.gpu
+def test_reference_c_abi_test_restated(tmp_path):
+    """mpc/src/ffi/tests/secret_share.c restated in C99 against the batch C ABI."""
+    exe = _compile_c(tmp_path)
+    res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "all C-ABI round trips passed" in res.stdout
