@@ -18,9 +18,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a)")
 
 
+def _ensure_built():
+    """Build the C-ABI library in-tree when it is missing or stale (nvcc cross-compiles without a GPU)."""
+    builder = importlib.import_module("mpc-protocols_b200.build")
+    if builder.needs_build():
+        builder.build()
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    _ensure_built()
+
+
 @pytest.fixture(scope="session")
 def hb():
     """The product package (directory name has a hyphen, so it is imported by string)."""
+    _ensure_built()
     return importlib.import_module("mpc-protocols_b200")
 
 
