@@ -489,7 +489,7 @@ static int run_batched(hbmpc_ctx *ctx, size_t B, bool any_host, size_t max_item_
 static int launch_matvec(hbmpc_ctx *ctx, Lane &ln, MatvecArgs a, int flag_words) {
     cudaStream_t st = ln.stream;
     if (a.B == 0) return 0;
-    MatvecPlan p = matvec_plan(a.R, a.C, flag_words, ctx->matvec_regs > 0 ? ctx->matvec_regs : 112);
+    MatvecPlan p = matvec_plan(a.R, a.C, flag_words, ctx->matvec_regs > 0 ? ctx->matvec_regs : 112, a.B, ctx->num_sms);
     if (p.tbt == 0) {
         // too wide for one shared-memory tile: two column blocks into temporaries, then add + row semantics
         if (a.C < 2 || a.row_len) {
@@ -999,10 +999,10 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         unsigned int *list1 = (unsigned int *)(fail1 + fail_bytes);
         unsigned int *count1 = list1 + Bc;
         CK(cudaMemsetAsync(aux, 0, 2 * (fail_bytes + Bc * 4 + 16), ln.stream));  // fail bytes, lists and counters of both levels
-        CK(cudaMemsetAsync(vp.dev, 0, Bc * 4, ln.stream));
         if (want_flags) CK(cudaMemsetAsync(vf.dev, 0, Bc * fw * 8, ln.stream));
 
         const bool fastN = T.fast_logn > 0 && !lean_phase;
+        if (!(fastN || T.er_logn > 0)) CK(cudaMemsetAsync(vp.dev, 0, Bc * 4, ln.stream));  // the NTT checks write path = 0 themselves
         if (fastN) {
             // optimistic-optimistic: all n = N shares on one degree-d polynomial <=> the top N-m coefficients of the inverse
             // NTT vanish; then the lowest d+t+1 agree as well (path 0, no flags).  Items that fail go to the dense check.
@@ -1021,6 +1021,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             na.m = (int)m;
             na.mout = T.mout;
             na.fail = fail1;
+            na.path = (int *)vp.dev;
             if ((rc = launch_ntt<1>(ctx, ln.stream, T.fast_logn, na))) return rc;
             compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail1, (long long)Bc, list1, count1);
             ctx->launches++;
@@ -1046,6 +1047,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             na.m = T.er_zero_from;
             na.mout = T.mout;
             na.fail = fail;
+            na.path = (int *)vp.dev;
             if ((rc = launch_ntt<2>(ctx, ln.stream, T.er_logn, na))) return rc;
             MatvecArgs tr{};
             tr.M = T.er_tri;
@@ -1079,10 +1081,14 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         a.flags = want_flags ? (unsigned long long *)vf.dev : nullptr;
         if (!erasure && (rc = launch_matvec(ctx, ln, a, fw))) return rc;
 
-        compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail, (long long)Bc, list, count);
-        ctx->launches++;
-        CK(cudaGetLastError());
-        if (erasure && !lean_phase) {
+        // session-sized batches: no compaction pass -- the decoder's threads look at fail[] themselves and compute Lc*y
+        const bool scan = Bc <= 65536 && !lean_phase;
+        if (!scan) {
+            compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail, (long long)Bc, list, count);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+        if (erasure && !lean_phase && !scan) {
             // the robust decoder corrects Lc*y[lowest d+1] by linearity: provide it for the failing items
             MatvecArgs lc{};
             lc.M = T.Lc;
@@ -1110,6 +1116,8 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         r.B = (long long)Bc;
         r.list = list;
         r.count = count;
+        r.fail_scan = scan ? fail : nullptr;
+        r.need_lc = (scan && erasure) ? 1 : 0;
         r.S = (int)S; r.m = (int)m; r.t = (int)t; r.needed = (int)needed; r.rmax = T.rmax; r.fast = T.fast;
         r.att_P = T.att_P; r.att_nsyn = T.att_nsyn; r.att_maxL = T.att_maxL; r.att_uoff = T.att_uoff;
         r.u2 = T.u2; r.sid = T.sid; r.tw = T.tw; r.itw = T.ritw; r.uinv = T.uinv;

@@ -243,7 +243,7 @@ inline size_t matvec_smem_bytes(int rows, int C, int tbt, int flag_words) {
 
 // Pick the shape with the most resident warps per SM (register file allows ~24 warps at <=84 regs) and the
 // best work balance (items per warp integral), keeping all of M resident when it fits in 227 KB.
-inline MatvecPlan matvec_plan(int R, int C, int flag_words, int regs_per_thread) {
+inline MatvecPlan matvec_plan(int R, int C, int flag_words, int regs_per_thread, long long B = -1, int num_sms = 148) {
     const size_t SMEM_CTA = 227 * 1024, SMEM_SM = 228 * 1024;
     MatvecPlan best{};
     double best_score = -1.0;
@@ -253,6 +253,8 @@ inline MatvecPlan matvec_plan(int R, int C, int flag_words, int regs_per_thread)
         if ((rps * (slices - 1)) >= R && slices > 1) continue;  // empty last slice
         bool any = false;
         for (int tbt : {4, 2, 1}) {
+            // session-sized batches: prefer tiles small enough to give every SM one (latency, not throughput, matters there)
+            if (B > 0 && tbt > 1 && (B + tbt * 32 - 1) / (tbt * 32) < num_sms) continue;
             for (int warps : {16, 8, 4}) {
                 size_t smem = matvec_smem_bytes(rps, C, tbt, flag_words);
                 if (smem > SMEM_CTA) continue;

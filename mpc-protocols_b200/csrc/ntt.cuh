@@ -36,6 +36,7 @@ struct NttArgs {
     // multiplied by wt[k] = Zc(w^k) (Zc = product over the ids outside the examined set; Montgomery form) while it is
     // loaded, ids outside the examined set contribute zero (in_map[k] < 0); outputs are left unscaled.
     const uint4 *wt;       // [N][2]
+    int *path;             // MODE 1/2: path[b] = 0 is written here (the decoder overwrites it for items that fail)
 };
 
 // SKIP_ONE: test for the trivial twiddle (only where the index is warp-uniform -- pass 0 -- so the test folds away or
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
                 for (int i = 0; i < 8; ++i) x[e][i] = 0;
             }
         }
+        if (MODE != 0 && a.path && active && tid_i == 0) a.path[b] = 0;
         // the staged values are in registers (and were examined by geq_mod): the slots can take the next tile's inputs
         prefetch(tile + gridDim.x, bad);
         ntt_stages<G, E, true>(x, sTw, 0, 1, LOGN - 1);

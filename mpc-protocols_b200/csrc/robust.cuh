@@ -46,6 +46,8 @@ struct RobustArgs {
     long long in_sb, in_sc, B;
     const unsigned int *list;   // items that failed the optimistic check
     const unsigned int *count;
+    const unsigned char *fail_scan;  // non-null: no list -- every thread scans fail_scan[b] of its own items (small batches)
+    int need_lc;                // the optimistic stage did not leave Lc*y[lowest m] in `coeffs`: compute it here
     int S, m, t, needed, rmax;  // m = d+1, needed = d+t+1, rmax = min(t, S-needed)
     int fast;                   // attempt 0 (all S shares) is enabled
     const int *att_P;           // [1 + rmax] prefix size per attempt (index 0 = fast path)
@@ -430,7 +432,7 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
 #define HB_ROBUST_MINB 8
 #endif
 __global__ void __launch_bounds__(128, HB_ROBUST_MINB) robust_kernel(const RobustArgs a) {
-    const unsigned int cnt = *a.count;
+    const size_t cnt = a.fail_scan ? (size_t)a.B : (size_t)*a.count;
     const size_t T = (size_t)gridDim.x * blockDim.x;
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int nsyn_max = 0;
@@ -440,7 +442,8 @@ __global__ void __launch_bounds__(128, HB_ROBUST_MINB) robust_kernel(const Robus
     int rootpos[HB_ROBUST_MAXT];
 
     for (size_t idx = g; idx < cnt; idx += T) {
-        const long long b = a.list[idx];
+        if (a.fail_scan && !a.fail_scan[idx]) continue;
+        const long long b = a.fail_scan ? (long long)idx : (long long)a.list[idx];
         int L = -1, path = -8, used_att = -1;
         if (a.fast) {
             L = rs_attempt(a, 0, b, ws, lay, rootpos);
@@ -469,8 +472,23 @@ __global__ void __launch_bounds__(128, HB_ROBUST_MINB) robust_kernel(const Robus
             *(volatile unsigned int *)a.fail_any = 1u;
             continue;
         }
-        // corrected coefficients by linearity
+        // corrected coefficients by linearity (Lc*y first when the optimistic stage did not provide it)
         for (int k = 0; k < a.mout; ++k) {
+            if (a.need_lc) {
+                acc_t A0;
+                acc_zero(A0);
+                const uint4 *yb = a.in + b * a.in_sb * 2;
+                for (int i = 0; i < a.m; ++i) {
+                    uint32_t y[8], lc[8];
+                    ldg_fr(y, yb + (long long)a.order[i] * a.in_sc * 2);
+                    ldg_fr(lc, a.Lc + ((size_t)k * a.m + i) * 2);
+                    acc_mac(A0, y, lc);
+                }
+                uint32_t c0[8];
+                acc_reduce(A0, c0);
+                co[k * 2] = make_uint4(c0[0], c0[1], c0[2], c0[3]);
+                co[k * 2 + 1] = make_uint4(c0[4], c0[5], c0[6], c0[7]);
+            }
             acc_t A;
             acc_zero(A);
             bool any = false;
