@@ -649,3 +649,28 @@ def test_tiny_and_maximal_party_counts(ctx, orc, n, t, d):
     assert np.array_equal(want["coeffs"], coeffs)
     co, sec, st = ctx.nonrobust_recover_batch(ids, shares, n, d)
     assert np.array_equal(co, coeffs) and np.array_equal(sec, coeffs[:, 0])
+
+
+def test_gpu_against_independent_python_model(ctx, hb):
+    """The CUDA path against the second, independent restatement (oracle/pymodel.py, plain Python big ints) -- not via the C oracle."""
+    from oracle import pymodel as pm
+
+    rng = pm.SplitMix64(0xA11CE)
+    for n, t, d, errs in [(7, 2, 2, [3]), (10, 3, 3, [0, 9]), (10, 3, 6, []), (13, 4, 4, [1, 2, 3, 12]), (16, 5, 5, [15])]:
+        coeffs = [rng.fr() for _ in range(d + 1)]
+        shares = pm.compute_shares(coeffs, n, d)
+        got = hb.from_limbs(ctx.compute_shares_batch(hb.to_limbs([coeffs]), n))[0]
+        assert got == shares
+        vals = list(shares)
+        for e in errs:
+            vals[e] = (vals[e] + 12345) % pm.R_MOD
+        ids = list(range(n))
+        ref = pm.robust_recover_secret([(i, v, d) for i, v in zip(ids, vals)], n, t)
+        rc, co, sec, path, flags = ctx.robust_interpolate_batch(ids, hb.to_limbs([vals]), n, d, t, want_flags=True)
+        assert rc == 0 and path[0] == ref["path"] and hb.from_limbs(sec)[0] == ref["secret"]
+        assert hb.from_limbs(co)[0][: len(ref["coeffs"])] == ref["coeffs"]
+        assert [(int(flags[0, i >> 6]) >> (i & 63)) & 1 for i in range(n)] == [int(f) for f in ref["flags"]]
+        out = pm.batch_recover_secret([(i, [v]) for i, v in zip(ids, vals)], n, d, t)
+        rc, co2, path2, _ = ctx.batch_recover(ids, hb.to_limbs([[v] for v in vals]), n, d, t)
+        want = out[0]["coeffs"] + [0] * (d + 1 - len(out[0]["coeffs"]))
+        assert rc == 0 and path2[0] == out[0]["path"] and hb.from_limbs(co2)[0] == want
