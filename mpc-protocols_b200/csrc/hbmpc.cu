@@ -198,6 +198,9 @@ struct hbmpc_ctx {
     int num_sms = 148;
     int matvec_regs = 0;
     int ntt_ctas[3][9] = {};                        // resident CTAs per SM of ntt_kernel<LOGN, MODE>
+    size_t scan_max = 65536;                        // HBMPC_SCAN_MAX: batches up to this size skip the compaction pass
+    bool no_speculation = false;                    // HBMPC_NO_SPECULATION=1: never try the persistent-attacker shortcut
+    unsigned int *h_spec = nullptr;                 // pinned: failing-item count + per-sender error histogram of the scout pass
     bool no_fastpath = false;                       // HBMPC_NO_FASTPATH=1: K3 never takes the all-shares-present inverse-NTT path
     bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
     size_t chunk_bytes = 16u << 20;                 // HBMPC_CHUNK_MB: target bytes per pipelined host copy
@@ -291,6 +294,10 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
         ctx->force_dense = fd && fd[0] == '1';
         const char *nf = getenv("HBMPC_NO_FASTPATH");
         ctx->no_fastpath = nf && nf[0] == '1';
+        const char *sx = getenv("HBMPC_SCAN_MAX");
+        if (sx) ctx->scan_max = (size_t)atoll(sx);
+        const char *ns = getenv("HBMPC_NO_SPECULATION");
+        ctx->no_speculation = ns && ns[0] == '1';
         const char *cm = getenv("HBMPC_CHUNK_MB");
         if (cm && atoi(cm) > 0) ctx->chunk_bytes = (size_t)atoi(cm) << 20;
     }
@@ -298,7 +305,8 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
     for (int i = 0; i < NLANES && ok; ++i) ok = cudaStreamCreateWithFlags(&ctx->lanes[i].stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaHostAlloc((void **)&ctx->h_status, 16, cudaHostAllocMapped) == cudaSuccess &&
          cudaHostGetDevicePointer((void **)&ctx->d_status, ctx->h_status, 0) == cudaSuccess &&
-         cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming) == cudaSuccess;
+         cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming) == cudaSuccess &&
+         cudaMallocHost((void **)&ctx->h_spec, 320 * sizeof(unsigned int)) == cudaSuccess;
     if (ok) {
         memset(ctx->h_status, 0, 16);
         cudaFuncAttributes fa;
@@ -321,24 +329,35 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
     return HBMPC_SUCCESS;
 }
 
+static void note_destroy_error(const char *what) {
+    cudaError_t e = cudaGetLastError();  // also clears it: a failure here must not surface in another context's next call
+    if (e != cudaSuccess && getenv("HBMPC_DEBUG")) fprintf(stderr, "hbmpc_ctx_destroy: %s: %s\n", what, cudaGetErrorString(e));
+}
+
 extern "C" void hbmpc_ctx_destroy(hbmpc_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (auto &ln : ctx->lanes)
         if (ln.stream) cudaStreamSynchronize(ln.stream);
+    note_destroy_error("sync");
     for (void *p : ctx->owned) cudaFree(p);
+    note_destroy_error("owned");
     for (auto &e : ctx->recover)
         for (void *q : e.second.allocs) cudaFree(q);
+    note_destroy_error("recover tables");
     for (auto &ln : ctx->lanes)
         for (auto &b : ln.scratch)
             if (b.p) cudaFree(b.p);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->maps.p) cudaFree(ctx->maps.p);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+    if (ctx->h_spec) cudaFreeHost(ctx->h_spec);
+    note_destroy_error("host buffers");
     if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
     delete ctx->nonrobust;
     for (int i = 0; i < NLANES; ++i)
         if (ctx->lanes[i].stream && (i > 0 || ctx->own_stream)) cudaStreamDestroy(ctx->lanes[i].stream);
+    note_destroy_error("streams");
     delete ctx;
 }
 
@@ -1082,7 +1101,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         if (!erasure && (rc = launch_matvec(ctx, ln, a, fw))) return rc;
 
         // session-sized batches: no compaction pass -- the decoder's threads look at fail[] themselves and compute Lc*y
-        const bool scan = Bc <= 65536 && !lean_phase;
+        const bool scan = Bc <= ctx->scan_max && !lean_phase;
         if (!scan) {
             compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail, (long long)Bc, list, count);
             ctx->launches++;
@@ -1135,9 +1154,122 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         if ((rc = scratch_get(ctx, ln, 6, (size_t)blocks * threads * lay.total * 32 + 64, &ws))) return rc;
         r.ws = (uint4 *)ws;
         r.ws_elems = lay.total;
-        robust_kernel<<<(unsigned)blocks, threads, 0, ln.stream>>>(r);
-        ctx->launches++;
-        CK(cudaGetLastError());
+        auto launch_robust = [&](const RobustArgs &ra) -> int {
+            robust_kernel<<<(unsigned)blocks, threads, 0, ln.stream>>>(ra);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            return 0;
+        };
+        // Persistent-attacker shortcut (synchronous calls with many failing items): decode a few scouts, and if the same
+        // <= t senders are wrong in most of them, interpolate every other failing item from senders believed honest and
+        // verify against ALL supplied shares with one dense launch; whatever is not explained by <= t errors goes to the
+        // full decoder.  Results are identical to decoding everything (see robust.cuh: spec_finalize_kernel).
+        const unsigned int SCOUTS = 64, SPEC_MIN = 1024;
+        bool done = false;
+        if (!scan && !ctx->async && !ctx->no_speculation && T.rmax >= 1) {
+            CK(cudaMemcpyAsync(ctx->h_spec, count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
+            CK(cudaStreamSynchronize(ln.stream));
+            const unsigned int cnt = ctx->h_spec[0];
+            if (cnt >= SPEC_MIN) {
+                // ---- scouts
+                void *histbuf = nullptr;
+                if ((rc = scratch_get(ctx, ln, 9, 4096, &histbuf))) return rc;
+                unsigned int *hist = (unsigned int *)histbuf;
+                CK(cudaMemsetAsync(hist, 0, S * sizeof(unsigned int), ln.stream));
+                RobustArgs rs = r;
+                rs.list_first = 0;
+                rs.list_max = SCOUTS;
+                rs.hist = hist;
+                rs.clear_fail = fail;
+                rs.need_lc = erasure ? 1 : 0;
+                if ((rc = launch_robust(rs))) return rc;
+                CK(cudaMemcpyAsync(ctx->h_spec + 8, hist, S * sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
+                CK(cudaStreamSynchronize(ln.stream));
+                std::vector<char> suspect(S, 0);
+                size_t nsus = 0;
+                for (size_t j = 0; j < S; ++j)
+                    if (ctx->h_spec[8 + j] >= SCOUTS / 2) { suspect[j] = 1; ++nsus; }
+                if (nsus >= 1 && nsus <= t && S - nsus >= m) {
+                    // ---- tables for "interpolate from the lowest m unsuspected ids, compare with every other supplied share"
+                    std::vector<HFr> dom = domain_elements(n, n);
+                    std::vector<int> I, O, pos_of(S);
+                    for (size_t i = 0; i < S; ++i) {
+                        pos_of[order[i]] = (int)i;
+                        if (!suspect[order[i]] && I.size() < m) I.push_back(order[i]);
+                        else O.push_back(order[i]);
+                    }
+                    std::vector<HFr> xi(m), xo(O.size());
+                    for (size_t i = 0; i < m; ++i) xi[i] = dom[ids[I[i]]];
+                    for (size_t i = 0; i < O.size(); ++i) xo[i] = dom[ids[O[i]]];
+                    Lagrange Ls = lagrange_basis(xi);
+                    std::vector<HFr> Ms = lagrange_eval_rows(xi, Ls, xo);
+                    Ms.insert(Ms.end(), Ls.Lc.begin(), Ls.Lc.begin() + (size_t)T.mout * m);
+                    std::vector<uint32_t> mw;
+                    to_u32(Ms, mw);
+                    std::vector<int> maps(I);
+                    maps.insert(maps.end(), O.begin(), O.end());
+                    maps.insert(maps.end(), pos_of.begin(), pos_of.end());
+                    const int fws = (int)((S + 63) / 64);
+                    const size_t off_maps = ((mw.size() * 4 + 255) / 256) * 256, off_sf = off_maps + ((maps.size() * 4 + 255) / 256) * 256;
+                    void *sp = nullptr;
+                    if ((rc = scratch_get(ctx, ln, 9, off_sf + Bc * (size_t)fws * 8 + 4096, &sp))) return rc;
+                    CK(cudaMemcpyAsync(sp, mw.data(), mw.size() * 4, cudaMemcpyHostToDevice, ln.stream));
+                    CK(cudaMemcpyAsync((char *)sp + off_maps, maps.data(), maps.size() * 4, cudaMemcpyHostToDevice, ln.stream));
+                    unsigned long long *sflags = (unsigned long long *)((char *)sp + off_sf);
+                    CK(cudaMemsetAsync(sflags, 0, Bc * (size_t)fws * 8, ln.stream));
+                    ctx->h_spec[1] = cnt - SCOUTS;
+                    CK(cudaMemcpyAsync(count1, ctx->h_spec + 1, sizeof(unsigned int), cudaMemcpyHostToDevice, ln.stream));
+                    const int *dmaps = (const int *)((char *)sp + off_maps);
+                    MatvecArgs sm{};
+                    sm.M = (const uint4 *)sp;
+                    sm.in = (const uint4 *)vi.dev;
+                    sm.out = (uint4 *)vc.dev;
+                    sm.R = (int)(O.size() + T.mout);
+                    sm.C = (int)m;
+                    sm.B = (long long)Bc;
+                    sm.in_sb = vi.sb; sm.in_sc = vi.sj;
+                    sm.in_chunk_major = sender_major ? 0 : 1;
+                    sm.out_sb = T.mout; sm.out_sr = 1;
+                    sm.col_map = dmaps;
+                    sm.n_chk = (int)O.size();
+                    sm.n_gate = 0;
+                    sm.chk_map = dmaps + m;
+                    sm.flags = sflags;
+                    sm.item_list = list + SCOUTS;
+                    sm.item_count = count1;
+                    if ((rc = launch_matvec(ctx, ln, sm, fws))) return rc;
+                    SpecArgs sa{};
+                    sa.list = list; sa.first = SCOUTS; sa.count = cnt;
+                    sa.sflags = sflags;
+                    sa.flags = a.flags;
+                    sa.flag_words = fws;
+                    sa.pos_of = dmaps + S;
+                    sa.S = (int)S; sa.t = (int)t; sa.needed = (int)needed; sa.rmax = T.rmax;
+                    sa.path = (int *)vp.dev;
+                    sa.fail = fail;
+                    sa.fail_any = ctx->d_status + 2;
+                    sa.coeffs = (uint4 *)vc.dev;
+                    sa.mout = T.mout;
+                    spec_finalize_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(sa);
+                    ctx->launches++;
+                    CK(cudaGetLastError());
+                    // ---- what speculation could not explain: full decoder (the scouts are already done)
+                    CK(cudaMemsetAsync(count, 0, sizeof(unsigned int), ln.stream));
+                    compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail, (long long)Bc, list, count);
+                    ctx->launches++;
+                    CK(cudaGetLastError());
+                    RobustArgs rr = r;
+                    rr.need_lc = 1;  // the speculative launch overwrote coeffs
+                    if ((rc = launch_robust(rr))) return rc;
+                } else {
+                    RobustArgs rr = r;
+                    rr.list_first = SCOUTS;
+                    if ((rc = launch_robust(rr))) return rc;
+                }
+                done = true;
+            }
+        }
+        if (!done && (rc = launch_robust(r))) return rc;
 
         if (want_secrets) {
             gather_first_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>((long long)Bc, (long long)m, (const uint4 *)vc.dev, (uint4 *)vs.dev);

@@ -48,6 +48,10 @@ struct RobustArgs {
     const unsigned int *count;
     const unsigned char *fail_scan;  // non-null: no list -- every thread scans fail_scan[b] of its own items (small batches)
     int need_lc;                // the optimistic stage did not leave Lc*y[lowest m] in `coeffs`: compute it here
+    unsigned int *hist;         // optional [S]: hist[arrival j] += 1 for every error found at sender j (scout pass)
+    unsigned int list_first;    // list mode: process list[list_first .. min(count, list_first + list_max))
+    unsigned int list_max;      // 0: no limit
+    unsigned char *clear_fail;  // optional: fail flag of every processed item is cleared (scout pass before a re-compaction)
     int S, m, t, needed, rmax;  // m = d+1, needed = d+t+1, rmax = min(t, S-needed)
     int fast;                   // attempt 0 (all S shares) is enabled
     const int *att_P;           // [1 + rmax] prefix size per attempt (index 0 = fast path)
@@ -432,7 +436,8 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
 #define HB_ROBUST_MINB 8
 #endif
 __global__ void __launch_bounds__(128, HB_ROBUST_MINB) robust_kernel(const RobustArgs a) {
-    const size_t cnt = a.fail_scan ? (size_t)a.B : (size_t)*a.count;
+    size_t cnt = a.fail_scan ? (size_t)a.B : (size_t)*a.count;
+    if (!a.fail_scan && a.list_max && cnt > (size_t)a.list_first + a.list_max) cnt = (size_t)a.list_first + a.list_max;
     const size_t T = (size_t)gridDim.x * blockDim.x;
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int nsyn_max = 0;
@@ -441,7 +446,7 @@ __global__ void __launch_bounds__(128, HB_ROBUST_MINB) robust_kernel(const Robus
     FrWs ws{a.ws + g * 2, T};
     int rootpos[HB_ROBUST_MAXT];
 
-    for (size_t idx = g; idx < cnt; idx += T) {
+    for (size_t idx = g + (a.fail_scan ? 0 : a.list_first); idx < cnt; idx += T) {
         if (a.fail_scan && !a.fail_scan[idx]) continue;
         const long long b = a.fail_scan ? (long long)idx : (long long)a.list[idx];
         int L = -1, path = -8, used_att = -1;
@@ -469,6 +474,7 @@ __global__ void __launch_bounds__(128, HB_ROBUST_MINB) robust_kernel(const Robus
             for (int k = 0; k < a.mout; ++k) { co[k * 2] = make_uint4(0, 0, 0, 0); co[k * 2 + 1] = make_uint4(0, 0, 0, 0); }
             if (fl) for (int w = 0; w < a.flag_words; ++w) fl[w] = 0ull;
             a.path[b] = -8;
+            if (a.clear_fail) a.clear_fail[b] = 0;
             *(volatile unsigned int *)a.fail_any = 1u;
             continue;
         }
@@ -534,7 +540,57 @@ __global__ void __launch_bounds__(128, HB_ROBUST_MINB) robust_kernel(const Robus
                 if (!fr_eq(fv, y)) fl[j >> 6] |= 1ull << (j & 63);
             }
         }
+        if (a.hist)
+            for (int q = 0; q < L; ++q) atomicAdd(&a.hist[a.order[rootpos[q]]], 1u);
+        if (a.clear_fail) a.clear_fail[b] = 0;
         a.path[b] = path;
+    }
+}
+
+// Speculative decode for persistent attackers (the same <= t senders wrong in every chunk).  The dense kernel has
+// interpolated P from d+1 senders believed honest and set flag bit j for every other supplied sender whose share disagrees
+// with P.  If at most t shares disagree, P is the polynomial the reference decodes (it is the only one within distance t of
+// the prefixes it examines) and its round is the first r whose prefix holds at most r of the mismatches -- the same rule as
+// the decoder's fast path.  Otherwise the item stays in the failing set for the full decoder.
+struct SpecArgs {
+    const unsigned int *list;      // failing items
+    unsigned int first, count;     // process list[first .. count)
+    const unsigned long long *sflags;  // [B][flag_words] mismatch bits in arrival order (scratch)
+    unsigned long long *flags;     // user flags (may be nullptr)
+    int flag_words;
+    const int *pos_of;             // [S] sorted position of arrival index j
+    int S, t, needed, rmax;
+    int *path;
+    unsigned char *fail;           // cleared for accepted items
+    unsigned int *fail_any;
+    uint4 *coeffs;
+    int mout;
+};
+__global__ void spec_finalize_kernel(const SpecArgs a) {
+    for (unsigned int idx = a.first + blockIdx.x * blockDim.x + threadIdx.x; idx < a.count; idx += gridDim.x * blockDim.x) {
+        const long long b = a.list[idx];
+        const unsigned long long *sf = a.sflags + b * a.flag_words;
+        int e = 0;
+        for (int w = 0; w < a.flag_words; ++w) e += __popcll(sf[w]);
+        if (e > a.t) continue;  // not explained by <= t errors: left to the full decoder (fail[b] stays set)
+        // prefix counts: cnt[p] = number of mismatches at sorted positions < p, evaluated lazily for p = needed + r
+        int path = -8;
+        for (int r = 1; r <= a.rmax; ++r) {
+            const int P = a.needed + r;
+            int c = 0;
+            for (int j = 0; j < a.S; ++j)
+                if (((sf[j >> 6] >> (j & 63)) & 1ull) && a.pos_of[j] < P) ++c;
+            if (c <= r) { path = r; break; }
+        }
+        a.fail[b] = 0;
+        a.path[b] = path;
+        if (path < 0) {  // the reference's OEC loop runs out of rounds: DecodingError
+            uint4 *co = a.coeffs + b * a.mout * 2;
+            for (int k = 0; k < 2 * a.mout; ++k) co[k] = make_uint4(0, 0, 0, 0);
+            *(volatile unsigned int *)a.fail_any = 1u;
+        }
+        if (a.flags)
+            for (int w = 0; w < a.flag_words; ++w) a.flags[b * a.flag_words + w] = path < 0 ? 0ull : sf[w];
     }
 }
 

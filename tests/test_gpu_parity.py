@@ -674,3 +674,58 @@ def test_gpu_against_independent_python_model(ctx, hb):
         rc, co2, path2, _ = ctx.batch_recover(ids, hb.to_limbs([[v] for v in vals]), n, d, t)
         want = out[0]["coeffs"] + [0] * (d + 1 - len(out[0]["coeffs"]))
         assert rc == 0 and path2[0] == out[0]["path"] and hb.from_limbs(co2)[0] == want
+
+
+@pytest.mark.parametrize("n,t,S", [(16, 5, 16), (16, 5, 14), (13, 4, 13), (64, 21, 64), (64, 21, 60)])
+def test_persistent_attacker_speculation_is_exact(hb, orc, monkeypatch, n, t, S):
+    """Many failing chunks with the same corrupted senders trigger the speculative path (scouts -> suspected senders ->
+    interpolate from the others -> verify against all supplied shares).  Mixed in: chunks whose errors sit elsewhere
+    (speculation must hand them to the full decoder), clean chunks, chunks where a suspected sender happens to be right,
+    and chunks with more than t errors.  Everything must equal the oracle and the run with speculation switched off."""
+    d = t
+    B = 3000 if n <= 16 else 1500
+    rng = np.random.default_rng(n * 7 + S)
+    coeffs, shares = _codewords(orc, n, d, B, 0x5EED6000 + n + S)
+    ids = np.sort(rng.permutation(n)[:S])
+    arrival = rng.permutation(S)
+    words = shares[:, ids[arrival]].copy()                       # [B][S] in arrival order
+    x = S - (d + t + 1)                                          # extra shares: OEC can absorb at most min(t, x) errors
+    nbad = max(1, min(t, x))
+    bad_senders = rng.permutation(S)[:nbad]
+    for b in range(B):
+        kind = b % 10
+        if kind == 0:
+            continue                                             # clean chunk
+        if kind == 1:                                            # errors somewhere else
+            for p in rng.choice(S, size=int(rng.integers(1, nbad + 1)), replace=False):
+                words[b, p, 0] ^= np.uint64(rng.integers(1, 1 << 30))
+        elif kind == 2 and nbad > 1:                             # one suspected sender happens to be right
+            for p in bad_senders[1:]:
+                words[b, p, 0] ^= np.uint64(rng.integers(1, 1 << 30))
+        elif kind == 3:                                          # more than the decodable number of errors
+            for p in rng.choice(S, size=min(S, t + 1), replace=False):
+                words[b, p, 0] ^= np.uint64(rng.integers(1, 1 << 30))
+        else:                                                    # the persistent attackers
+            for p in bad_senders:
+                words[b, p, 0] ^= np.uint64(rng.integers(1, 1 << 30))
+    evals = np.ascontiguousarray(words.transpose(1, 0, 2))
+    want = orc.batch_recover_secret(ids[arrival], evals, n, d, t, threads=orc.max_threads())
+    monkeypatch.setenv("HBMPC_SCAN_MAX", "0")          # list mode also for this test-sized batch, so the shortcut can trigger
+    c = hb.Context(0)
+    monkeypatch.setenv("HBMPC_NO_SPECULATION", "1")
+    c_off = hb.Context(0)
+    try:
+        launches = []
+        for cc in (c, c_off):
+            l0 = cc.launch_count
+            for fl in (True, False):
+                got = cc.batch_recover(ids[arrival], evals, n, d, t, want_flags=fl)
+                _compare_recover(got, want, B)
+            rc, co, sec, path, flags = cc.robust_interpolate_batch(ids[arrival], words, n, d, t, want_flags=True)
+            assert rc == want["rc"] and np.array_equal(path, want["path"]) and np.array_equal(co, want["coeffs"])
+            assert np.array_equal(flags, want["flags"][:, : flags.shape[1]])
+            launches.append(cc.launch_count - l0)
+        assert launches[0] > launches[1], "the speculative path did not run"
+    finally:
+        c.close()
+        c_off.close()

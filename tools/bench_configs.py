@@ -65,9 +65,12 @@ def main():
         bad_senders = torch.randperm(n, device=dev)[:t]
         ev[bad_senders, :, 0] ^= 0x77
         rec = torch.empty((B, d + 1, 4), dtype=torch.int64, device=dev); path = torch.empty((B,), dtype=torch.int32, device=dev)
-        ms = timed(lambda: ctx.batch_recover(np.arange(n), ev, n, d, t, out=(rec, path, None)), reps=2)
+        ms_async = timed(lambda: ctx.batch_recover(np.arange(n), ev, n, d, t, out=(rec, path, None)), reps=2)
         rc = ctx.synchronize()
-        out["c3_under_attack_n64_t21"] = {"B": B, "corrupted_senders": t, "ms": ms, "chunks_per_s": B / (ms * 1e-3), "rc": rc,
+        ctx.set_async(False)   # synchronous calls may use the persistent-attacker shortcut (needs a host decision mid-call)
+        ms = timed(lambda: ctx.batch_recover(np.arange(n), ev, n, d, t, out=(rec, path, None)), reps=2)
+        ctx.set_async(True)
+        out["c3_under_attack_n64_t21"] = {"B": B, "corrupted_senders": t, "ms": ms, "chunks_per_s": B / (ms * 1e-3), "ms_async_full_decoder": ms_async, "chunks_per_s_full_decoder": B / (ms_async * 1e-3), "rc": rc,
                                           "all_recovered": bool(torch.equal(rec, coeffs)), "max_path": int(path.max())}
     if "lat" in which:   # per-call latency at session-sized batches (device pointers, synchronous mode, wall clock)
         import time
