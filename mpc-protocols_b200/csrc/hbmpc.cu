@@ -164,7 +164,7 @@ struct DevBuf {
 // are all device pointers; lanes 1..3 pipeline calls with host buffers chunk by chunk (H2D | kernels | D2H overlap).
 struct Lane {
     cudaStream_t stream = nullptr;
-    DevBuf scratch[10];
+    DevBuf scratch[12];
 };
 static const int NLANES = 4;
 
@@ -178,6 +178,11 @@ struct RecoverTables {
     long long *att_uoff = nullptr;
     int *sid = nullptr;
     uint4 *u2 = nullptr, *tw = nullptr, *ritw = nullptr, *uinv = nullptr, *xs = nullptr, *xinv = nullptr, *Lc = nullptr, *Veval = nullptr;
+    // staged decoder (fast attempt on all S shares): syndrome weights by domain index, domain index -> sorted position
+    uint4 *syn_wt = nullptr;
+    int *pos_of_dom = nullptr;
+    int nsyn0 = 0, maxL0 = 0;
+    long long uoff0 = 0;
     // all-shares-present fast path (S == n == N): inverse NTT + degree check
     int fast_logn = 0;
     uint4 *itw = nullptr, *iscale = nullptr;
@@ -197,9 +202,11 @@ struct hbmpc_ctx {
     std::string err;
     int num_sms = 148;
     int matvec_regs = 0;
-    int ntt_ctas[3][9] = {};                        // resident CTAs per SM of ntt_kernel<LOGN, MODE>
+    int ntt_ctas[5][9] = {};                        // resident CTAs per SM of ntt_kernel<LOGN, MODE>
     size_t scan_max = 65536;                        // HBMPC_SCAN_MAX: batches up to this size skip the compaction pass
     bool no_speculation = false;                    // HBMPC_NO_SPECULATION=1: never try the persistent-attacker shortcut
+    size_t staged_min = 4096;                       // HBMPC_STAGED_MIN: failing sets of at least this many items use the staged decoder
+    int staged_seg = 8;                             // HBMPC_STAGED_SEG: Berlekamp-Massey iterations between two re-sorts
     unsigned int *h_spec = nullptr;                 // pinned: failing-item count + per-sender error histogram of the scout pass
     bool no_fastpath = false;                       // HBMPC_NO_FASTPATH=1: K3 never takes the all-shares-present inverse-NTT path
     bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
@@ -298,6 +305,10 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
         if (sx) ctx->scan_max = (size_t)atoll(sx);
         const char *ns = getenv("HBMPC_NO_SPECULATION");
         ctx->no_speculation = ns && ns[0] == '1';
+        const char *sm = getenv("HBMPC_STAGED_MIN");
+        if (sm) ctx->staged_min = (size_t)atoll(sm);
+        const char *sg = getenv("HBMPC_STAGED_SEG");
+        if (sg && atoi(sg) > 0) ctx->staged_seg = atoi(sg);
         const char *cm = getenv("HBMPC_CHUNK_MB");
         if (cm && atoi(cm) > 0) ctx->chunk_bytes = (size_t)atoi(cm) << 20;
     }
@@ -835,6 +846,20 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
         if ((rc = get_inverse_twiddles(ctx, domain_size(n), &T.ritw, &sc))) return rc;
     }
     if ((rc = upload_fr(ctx, U, &T.uinv, &T.allocs))) return rc;
+    if (T.fast) {
+        const int Nd = domain_size(n);
+        std::vector<HFr> swt((size_t)Nd, hfr::ZERO);
+        std::vector<int> pod((size_t)Nd, -1);
+        for (size_t i = 0; i < S; ++i) {
+            swt[sorted_ids[i]] = U2[(size_t)att_uoff[0] + i];
+            pod[sorted_ids[i]] = (int)i;
+        }
+        if ((rc = upload_fr(ctx, swt, &T.syn_wt, &T.allocs))) return rc;
+        if ((rc = upload(ctx, pod, &T.pos_of_dom, &T.allocs))) return rc;
+        T.nsyn0 = att_nsyn[0];
+        T.maxL0 = att_maxL[0];
+        T.uoff0 = att_uoff[0];
+    }
     if ((rc = upload_fr(ctx, xs, &T.xs, &T.allocs))) return rc;
     if ((rc = upload_fr(ctx, xinv, &T.xinv, &T.allocs))) return rc;
     if ((rc = upload_fr(ctx, L.Lc, &T.Lc, &T.allocs))) return rc;
@@ -892,6 +917,127 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
         T.er_zero_from = N - (int)t;
         while ((1 << T.er_logn) < N) ++T.er_logn;
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ K4 staged decoder
+// Decodes the failing items list[first .. cnt) (cnt known on the host) wave by wave through the stages described in
+// robust.cuh; what the fast attempt cannot decode is collected in a second list and finished by robust_kernel's exact path.
+static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const RobustArgs &r, const int *in_map, unsigned int first,
+                         unsigned int cnt, long long fb_blocks, int fb_threads) {
+    if (cnt <= first) return 0;
+    cudaStream_t st = ln.stream;
+    const int logn = r.logn, N = 1 << logn;
+    const int tp = r.t + 2, syn_ld = std::max(T.nsyn0, 1), seg = ctx->staged_seg;
+    const int nseg = (T.nsyn0 + seg - 1) / seg;
+    const size_t total = cnt - first;
+    const size_t per_slot = ((size_t)syn_ld + 5 * (size_t)tp + 1) * 32 + 16 + 32 + 4 + 1;
+    size_t budget = (size_t)1536 << 20;
+    if (const char *wm = getenv("HBMPC_STAGED_WS_MB")) if (atoll(wm) > 0) budget = (size_t)atoll(wm) << 20;
+    size_t Wmax = std::max<size_t>(budget / per_slot, 1024) & ~(size_t)1023;
+    if (Wmax > total) Wmax = total;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    const size_t o_syn = off;   off = al(off + Wmax * syn_ld * 32);
+    const size_t o_lam = off;   off = al(off + Wmax * tp * 32);
+    const size_t o_bp = off;    off = al(off + Wmax * tp * 32);
+    const size_t o_om = off;    off = al(off + Wmax * tp * 32);
+    const size_t o_num = off;   off = al(off + Wmax * tp * 32);
+    const size_t o_den = off;   off = al(off + Wmax * tp * 32);
+    const size_t o_bdis = off;  off = al(off + Wmax * 32);
+    const size_t o_state = off; off = al(off + Wmax * 16);
+    const size_t o_mask = off;  off = al(off + Wmax * 32);
+    const size_t o_perm = off;  off = al(off + Wmax * 4);
+    const size_t o_key = off;   off = al(off + Wmax);
+    void *wsp = nullptr, *aux = nullptr;
+    int rc;
+    if ((rc = scratch_get(ctx, ln, 10, off, &wsp))) return rc;
+    const size_t hist_bytes = (size_t)(nseg + 1) * 256 * 4;
+    if ((rc = scratch_get(ctx, ln, 11, al(hist_bytes) + total * 4 + 256, &aux))) return rc;
+    unsigned int *hist = (unsigned int *)aux;
+    unsigned int *count2 = (unsigned int *)((char *)aux + al(hist_bytes));
+    unsigned int *list2 = count2 + 4;
+    CK(cudaMemsetAsync(count2, 0, 16, st));
+    char *w8 = (char *)wsp;
+    StagedArgs sa{};
+    sa.syn = (uint4 *)(w8 + o_syn); sa.lam = (uint4 *)(w8 + o_lam); sa.bp = (uint4 *)(w8 + o_bp); sa.om = (uint4 *)(w8 + o_om);
+    sa.num = (uint4 *)(w8 + o_num); sa.den = (uint4 *)(w8 + o_den); sa.bdis = (uint4 *)(w8 + o_bdis); sa.state = (int4 *)(w8 + o_state);
+    sa.rootmask = (unsigned int *)(w8 + o_mask); sa.key = (unsigned char *)(w8 + o_key);
+    unsigned int *perm = (unsigned int *)(w8 + o_perm);
+    sa.syn_ld = syn_ld; sa.tp = tp; sa.nsyn = T.nsyn0; sa.maxL = T.maxL0;
+    sa.pos_of_dom = T.pos_of_dom;
+    sa.uinv0 = T.uinv + T.uoff0 * 2;
+    sa.list2 = list2; sa.count2 = count2;
+    for (size_t w0 = first; w0 < cnt; w0 += Wmax) {
+        const unsigned int W = (unsigned int)std::min<size_t>(Wmax, cnt - w0);
+        const unsigned int gb = (W + 127) / 128;
+        sa.W = W;
+        sa.perm = nullptr;
+        sa.list_first = (unsigned int)w0;
+        CK(cudaMemsetAsync(sa.rootmask, 0, (size_t)W * 32, st));
+        CK(cudaMemsetAsync(hist, 0, hist_bytes, st));
+        {   // 1. syndromes of the weighted word (all S shares)
+            NttArgs na{};
+            na.in = r.in; na.in_sb = r.in_sb; na.in_sc = r.in_sc;
+            na.out = sa.syn; na.out_sb = syn_ld; na.out_sr = 1;
+            na.tw = T.tw;
+            na.B = (long long)W;
+            na.cols = N; na.n = N;
+            na.err = ctx->d_status;
+            na.in_map = in_map;
+            na.wt = T.syn_wt;
+            na.m = N + 1; na.mout = T.nsyn0;
+            na.item_list = r.list + w0;
+            if ((rc = launch_ntt<2>(ctx, st, logn, na))) return rc;
+        }
+        // 2. Berlekamp-Massey in segments, slots re-sorted by locator degree in between
+        for (int k = 0; k < nseg; ++k) {
+            sa.j0 = k * seg;
+            sa.j1 = std::min(T.nsyn0, sa.j0 + seg);
+            bm_segment_kernel<<<gb, 128, 0, st>>>(sa);
+            unsigned int *h = hist + (size_t)k * 256;
+            sort_hist_kernel<<<std::min<unsigned int>((W + 1023) / 1024, (unsigned int)ctx->num_sms * 2), 256, 0, st>>>(sa.key, W, h);
+            sort_scan_kernel<<<1, 32, 0, st>>>(h);
+            sort_scatter_kernel<<<std::min<unsigned int>((W + 2047) / 2048, (unsigned int)ctx->num_sms * 2), 256, 0, st>>>(sa.key, W, h, perm);
+            ctx->launches += 4;
+            CK(cudaGetLastError());
+            sa.perm = perm;
+        }
+        // 3. Omega, Lambda' and zero padding
+        omega_kernel<<<gb, 128, 0, st>>>(sa);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        NttArgs nb{};
+        nb.in_sb = tp; nb.in_sc = 1;
+        nb.out_sb = tp; nb.out_sr = 1;
+        nb.tw = T.ritw;
+        nb.B = (long long)W;
+        nb.cols = tp; nb.n = N;
+        nb.err = ctx->d_status;
+        nb.rootmask = sa.rootmask;
+        nb.idset = in_map;
+        nb.in = sa.lam;   // 4. Chien search
+        if ((rc = launch_ntt<3>(ctx, st, logn, nb))) return rc;
+        nb.in = sa.om; nb.out = sa.num;   // 5. Forney numerators / denominators at the roots
+        if ((rc = launch_ntt<4>(ctx, st, logn, nb))) return rc;
+        nb.in = sa.bp; nb.out = sa.den;
+        if ((rc = launch_ntt<4>(ctx, st, logn, nb))) return rc;
+        // 6. error values, path, corrected coefficients, flags
+        staged_finish_kernel<<<gb, 128, 0, st>>>(r, sa);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    // leftovers: the literal OEC rounds
+    RobustArgs rf = r;
+    rf.list = list2;
+    rf.count = count2;
+    rf.fail_scan = nullptr;
+    rf.fast = 0;
+    rf.list_first = 0;
+    rf.list_max = 0;
+    robust_kernel<<<(unsigned)fb_blocks, fb_threads, 0, st>>>(rf);
+    ctx->launches++;
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -1166,10 +1312,20 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         // full decoder.  Results are identical to decoding everything (see robust.cuh: spec_finalize_kernel).
         const unsigned int SCOUTS = 64, SPEC_MIN = 1024;
         bool done = false;
-        if (!scan && !ctx->async && !ctx->no_speculation && T.rmax >= 1) {
+        // large failing sets go through the staged decoder (needs the count on the host: synchronous calls only)
+        auto decode_list = [&](const RobustArgs &ra, unsigned int cnt_host) -> int {
+            if (T.fast && !ra.hist && cnt_host != UINT_MAX && cnt_host > ra.list_first && (size_t)(cnt_host - ra.list_first) >= ctx->staged_min)
+                return staged_decode(ctx, ln, T, ra, P.in_map, ra.list_first, cnt_host, blocks, threads);
+            return launch_robust(ra);
+        };
+        unsigned int cnt_host = UINT_MAX;
+        if (!scan && !ctx->async && T.rmax >= 1) {
             CK(cudaMemcpyAsync(ctx->h_spec, count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
             CK(cudaStreamSynchronize(ln.stream));
-            const unsigned int cnt = ctx->h_spec[0];
+            cnt_host = ctx->h_spec[0];
+        }
+        if (cnt_host != UINT_MAX && !ctx->no_speculation) {
+            const unsigned int cnt = cnt_host;
             if (cnt >= SPEC_MIN) {
                 // ---- scouts
                 void *histbuf = nullptr;
@@ -1260,16 +1416,18 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
                     CK(cudaGetLastError());
                     RobustArgs rr = r;
                     rr.need_lc = 1;  // the speculative launch overwrote coeffs
-                    if ((rc = launch_robust(rr))) return rc;
+                    CK(cudaMemcpyAsync(ctx->h_spec, count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
+                    CK(cudaStreamSynchronize(ln.stream));
+                    if ((rc = decode_list(rr, ctx->h_spec[0]))) return rc;
                 } else {
                     RobustArgs rr = r;
                     rr.list_first = SCOUTS;
-                    if ((rc = launch_robust(rr))) return rc;
+                    if ((rc = decode_list(rr, cnt))) return rc;
                 }
                 done = true;
             }
         }
-        if (!done && (rc = launch_robust(r))) return rc;
+        if (!done && (rc = decode_list(r, cnt_host))) return rc;
 
         if (want_secrets) {
             gather_first_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>((long long)Bc, (long long)m, (const uint4 *)vc.dev, (uint4 *)vs.dev);

@@ -37,6 +37,13 @@ struct NttArgs {
     // loaded, ids outside the examined set contribute zero (in_map[k] < 0); outputs are left unscaled.
     const uint4 *wt;       // [N][2]
     int *path;             // MODE 1/2: path[b] = 0 is written here (the decoder overwrites it for items that fail)
+    // staged robust decoder (robust.cuh): the input item of output slot b is item_list[b] (MODE 2: syndromes of the failing
+    // items); MODE 3 (Chien search) sets bit `pos` of rootmask[b][8] for every transformed value that is zero at a domain
+    // position of the supplied id set (idset[pos] >= 0); MODE 4 stores the value at the q-th set bit of rootmask[b] to
+    // out[b][q] (Forney numerators / denominators at the error positions only)
+    const unsigned int *item_list;
+    unsigned int *rootmask;
+    const int *idset;
 };
 
 // SKIP_ONE: test for the trivial twiddle (only where the index is warp-uniform -- pass 0 -- so the test folds away or
@@ -100,7 +107,21 @@ __host__ __device__ constexpr int ntt_g() { return LOGN < HB_NTT_G ? LOGN : (LOG
 // one transformed value at natural-order position `pos` of item b
 template <int MODE>
 __device__ __forceinline__ void ntt_emit(const NttArgs &a, long long b, int pos, const uint32_t (&v)[8], const uint32_t (&sc)[8]) {
-    if (MODE == 0) {
+    if (MODE == 3) {
+        if (fr_is_zero(v) && a.idset[pos] >= 0) atomicOr(a.rootmask + b * 8 + (pos >> 5), 1u << (pos & 31));
+    } else if (MODE == 4) {
+        const unsigned int *mk = a.rootmask + b * 8;
+        const unsigned int w = mk[pos >> 5];
+        if ((w >> (pos & 31)) & 1u) {
+            int q = __popc(w & ((1u << (pos & 31)) - 1u));
+            for (int i = 0; i < (pos >> 5); ++i) q += __popc(mk[i]);
+            if (q < a.cols) {  // a locator has at most cols - 1 roots; anything else is a slot the decoder has given up on
+                uint4 *o = a.out + (b * a.out_sb + (long long)q * a.out_sr) * 2;
+                o[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                o[1] = make_uint4(v[4], v[5], v[6], v[7]);
+            }
+        }
+    } else if (MODE == 0) {
         if (pos < a.n) {
             uint4 *o = a.out + (b * a.out_sb + (long long)pos * a.out_sr) * 2;
             stg_stream(o, make_uint4(v[0], v[1], v[2], v[3]));
@@ -155,7 +176,7 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
         const int pos = tid_i * E + e;
         const int k = (int)(__brev((unsigned)pos) >> (32 - LOGN));
         k_of[e] = k;
-        rec_of[e] = (k < a.cols) ? ((MODE != 0 && a.in_map) ? a.in_map[k] : k) : -1;
+        rec_of[e] = (k < a.cols) ? (((MODE == 1 || MODE == 2) && a.in_map) ? a.in_map[k] : k) : -1;
     }
     uint4 *myIn = sIn + threadIdx.x;
     // `gate` carries a data dependence on the values just read from the staging slots, so the asynchronous copies that
@@ -164,10 +185,11 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
     auto prefetch = [&](long long t, unsigned int gate) {
         const long long bb = t * IPC + item_l;
         if (t < ntiles && bb < a.B && gate != never) {
+            const long long src = (MODE == 2 && a.item_list) ? (long long)a.item_list[bb] : bb;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 if (rec_of[e] < 0) continue;
-                const uint4 *p = a.in + (bb * a.in_sb + (long long)rec_of[e] * a.in_sc) * 2;
+                const uint4 *p = a.in + (src * a.in_sb + (long long)rec_of[e] * a.in_sc) * 2;
                 cp_async16(myIn + (e * 2) * HB_NTT_BLOCK, p);
                 cp_async16(myIn + (e * 2 + 1) * HB_NTT_BLOCK, p + 1);
             }
@@ -182,12 +204,14 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
         uint32_t x[E][8];
         // ---- pass 0: inputs from the prefetch staging (thread-private slots: no barrier), stages with half = 1, 2, 4
         cp_async_wait_all();
+        unsigned dep = 0;  // MODE 3/4: data dependence of the next prefetch on the staged values (see `gate`)
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             if (active && rec_of[e] >= 0) {
                 const int k = k_of[e];
                 load_fr(x[e], myIn[(e * 2) * HB_NTT_BLOCK], myIn[(e * 2 + 1) * HB_NTT_BLOCK]);
-                bad |= geq_mod(x[e]) ? 1u : 0u;
+                if (MODE <= 2) bad |= geq_mod(x[e]) ? 1u : 0u;  // MODE 3/4 read decoder state, not user data
+                else dep |= (x[e][0] ^ x[e][7]) >> 31;
                 if (MODE == 2) {
                     uint32_t w[8], y[8];
                     load_fr(w, __ldg(a.wt + k * 2), __ldg(a.wt + k * 2 + 1));
@@ -200,9 +224,9 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
                 for (int i = 0; i < 8; ++i) x[e][i] = 0;
             }
         }
-        if (MODE != 0 && a.path && active && tid_i == 0) a.path[b] = 0;
+        if ((MODE == 1 || MODE == 2) && a.path && active && tid_i == 0) a.path[b] = 0;
         // the staged values are in registers (and were examined by geq_mod): the slots can take the next tile's inputs
-        prefetch(tile + gridDim.x, bad);
+        prefetch(tile + gridDim.x, bad | dep);
         ntt_stages<G, E, true>(x, sTw, 0, 1, LOGN - 1);
         if constexpr (NP == 1) {
 #pragma unroll

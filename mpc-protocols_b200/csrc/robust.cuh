@@ -428,6 +428,89 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
     return L;
 }
 
+// Writes the outcome of one decoded item: path < 0 -> DecodingError (zeroed outputs); otherwise the corrected coefficients by
+// linearity, the flag bits (error positions + shares beyond the examined prefix that disagree with the decoded polynomial),
+// the scout histogram and the path.  rootpos[0..L) = sorted positions of the errors, load_ev(e, q) = canonical error value q.
+template <typename EvLoad>
+__device__ __forceinline__ void robust_store_item(const RobustArgs &a, long long b, int L, const int *rootpos, int path, int Pused, EvLoad load_ev) {
+    uint4 *co = a.coeffs + b * a.mout * 2;
+    unsigned long long *fl = a.flags ? a.flags + b * a.flag_words : nullptr;
+    if (path < 0) {
+        for (int k = 0; k < a.mout; ++k) { co[k * 2] = make_uint4(0, 0, 0, 0); co[k * 2 + 1] = make_uint4(0, 0, 0, 0); }
+        if (fl) for (int w = 0; w < a.flag_words; ++w) fl[w] = 0ull;
+        a.path[b] = -8;
+        if (a.clear_fail) a.clear_fail[b] = 0;
+        *(volatile unsigned int *)a.fail_any = 1u;
+        return;
+    }
+    // corrected coefficients by linearity (Lc*y first when the optimistic stage did not provide it)
+    for (int k = 0; k < a.mout; ++k) {
+        if (a.need_lc) {
+            acc_t A0;
+            acc_zero(A0);
+            const uint4 *yb = a.in + b * a.in_sb * 2;
+            for (int i = 0; i < a.m; ++i) {
+                uint32_t y[8], lc[8];
+                ldg_fr(y, yb + (long long)a.order[i] * a.in_sc * 2);
+                ldg_fr(lc, a.Lc + ((size_t)k * a.m + i) * 2);
+                acc_mac(A0, y, lc);
+            }
+            uint32_t c0[8];
+            acc_reduce(A0, c0);
+            co[k * 2] = make_uint4(c0[0], c0[1], c0[2], c0[3]);
+            co[k * 2 + 1] = make_uint4(c0[4], c0[5], c0[6], c0[7]);
+        }
+        acc_t A;
+        acc_zero(A);
+        bool any = false;
+        for (int q = 0; q < L; ++q) {
+            if (rootpos[q] >= a.m) break;
+            uint32_t e[8], lc[8];
+            load_ev(e, q);
+            ldg_fr(lc, a.Lc + ((size_t)k * a.m + rootpos[q]) * 2);
+            acc_mac(A, e, lc);
+            any = true;
+        }
+        if (any) {
+            uint32_t corr[8], c[8], r[8];
+            acc_reduce(A, corr);
+            load_fr(c, co[k * 2], co[k * 2 + 1]);
+            fr_sub(r, c, corr);
+            co[k * 2] = make_uint4(r[0], r[1], r[2], r[3]);
+            co[k * 2 + 1] = make_uint4(r[4], r[5], r[6], r[7]);
+        }
+    }
+    if (fl) {
+        for (int w = 0; w < a.flag_words; ++w) fl[w] = 0ull;
+        for (int q = 0; q < L; ++q) {
+            const int j = a.order[rootpos[q]];
+            fl[j >> 6] |= 1ull << (j & 63);
+        }
+        // shares beyond the examined prefix: evaluate the decoded polynomial (needs all m coefficients: mout == m)
+        
+        const uint4 *ybase = a.in + b * a.in_sb * 2;
+        for (int s = Pused; s < a.S; ++s) {
+            acc_t A;
+            acc_zero(A);
+            for (int k = 0; k < a.m; ++k) {
+                uint32_t c[8], v[8];
+                load_fr(c, co[k * 2], co[k * 2 + 1]);
+                ldg_fr(v, a.Veval + ((size_t)s * a.m + k) * 2);
+                acc_mac(A, c, v);
+            }
+            uint32_t fv[8], y[8];
+            acc_reduce(A, fv);
+            const int j = a.order[s];
+            ldg_fr(y, ybase + (long long)j * a.in_sc * 2);
+            if (!fr_eq(fv, y)) fl[j >> 6] |= 1ull << (j & 63);
+        }
+    }
+    if (a.hist)
+        for (int q = 0; q < L; ++q) atomicAdd(&a.hist[a.order[rootpos[q]]], 1u);
+    if (a.clear_fail) a.clear_fail[b] = 0;
+    a.path[b] = path;
+}
+
 #ifndef HB_ROBUST_MAXT
 #define HB_ROBUST_MAXT 85  // t < n/3, n <= 256
 #endif
@@ -468,82 +551,7 @@ __global__ void __launch_bounds__(128, HB_ROBUST_MINB) robust_kernel(const Robus
                 if (L >= 0) { path = r; used_att = r; break; }
             }
         }
-        uint4 *co = a.coeffs + b * a.mout * 2;
-        unsigned long long *fl = a.flags ? a.flags + b * a.flag_words : nullptr;
-        if (path < 0) {
-            for (int k = 0; k < a.mout; ++k) { co[k * 2] = make_uint4(0, 0, 0, 0); co[k * 2 + 1] = make_uint4(0, 0, 0, 0); }
-            if (fl) for (int w = 0; w < a.flag_words; ++w) fl[w] = 0ull;
-            a.path[b] = -8;
-            if (a.clear_fail) a.clear_fail[b] = 0;
-            *(volatile unsigned int *)a.fail_any = 1u;
-            continue;
-        }
-        // corrected coefficients by linearity (Lc*y first when the optimistic stage did not provide it)
-        for (int k = 0; k < a.mout; ++k) {
-            if (a.need_lc) {
-                acc_t A0;
-                acc_zero(A0);
-                const uint4 *yb = a.in + b * a.in_sb * 2;
-                for (int i = 0; i < a.m; ++i) {
-                    uint32_t y[8], lc[8];
-                    ldg_fr(y, yb + (long long)a.order[i] * a.in_sc * 2);
-                    ldg_fr(lc, a.Lc + ((size_t)k * a.m + i) * 2);
-                    acc_mac(A0, y, lc);
-                }
-                uint32_t c0[8];
-                acc_reduce(A0, c0);
-                co[k * 2] = make_uint4(c0[0], c0[1], c0[2], c0[3]);
-                co[k * 2 + 1] = make_uint4(c0[4], c0[5], c0[6], c0[7]);
-            }
-            acc_t A;
-            acc_zero(A);
-            bool any = false;
-            for (int q = 0; q < L; ++q) {
-                if (rootpos[q] >= a.m) break;
-                uint32_t e[8], lc[8];
-                ws.ld(e, lay.ev + q);
-                ldg_fr(lc, a.Lc + ((size_t)k * a.m + rootpos[q]) * 2);
-                acc_mac(A, e, lc);
-                any = true;
-            }
-            if (any) {
-                uint32_t corr[8], c[8], r[8];
-                acc_reduce(A, corr);
-                load_fr(c, co[k * 2], co[k * 2 + 1]);
-                fr_sub(r, c, corr);
-                co[k * 2] = make_uint4(r[0], r[1], r[2], r[3]);
-                co[k * 2 + 1] = make_uint4(r[4], r[5], r[6], r[7]);
-            }
-        }
-        if (fl) {
-            for (int w = 0; w < a.flag_words; ++w) fl[w] = 0ull;
-            for (int q = 0; q < L; ++q) {
-                const int j = a.order[rootpos[q]];
-                fl[j >> 6] |= 1ull << (j & 63);
-            }
-            // shares beyond the examined prefix: evaluate the decoded polynomial (needs all m coefficients: mout == m)
-            const int Pused = a.att_P[used_att];
-            const uint4 *ybase = a.in + b * a.in_sb * 2;
-            for (int s = Pused; s < a.S; ++s) {
-                acc_t A;
-                acc_zero(A);
-                for (int k = 0; k < a.m; ++k) {
-                    uint32_t c[8], v[8];
-                    load_fr(c, co[k * 2], co[k * 2 + 1]);
-                    ldg_fr(v, a.Veval + ((size_t)s * a.m + k) * 2);
-                    acc_mac(A, c, v);
-                }
-                uint32_t fv[8], y[8];
-                acc_reduce(A, fv);
-                const int j = a.order[s];
-                ldg_fr(y, ybase + (long long)j * a.in_sc * 2);
-                if (!fr_eq(fv, y)) fl[j >> 6] |= 1ull << (j & 63);
-            }
-        }
-        if (a.hist)
-            for (int q = 0; q < L; ++q) atomicAdd(&a.hist[a.order[rootpos[q]]], 1u);
-        if (a.clear_fail) a.clear_fail[b] = 0;
-        a.path[b] = path;
+        robust_store_item(a, b, L, rootpos, path, used_att < 0 ? 0 : a.att_P[used_att], [&](uint32_t (&e)[8], int q) { ws.ld(e, lay.ev + q); });
     }
 }
 
@@ -592,6 +600,280 @@ __global__ void spec_finalize_kernel(const SpecArgs a) {
         if (a.flags)
             for (int w = 0; w < a.flag_words; ++w) a.flags[b * a.flag_words + w] = path < 0 ? 0ull : sf[w];
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Staged decoder for large failing sets (the throughput path of K4).  robust_kernel above keeps one codeword per thread
+// from start to finish: its lanes diverge with the error count of their codewords (Berlekamp-Massey trip counts) and its
+// transforms run serially through a global workspace.  Here the fast attempt (all S shares, see the header) is cut into
+// uniform stages over a WAVE of failing items, each with per-slot state in global memory (item-major, one 32-byte sector
+// per field element):
+//   1. syndromes        ntt_kernel<LOGN,2> on the weighted word (warp-cooperative transform, item_list indirection)
+//   2. Berlekamp-Massey bm_segment_kernel, one thread per slot, in segments of a few iterations; between segments the
+//                       slots are re-sorted by their current locator degree L (counting sort), so the lanes of a warp
+//                       run the same trip counts: codewords with few errors reveal themselves early (L stops growing)
+//                       and no longer ride along with the longest one
+//   3. Omega, Lambda'   omega_kernel (sorted by L)
+//   4. Chien search     ntt_kernel<LOGN,3> on Lambda -> bit mask of the roots among the supplied ids
+//   5. Forney values    ntt_kernel<LOGN,4> on Omega and Lambda' -> values at the roots only
+//   6. finish           staged_finish_kernel (sorted by L): error values, path rule, corrected coefficients, flags
+// Items whose fast attempt fails (more than maxL errors overall, a locator without enough roots) are appended to a second
+// list and go through robust_kernel's exact path (fast = 0): outcomes are bit-identical by construction, whatever the route.
+struct StagedArgs {
+    uint4 *syn;                 // [W][syn_ld] syndromes (Montgomery form)
+    uint4 *lam, *bp, *om;       // [W][tp]     Lambda, B (later Lambda'), Omega
+    uint4 *num, *den;           // [W][tp]     Omega / Lambda' at the roots (later: canonical error values in num)
+    uint4 *bdis;                // [W]         discrepancy at the last length change
+    int4 *state;                // [W]         (L, lenB, shift, dead)
+    unsigned int *rootmask;     // [W][8]
+    unsigned char *key;         // [W]         sort key: L, 255 = dead
+    const unsigned int *perm;   // [W]         slots in sorted order (nullptr: identity)
+    unsigned int W;
+    int syn_ld, tp, nsyn, maxL, j0, j1;
+    // finish
+    unsigned int list_first;    // slot s decodes item list[list_first + s]
+    const int *pos_of_dom;      // [N] sorted position of the share with domain index k (-1: not supplied)
+    const uint4 *uinv0;         // [S] attempt-0 uinv
+    unsigned int *list2, *count2;  // items left to the exact path
+};
+
+__device__ __forceinline__ void ld_fr2(uint32_t (&a)[8], const uint4 *p) { load_fr(a, p[0], p[1]); }
+__device__ __forceinline__ void st_fr2(uint4 *p, const uint32_t (&a)[8]) {
+    p[0] = make_uint4(a[0], a[1], a[2], a[3]);
+    p[1] = make_uint4(a[4], a[5], a[6], a[7]);
+}
+
+// Berlekamp-Massey iterations j0 <= j < j1 of every live slot (same recurrences as rs_attempt)
+__global__ void __launch_bounds__(128, 4) bm_segment_kernel(const StagedArgs a) {
+    const unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.W) return;
+    const unsigned int slot = a.perm ? a.perm[idx] : idx;
+    uint4 *lam = a.lam + (size_t)slot * a.tp * 2, *bp = a.bp + (size_t)slot * a.tp * 2;
+    const uint4 *syn = a.syn + (size_t)slot * a.syn_ld * 2;
+    uint32_t one[8], bdis[8];
+    one_mont_limbs(one);
+    int L, lenB, shift;
+    if (a.j0 == 0) {
+        copy8(bdis, one);
+        st_fr2(lam, one);
+        st_fr2(bp, one);
+        L = 0; lenB = 1; shift = 1;
+    } else {
+        const int4 st = a.state[slot];
+        if (st.w) return;  // dead: the fast attempt cannot succeed
+        L = st.x; lenB = st.y; shift = st.z;
+        ld_fr2(bdis, a.bdis + (size_t)slot * 2);
+    }
+    bool dead = false;
+#pragma unroll 1
+    for (int j = a.j0; j < a.j1; ++j) {
+        uint32_t delta[8];
+        {
+            acc_t A;
+            acc_zero(A);
+            const int lim = L < j ? L : j;
+            uint32_t x[8], sy[8];
+            ld_fr2(x, lam);
+            ld_fr2(sy, syn + (size_t)j * 2);
+#pragma unroll 1
+            for (int l = 0; l <= lim; ++l) {
+                uint32_t xn[8], sn[8];
+                const int ln = l < lim ? l + 1 : l;  // software pipelining: the next operands are in flight during the product
+                ld_fr2(xn, lam + (size_t)ln * 2);
+                ld_fr2(sn, syn + (size_t)(j - ln) * 2);
+                acc_mac(A, x, sy);
+                copy8(x, xn);
+                copy8(sy, sn);
+            }
+            acc_reduce(A, delta);
+        }
+        if (fr_is_zero(delta)) { ++shift; continue; }
+        uint32_t nd[8];
+        fr_neg(nd, delta);
+        const bool grow = 2 * L <= j;
+        const int newL = grow ? j + 1 - L : L;
+        if (newL > a.maxL) { dead = true; break; }
+#pragma unroll 1
+        for (int l = newL; l >= 0; --l) {
+            uint32_t lm[8], bl[8], res[8];
+            if (l <= L) ld_fr2(lm, lam + (size_t)l * 2); else set_zero(lm);
+            const int bi = l - shift;
+            const bool hasb = bi >= 0 && bi < lenB;
+            if (hasb) ld_fr2(bl, bp + (size_t)bi * 2); else set_zero(bl);
+            acc_t A;
+            acc_zero(A);
+            acc_mac(A, lm, bdis);
+            if (hasb) acc_mac(A, bl, nd);
+            acc_reduce(A, res);
+            st_fr2(lam + (size_t)l * 2, res);
+            if (grow && l <= L) st_fr2(bp + (size_t)l * 2, lm);
+        }
+        if (grow) {
+            lenB = L + 1;
+            L = newL;
+            copy8(bdis, delta);
+            shift = 1;
+        } else {
+            ++shift;
+        }
+    }
+    a.state[slot] = make_int4(L, lenB, shift, dead ? 1 : 0);
+    st_fr2(a.bdis + (size_t)slot * 2, bdis);
+    a.key[slot] = dead ? (unsigned char)255 : (unsigned char)L;
+}
+
+// counting sort of the slots by key (any order inside a bin): hist -> exclusive scan -> scatter
+__global__ void sort_hist_kernel(const unsigned char *key, unsigned int W, unsigned int *hist) {
+    __shared__ unsigned int h[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < W; i += gridDim.x * blockDim.x) atomicAdd(&h[key[i]], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (h[i]) atomicAdd(&hist[i], h[i]);
+}
+__global__ void sort_scan_kernel(unsigned int *hist) {  // <<<1, 32>>>: hist -> exclusive prefix sums
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int i = 0; i < 256; ++i) { const unsigned int c = hist[i]; hist[i] = run; run += c; }
+    }
+}
+__global__ void sort_scatter_kernel(const unsigned char *key, unsigned int W, unsigned int *offs, unsigned int *perm) {
+    __shared__ unsigned int h[256], base[256];
+    const unsigned int per = (W + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * per, hi = min(W, lo + per);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (unsigned int i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&h[key[i]], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        base[i] = h[i] ? atomicAdd(&offs[i], h[i]) : 0u;
+        h[i] = 0;
+    }
+    __syncthreads();
+    for (unsigned int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const unsigned int k = key[i];
+        perm[base[k] + atomicAdd(&h[k], 1u)] = i;
+    }
+}
+
+// Omega = S*Lambda mod z^L, Lambda' coefficients l*Lambda_l (into the dead B polynomial), zero padding for the transforms
+__global__ void __launch_bounds__(128, 4) omega_kernel(const StagedArgs a) {
+    const unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.W) return;
+    const unsigned int slot = a.perm ? a.perm[idx] : idx;
+    const int4 st = a.state[slot];
+    if (st.w) return;
+    const int L = st.x;
+    uint4 *lam = a.lam + (size_t)slot * a.tp * 2, *bp = a.bp + (size_t)slot * a.tp * 2, *om = a.om + (size_t)slot * a.tp * 2;
+    const uint4 *syn = a.syn + (size_t)slot * a.syn_ld * 2;
+    uint32_t zero[8], one[8], lmul[8];
+    set_zero(zero);
+    one_mont_limbs(one);
+    copy8(lmul, one);
+#pragma unroll 1
+    for (int l = 0; l < L; ++l) {
+        acc_t A;
+        acc_zero(A);
+#pragma unroll 1
+        for (int k = 0; k <= l; ++k) {
+            uint32_t x[8], sy[8];
+            ld_fr2(x, lam + (size_t)k * 2);
+            ld_fr2(sy, syn + (size_t)(l - k) * 2);
+            acc_mac(A, x, sy);
+        }
+        uint32_t o[8];
+        acc_reduce(A, o);
+        st_fr2(om + (size_t)l * 2, o);
+    }
+#pragma unroll 1
+    for (int l = 1; l <= L; ++l) {
+        uint32_t c[8], lc[8], nl[8];
+        ld_fr2(c, lam + (size_t)l * 2);
+        mont_mul(lc, c, lmul);
+        st_fr2(bp + (size_t)(l - 1) * 2, lc);
+        fr_add(nl, lmul, one);
+        copy8(lmul, nl);
+    }
+    for (int l = L; l < a.tp; ++l) { st_fr2(om + (size_t)l * 2, zero); st_fr2(bp + (size_t)l * 2, zero); }
+    for (int l = L + 1; l < a.tp; ++l) st_fr2(lam + (size_t)l * 2, zero);
+}
+
+__global__ void __launch_bounds__(128, 4) staged_finish_kernel(const RobustArgs a, const StagedArgs s) {
+    const unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.W) return;
+    const unsigned int slot = s.perm ? s.perm[idx] : idx;
+    const unsigned int item = a.list[s.list_first + slot];
+    const long long b = (long long)item;
+    const int4 st = s.state[slot];
+    const int L = st.x;
+    int rootpos[HB_ROBUST_MAXT];
+    bool ok = !st.w && L <= s.maxL;
+    if (ok) {
+        const unsigned int *mk = s.rootmask + (size_t)slot * 8;
+        int nroots = 0;
+        const int N = 1 << a.logn;
+        for (int w = 0; w < (N + 31) / 32; ++w) {
+            unsigned int bits = mk[w];
+            while (bits) {
+                const int k = w * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (nroots < L) rootpos[nroots] = s.pos_of_dom[k];
+                ++nroots;
+            }
+        }
+        ok = nroots == L;
+    }
+    uint4 *num = s.num + (size_t)slot * s.tp * 2, *den = s.den + (size_t)slot * s.tp * 2;
+    uint32_t one[8], run[8];
+    one_mont_limbs(one);
+    copy8(run, one);
+    if (ok && L > 0) {
+        // c_q = -x_q Omega(x_q^-1) / Lambda'(x_q^-1): one inversion for all of them (prefix products kept in `den`'s partner `om`)
+        uint4 *pre = s.om + (size_t)slot * s.tp * 2;
+#pragma unroll 1
+        for (int q = 0; q < L; ++q) {
+            uint32_t dv[8], nr[8];
+            ld_fr2(dv, den + (size_t)q * 2);
+            if (fr_is_zero(dv)) { ok = false; break; }
+            st_fr2(pre + (size_t)q * 2, run);
+            mont_mul(nr, run, dv);
+            copy8(run, nr);
+        }
+        if (ok) {
+            uint32_t inv[8];
+            fr_inv_mont(inv, run);
+#pragma unroll 1
+            for (int q = L - 1; q >= 0; --q) {
+                uint32_t pr[8], dv[8], dinv[8], nv[8], xq[8], numv[8], c[8], nc[8], u[8], e[8], ninv[8];
+                ld_fr2(pr, pre + (size_t)q * 2);
+                ld_fr2(dv, den + (size_t)q * 2);
+                ld_fr2(nv, num + (size_t)q * 2);
+                ldg_fr(xq, a.xs + rootpos[q] * 2);
+                mont_mul(numv, nv, xq);
+                mont_mul(dinv, inv, pr);
+                mont_mul(ninv, inv, dv);
+                copy8(inv, ninv);
+                mont_mul(c, numv, dinv);
+                fr_neg(nc, c);
+                ldg_fr(u, s.uinv0 + rootpos[q] * 2);
+                mont_mul(e, nc, u);  // Montgomery c times canonical uinv -> canonical error value
+                st_fr2(num + (size_t)q * 2, e);
+            }
+        }
+    }
+    if (!ok) {  // the fast attempt failed: this item takes the exact path
+        s.list2[atomicAdd(s.count2, 1u)] = item;
+        return;
+    }
+    int path = -8;
+    {
+        int q = 0;
+        for (int r = 1; r <= a.rmax; ++r) {
+            while (q < L && rootpos[q] < a.needed + r) ++q;
+            if (q <= r) { path = r; break; }
+        }
+    }
+    robust_store_item(a, b, L, rootpos, path, a.S, [&](uint32_t (&e)[8], int q) { ld_fr2(e, num + (size_t)q * 2); });
 }
 
 // items with fail[b] != 0 -> list (any order)
