@@ -202,8 +202,9 @@ struct hbmpc_ctx {
     std::string err;
     int num_sms = 148;
     int matvec_regs = 0;
-    int ntt_ctas[5][9] = {};                        // resident CTAs per SM of ntt_kernel<LOGN, MODE>
+    int ntt_ctas[6][9] = {};                        // resident CTAs per SM of ntt_kernel<LOGN, MODE>
     size_t scan_max = 65536;                        // HBMPC_SCAN_MAX: batches up to this size skip the compaction pass
+    bool no_staged_direct = false;                  // HBMPC_NO_STAGED_DIRECT=1: failing items of the all-points check take the dense check first
     bool no_speculation = false;                    // HBMPC_NO_SPECULATION=1: never try the persistent-attacker shortcut
     size_t staged_min = 4096;                       // HBMPC_STAGED_MIN: failing sets of at least this many items use the staged decoder
     int staged_seg = 8;                             // HBMPC_STAGED_SEG: Berlekamp-Massey iterations between two re-sorts
@@ -305,6 +306,8 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
         if (sx) ctx->scan_max = (size_t)atoll(sx);
         const char *ns = getenv("HBMPC_NO_SPECULATION");
         ctx->no_speculation = ns && ns[0] == '1';
+        const char *nd = getenv("HBMPC_NO_STAGED_DIRECT");
+        ctx->no_staged_direct = nd && nd[0] == '1';
         const char *sm = getenv("HBMPC_STAGED_MIN");
         if (sm) ctx->staged_min = (size_t)atoll(sm);
         const char *sg = getenv("HBMPC_STAGED_SEG");
@@ -923,32 +926,42 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
 // ------------------------------------------------------------------------------------------------ K4 staged decoder
 // Decodes the failing items list[first .. cnt) (cnt known on the host) wave by wave through the stages described in
 // robust.cuh; what the fast attempt cannot decode is collected in a second list and finished by robust_kernel's exact path.
-static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const RobustArgs &r, const int *in_map, unsigned int first,
-                         unsigned int cnt, long long fb_blocks, int fb_threads) {
+// direct != nullptr: the items come straight from the all-points NTT check (S == n == N); paths include 0, the coefficients
+// (INTT of the received word, left in `coeffs` by that check) are corrected by one sparse inverse transform per item, and the
+// leftovers are returned in direct[0] (list) / direct[1] (count) for the caller's dense check instead of being decoded here.
+static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const RobustArgs &r_in, const int *in_map, unsigned int first,
+                         unsigned int cnt, long long fb_blocks, int fb_threads, unsigned int **direct = nullptr) {
     if (cnt <= first) return 0;
+    RobustArgs r = r_in;
+    r.skip_coeffs = direct ? 1 : 0;
     cudaStream_t st = ln.stream;
     const int logn = r.logn, N = 1 << logn;
     const int tp = r.t + 2, syn_ld = std::max(T.nsyn0, 1), seg = ctx->staged_seg;
     const int nseg = (T.nsyn0 + seg - 1) / seg;
     const size_t total = cnt - first;
-    const size_t per_slot = ((size_t)syn_ld + 5 * (size_t)tp + 1) * 32 + 16 + 32 + 4 + 1;
-    size_t budget = (size_t)1536 << 20;
+    const size_t per_slot = (2 * ((size_t)syn_ld + 2 * (size_t)tp + 1) + 5 * (size_t)tp + 1) * 32 + 2 * 16 + 2 * 4 + 1 + 16 + 32 + 1 + 4 + 1;
+    size_t budget = (size_t)3072 << 20;
     if (const char *wm = getenv("HBMPC_STAGED_WS_MB")) if (atoll(wm) > 0) budget = (size_t)atoll(wm) << 20;
     size_t Wmax = std::max<size_t>(budget / per_slot, 1024) & ~(size_t)1023;
     if (Wmax > total) Wmax = total;
+    const size_t Wg = (Wmax + 31) / 32 * 32;  // group-interleaved arrays hold whole groups of 32 positions
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off = 0;
-    const size_t o_syn = off;   off = al(off + Wmax * syn_ld * 32);
-    const size_t o_lam = off;   off = al(off + Wmax * tp * 32);
-    const size_t o_bp = off;    off = al(off + Wmax * tp * 32);
-    const size_t o_om = off;    off = al(off + Wmax * tp * 32);
-    const size_t o_num = off;   off = al(off + Wmax * tp * 32);
-    const size_t o_den = off;   off = al(off + Wmax * tp * 32);
-    const size_t o_bdis = off;  off = al(off + Wmax * 32);
-    const size_t o_state = off; off = al(off + Wmax * 16);
-    const size_t o_mask = off;  off = al(off + Wmax * 32);
-    const size_t o_perm = off;  off = al(off + Wmax * 4);
-    const size_t o_key = off;   off = al(off + Wmax);
+    auto take = [&](size_t bytes) { const size_t o = off; off = al(off + bytes); return o; };
+    size_t o_synG[2], o_lamG[2], o_bpG[2], o_bdisP[2], o_stateP[2], o_originP[2];
+    for (int i = 0; i < 2; ++i) {
+        o_synG[i] = take(Wg * syn_ld * 32);
+        o_lamG[i] = take(Wg * tp * 32);
+        o_bpG[i] = take(Wg * tp * 32);
+        o_bdisP[i] = take(Wg * 32);
+        o_stateP[i] = take(Wg * 16);
+        o_originP[i] = take(Wg * 4);
+    }
+    const size_t o_keyP = take(Wg);
+    const size_t o_lam = take(Wmax * tp * 32), o_bp = take(Wmax * tp * 32), o_om = take(Wmax * tp * 32);
+    const size_t o_num = take(Wmax * tp * 32), o_den = take(Wmax * tp * 32);
+    const size_t o_state = take(Wmax * 16), o_mask = take(Wmax * 32), o_perm = take(Wmax * 4), o_key = take(Wmax);
+    const size_t o_runs = take(Wmax * 32), o_okf = take(Wmax);
     void *wsp = nullptr, *aux = nullptr;
     int rc;
     if ((rc = scratch_get(ctx, ln, 10, off, &wsp))) return rc;
@@ -960,26 +973,44 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
     CK(cudaMemsetAsync(count2, 0, 16, st));
     char *w8 = (char *)wsp;
     StagedArgs sa{};
-    sa.syn = (uint4 *)(w8 + o_syn); sa.lam = (uint4 *)(w8 + o_lam); sa.bp = (uint4 *)(w8 + o_bp); sa.om = (uint4 *)(w8 + o_om);
-    sa.num = (uint4 *)(w8 + o_num); sa.den = (uint4 *)(w8 + o_den); sa.bdis = (uint4 *)(w8 + o_bdis); sa.state = (int4 *)(w8 + o_state);
-    sa.rootmask = (unsigned int *)(w8 + o_mask); sa.key = (unsigned char *)(w8 + o_key);
+    sa.lam = (uint4 *)(w8 + o_lam); sa.bp = (uint4 *)(w8 + o_bp); sa.om = (uint4 *)(w8 + o_om);
+    sa.num = (uint4 *)(w8 + o_num); sa.den = (uint4 *)(w8 + o_den); sa.state = (int4 *)(w8 + o_state);
+    sa.rootmask = (unsigned int *)(w8 + o_mask); sa.key = (unsigned char *)(w8 + o_key); sa.keyP = (unsigned char *)(w8 + o_keyP);
     unsigned int *perm = (unsigned int *)(w8 + o_perm);
     sa.syn_ld = syn_ld; sa.tp = tp; sa.nsyn = T.nsyn0; sa.maxL = T.maxL0;
     sa.pos_of_dom = T.pos_of_dom;
     sa.uinv0 = T.uinv + T.uoff0 * 2;
     sa.list2 = list2; sa.count2 = count2;
+    sa.direct = direct ? 1 : 0;
+    sa.runs = (uint4 *)(w8 + o_runs); sa.okf = (unsigned char *)(w8 + o_okf);
+    const bool prof = getenv("HBMPC_STAGED_PROF") != nullptr;
+    cudaEvent_t pe[8] = {};
+    float pms[7] = {};
+    if (prof) for (auto &e : pe) cudaEventCreate(&e);
+    auto sort_by = [&](const unsigned char *key, unsigned int W, unsigned int *h) -> int {
+        sort_hist_kernel<<<std::min<unsigned int>((W + 1023) / 1024, (unsigned int)ctx->num_sms * 2), 256, 0, st>>>(key, W, h);
+        sort_scan_kernel<<<1, 32, 0, st>>>(h);
+        sort_scatter_kernel<<<std::min<unsigned int>((W + 2047) / 2048, (unsigned int)ctx->num_sms * 2), 256, 0, st>>>(key, W, h, perm);
+        ctx->launches += 3;
+        CK(cudaGetLastError());
+        return 0;
+    };
     for (size_t w0 = first; w0 < cnt; w0 += Wmax) {
         const unsigned int W = (unsigned int)std::min<size_t>(Wmax, cnt - w0);
         const unsigned int gb = (W + 127) / 128;
         sa.W = W;
-        sa.perm = nullptr;
         sa.list_first = (unsigned int)w0;
+        for (int i = 0; i < 2; ++i) {
+            sa.synG[i] = (uint4 *)(w8 + o_synG[i]); sa.lamG[i] = (uint4 *)(w8 + o_lamG[i]); sa.bpG[i] = (uint4 *)(w8 + o_bpG[i]);
+            sa.bdisP[i] = (uint4 *)(w8 + o_bdisP[i]); sa.stateP[i] = (int4 *)(w8 + o_stateP[i]); sa.originP[i] = (unsigned int *)(w8 + o_originP[i]);
+        }
         CK(cudaMemsetAsync(sa.rootmask, 0, (size_t)W * 32, st));
         CK(cudaMemsetAsync(hist, 0, hist_bytes, st));
-        {   // 1. syndromes of the weighted word (all S shares)
+        if (prof) cudaEventRecord(pe[0], st);
+        {   // 1. syndromes of the weighted word (all S shares), written by position (= slot at this point)
             NttArgs na{};
             na.in = r.in; na.in_sb = r.in_sb; na.in_sc = r.in_sc;
-            na.out = sa.syn; na.out_sb = syn_ld; na.out_sr = 1;
+            na.out = sa.synG[0]; na.out_sb = syn_ld; na.out_sr = 1; na.out_group32 = 1;
             na.tw = T.tw;
             na.B = (long long)W;
             na.cols = N; na.n = N;
@@ -990,23 +1021,32 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
             na.item_list = r.list + w0;
             if ((rc = launch_ntt<2>(ctx, st, logn, na))) return rc;
         }
-        // 2. Berlekamp-Massey in segments, slots re-sorted by locator degree in between
+        if (prof) cudaEventRecord(pe[1], st);
+        // 2. Berlekamp-Massey in segments; positions re-sorted by locator degree (and their state moved) in between
         for (int k = 0; k < nseg; ++k) {
             sa.j0 = k * seg;
             sa.j1 = std::min(T.nsyn0, sa.j0 + seg);
             bm_segment_kernel<<<gb, 128, 0, st>>>(sa);
-            unsigned int *h = hist + (size_t)k * 256;
-            sort_hist_kernel<<<std::min<unsigned int>((W + 1023) / 1024, (unsigned int)ctx->num_sms * 2), 256, 0, st>>>(sa.key, W, h);
-            sort_scan_kernel<<<1, 32, 0, st>>>(h);
-            sort_scatter_kernel<<<std::min<unsigned int>((W + 2047) / 2048, (unsigned int)ctx->num_sms * 2), 256, 0, st>>>(sa.key, W, h, perm);
-            ctx->launches += 4;
+            ctx->launches++;
             CK(cudaGetLastError());
-            sa.perm = perm;
+            if (k + 1 < nseg) {
+                if ((rc = sort_by(sa.keyP, W, hist + (size_t)k * 256))) return rc;
+                sa.perm = perm;
+                permute_kernel<<<(W + 255) / 256, 256, 0, st>>>(sa);
+                ctx->launches++;
+                CK(cudaGetLastError());
+                std::swap(sa.synG[0], sa.synG[1]); std::swap(sa.lamG[0], sa.lamG[1]); std::swap(sa.bpG[0], sa.bpG[1]);
+                std::swap(sa.bdisP[0], sa.bdisP[1]); std::swap(sa.stateP[0], sa.stateP[1]); std::swap(sa.originP[0], sa.originP[1]);
+            }
         }
-        // 3. Omega, Lambda' and zero padding
+        if (prof) cudaEventRecord(pe[2], st);
+        // 3. Omega, Lambda' and zero padding, per slot; final order of the slots by locator degree
         omega_kernel<<<gb, 128, 0, st>>>(sa);
         ctx->launches++;
         CK(cudaGetLastError());
+        if ((rc = sort_by(sa.key, W, hist + (size_t)nseg * 256))) return rc;
+        sa.perm = perm;
+        if (prof) cudaEventRecord(pe[3], st);
         NttArgs nb{};
         nb.in_sb = tp; nb.in_sc = 1;
         nb.out_sb = tp; nb.out_sr = 1;
@@ -1018,14 +1058,47 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
         nb.idset = in_map;
         nb.in = sa.lam;   // 4. Chien search
         if ((rc = launch_ntt<3>(ctx, st, logn, nb))) return rc;
+        if (prof) cudaEventRecord(pe[4], st);
         nb.in = sa.om; nb.out = sa.num;   // 5. Forney numerators / denominators at the roots
         if ((rc = launch_ntt<4>(ctx, st, logn, nb))) return rc;
         nb.in = sa.bp; nb.out = sa.den;
         if ((rc = launch_ntt<4>(ctx, st, logn, nb))) return rc;
+        if (prof) cudaEventRecord(pe[5], st);
         // 6. error values, path, corrected coefficients, flags
+        staged_prefix_kernel<<<gb, 128, 0, st>>>(r, sa);
+        staged_invert_kernel<<<(W + 128 * HB_INV_BATCH - 1) / (128 * HB_INV_BATCH), 128, 0, st>>>(sa);
         staged_finish_kernel<<<gb, 128, 0, st>>>(r, sa);
-        ctx->launches++;
+        ctx->launches += 3;
         CK(cudaGetLastError());
+        if (direct && !r.hist_only) {  // coefficients: INTT(y) - INTT(e)
+            NttArgs nc{};
+            nc.in = sa.num; nc.in_sb = tp; nc.in_sc = 1;
+            nc.out = r.coeffs; nc.out_sb = r.mout; nc.out_sr = 1;
+            nc.tw = T.itw;
+            nc.scale = T.iscale;
+            nc.B = (long long)W;
+            nc.cols = N; nc.n = N;
+            nc.err = ctx->d_status;
+            nc.mout = r.mout;
+            nc.rootmask = sa.rootmask;
+            nc.item_list = r.list + w0;
+            if ((rc = launch_ntt<5>(ctx, st, logn, nc))) return rc;
+        }
+        if (prof) {
+            cudaEventRecord(pe[6], st);
+            cudaEventSynchronize(pe[6]);
+            for (int i = 0; i < 6; ++i) { float ms = 0; cudaEventElapsedTime(&ms, pe[i], pe[i + 1]); pms[i] += ms; }
+        }
+    }
+    if (prof) {
+        fprintf(stderr, "staged_decode items=%zu: syndromes %.3f ms, berlekamp-massey+sorts %.3f, omega+sort %.3f, chien %.3f, forney %.3f, finish %.3f\n", total,
+                pms[0], pms[1], pms[2], pms[3], pms[4], pms[5]);
+        for (auto &e : pe) cudaEventDestroy(e);
+    }
+    if (direct) {
+        direct[0] = list2;
+        direct[1] = count2;
+        return 0;
     }
     // leftovers: the literal OEC rounds
     RobustArgs rf = r;
@@ -1193,6 +1266,69 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             CK(cudaGetLastError());
         }
 
+        // decoder arguments (shared by the staged decoder and robust_kernel)
+        RobustArgs r{};
+        r.in = (const uint4 *)vi.dev;
+        r.in_sb = vi.sb; r.in_sc = vi.sj;
+        r.B = (long long)Bc;
+        r.list = list;
+        r.count = count;
+        r.S = (int)S; r.m = (int)m; r.t = (int)t; r.needed = (int)needed; r.rmax = T.rmax; r.fast = T.fast;
+        r.att_P = T.att_P; r.att_nsyn = T.att_nsyn; r.att_maxL = T.att_maxL; r.att_uoff = T.att_uoff;
+        r.u2 = T.u2; r.sid = T.sid; r.tw = T.tw; r.itw = T.ritw; r.uinv = T.uinv;
+        { int lg = 0; while ((1 << lg) < domain_size(n)) ++lg; r.logn = lg; } r.xs = T.xs; r.xinv = T.xinv; r.Lc = T.Lc; r.Veval = T.Veval; r.order = P.order;
+        r.coeffs = (uint4 *)vc.dev;
+        r.mout = T.mout;
+        r.path = (int *)vp.dev;
+        r.flags = want_flags ? (unsigned long long *)vf.dev : nullptr;
+        r.flag_words = fw;
+        r.fail_any = ctx->d_status + 2;
+        const int threads = 128;
+        long long blocks = std::min<long long>((long long)ctx->num_sms * HB_ROBUST_MINB, (long long)((Bc + threads - 1) / threads));
+        if (blocks < 1) blocks = 1;
+
+        // Large failing sets of the all-points check (synchronous calls): straight to the staged decoder, which settles path 0
+        // (errors beyond the examined prefix only), the OEC round and the flags from the error positions; only what it cannot
+        // decode takes the dense check below.
+        bool staged_direct = false;
+        unsigned int *dense_list = list1, *dense_count = count1;
+        if (fastN && T.fast && !ctx->async && Bc > ctx->scan_max) {
+            CK(cudaMemcpyAsync(ctx->h_spec, count1, sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
+            CK(cudaStreamSynchronize(ln.stream));
+            const unsigned int c1 = ctx->h_spec[0];
+            bool persistent = false;
+            if (c1 >= ctx->staged_min && !ctx->no_staged_direct && !ctx->no_speculation && c1 >= 1024) {
+                // a few scouts first: when the same <= t senders are wrong in most of them, the persistent-attacker shortcut
+                // further down (dense interpolation from the senders believed honest) beats decoding every item
+                const unsigned int SC = 64;
+                void *histbuf = nullptr;
+                if ((rc = scratch_get(ctx, ln, 9, 4096, &histbuf))) return rc;
+                unsigned int *hist = (unsigned int *)histbuf;
+                CK(cudaMemsetAsync(hist, 0, S * sizeof(unsigned int), ln.stream));
+                RobustArgs rs = r;
+                rs.list = list1; rs.count = count1;
+                rs.hist = hist; rs.hist_only = 1;
+                unsigned int *unused[2] = {nullptr, nullptr};
+                if ((rc = staged_decode(ctx, ln, T, rs, P.in_map, 0, SC, blocks, threads, unused))) return rc;
+                CK(cudaMemcpyAsync(ctx->h_spec + 8, hist, S * sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
+                CK(cudaStreamSynchronize(ln.stream));
+                size_t nsus = 0;
+                for (size_t j = 0; j < S; ++j)
+                    if (ctx->h_spec[8 + j] >= SC / 2) ++nsus;
+                persistent = nsus >= 1 && nsus <= t && S - nsus >= m;
+            }
+            if (c1 >= ctx->staged_min && !ctx->no_staged_direct && !persistent) {
+                RobustArgs rd = r;
+                rd.list = list1;
+                rd.count = count1;
+                unsigned int *left[2] = {nullptr, nullptr};
+                if ((rc = staged_decode(ctx, ln, T, rd, P.in_map, 0, c1, blocks, threads, left))) return rc;
+                dense_list = left[0];
+                dense_count = left[1];
+                staged_direct = true;
+            }
+        }
+
         const bool erasure = T.er_logn > 0 && !fastN;
         if (erasure) {
             void *tmp = nullptr;
@@ -1227,7 +1363,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             if ((rc = launch_matvec(ctx, ln, tr, 0))) return rc;
         }
         MatvecArgs a{};
-        if (fastN) { a.item_list = list1; a.item_count = count1; }
+        if (fastN) { a.item_list = dense_list; a.item_count = dense_count; }
         a.M = T.M;
         a.in = (const uint4 *)vi.dev;
         a.out = (uint4 *)vc.dev;
@@ -1275,27 +1411,8 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             if ((rc = chunk_commit(ctx, ln, bc, b0, Bc, vc))) return rc;
             return chunk_commit(ctx, ln, bp, b0, Bc, vp);
         }
-        RobustArgs r{};
-        r.in = (const uint4 *)vi.dev;
-        r.in_sb = vi.sb; r.in_sc = vi.sj;
-        r.B = (long long)Bc;
-        r.list = list;
-        r.count = count;
         r.fail_scan = scan ? fail : nullptr;
         r.need_lc = (scan && erasure) ? 1 : 0;
-        r.S = (int)S; r.m = (int)m; r.t = (int)t; r.needed = (int)needed; r.rmax = T.rmax; r.fast = T.fast;
-        r.att_P = T.att_P; r.att_nsyn = T.att_nsyn; r.att_maxL = T.att_maxL; r.att_uoff = T.att_uoff;
-        r.u2 = T.u2; r.sid = T.sid; r.tw = T.tw; r.itw = T.ritw; r.uinv = T.uinv;
-        { int lg = 0; while ((1 << lg) < domain_size(n)) ++lg; r.logn = lg; } r.xs = T.xs; r.xinv = T.xinv; r.Lc = T.Lc; r.Veval = T.Veval; r.order = P.order;
-        r.coeffs = (uint4 *)vc.dev;
-        r.mout = T.mout;
-        r.path = (int *)vp.dev;
-        r.flags = a.flags;
-        r.flag_words = fw;
-        r.fail_any = ctx->d_status + 2;
-        const int threads = 128;
-        long long blocks = std::min<long long>((long long)ctx->num_sms * HB_ROBUST_MINB, (long long)((Bc + threads - 1) / threads));
-        if (blocks < 1) blocks = 1;
         void *ws = nullptr;
         if ((rc = scratch_get(ctx, ln, 6, (size_t)blocks * threads * lay.total * 32 + 64, &ws))) return rc;
         r.ws = (uint4 *)ws;
@@ -1314,7 +1431,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         bool done = false;
         // large failing sets go through the staged decoder (needs the count on the host: synchronous calls only)
         auto decode_list = [&](const RobustArgs &ra, unsigned int cnt_host) -> int {
-            if (T.fast && !ra.hist && cnt_host != UINT_MAX && cnt_host > ra.list_first && (size_t)(cnt_host - ra.list_first) >= ctx->staged_min)
+            if (T.fast && !staged_direct && !ra.hist && cnt_host != UINT_MAX && cnt_host > ra.list_first && (size_t)(cnt_host - ra.list_first) >= ctx->staged_min)
                 return staged_decode(ctx, ln, T, ra, P.in_map, ra.list_first, cnt_host, blocks, threads);
             return launch_robust(ra);
         };

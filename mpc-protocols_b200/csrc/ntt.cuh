@@ -44,6 +44,10 @@ struct NttArgs {
     const unsigned int *item_list;
     unsigned int *rootmask;
     const int *idset;
+    // MODE 5 (correction of the staged decoder, all N points supplied): inverse transform of the sparse error word (value q of
+    // in[b] at the q-th set bit of rootmask[b]), scaled by N^{-1}, SUBTRACTED from out[item_list[b]][k], k < mout
+    int out_group32;       // MODE 2: output slot b, element pos at out[(((b>>5)*out_sb + pos)*2 + half)*32 + (b&31)] (groups of 32
+                           // slots interleaved at 16-byte granularity: one thread per slot reads it coalesced)
 };
 
 // SKIP_ONE: test for the trivial twiddle (only where the index is warp-uniform -- pass 0 -- so the test folds away or
@@ -107,7 +111,18 @@ __host__ __device__ constexpr int ntt_g() { return LOGN < HB_NTT_G ? LOGN : (LOG
 // one transformed value at natural-order position `pos` of item b
 template <int MODE>
 __device__ __forceinline__ void ntt_emit(const NttArgs &a, long long b, int pos, const uint32_t (&v)[8], const uint32_t (&sc)[8]) {
-    if (MODE == 3) {
+    if (MODE == 5) {
+        if (pos < a.mout) {
+            uint32_t c[8], cur[8], r[8];
+            mont_mul(c, v, sc);
+            const long long ob = (long long)a.item_list[b];
+            uint4 *o = a.out + (ob * a.out_sb + (long long)pos * a.out_sr) * 2;
+            load_fr(cur, o[0], o[1]);
+            fr_sub(r, cur, c);
+            o[0] = make_uint4(r[0], r[1], r[2], r[3]);
+            o[1] = make_uint4(r[4], r[5], r[6], r[7]);
+        }
+    } else if (MODE == 3) {
         if (fr_is_zero(v) && a.idset[pos] >= 0) atomicOr(a.rootmask + b * 8 + (pos >> 5), 1u << (pos & 31));
     } else if (MODE == 4) {
         const unsigned int *mk = a.rootmask + b * 8;
@@ -135,9 +150,15 @@ __device__ __forceinline__ void ntt_emit(const NttArgs &a, long long b, int pos,
 #pragma unroll
                 for (int i = 0; i < 8; ++i) c[i] = v[i];
             }
-            uint4 *o = a.out + (b * a.out_sb + (long long)pos * a.out_sr) * 2;
-            stg_stream(o, make_uint4(c[0], c[1], c[2], c[3]));
-            stg_stream(o + 1, make_uint4(c[4], c[5], c[6], c[7]));
+            if (MODE == 2 && a.out_group32) {
+                uint4 *o = a.out + (((b >> 5) * a.out_sb + (long long)pos) * 2) * 32 + (b & 31);
+                o[0] = make_uint4(c[0], c[1], c[2], c[3]);
+                o[32] = make_uint4(c[4], c[5], c[6], c[7]);
+            } else {
+                uint4 *o = a.out + (b * a.out_sb + (long long)pos * a.out_sr) * 2;
+                stg_stream(o, make_uint4(c[0], c[1], c[2], c[3]));
+                stg_stream(o + 1, make_uint4(c[4], c[5], c[6], c[7]));
+            }
         } else if (pos >= a.m) {
             if (!fr_is_zero(v)) a.fail[b] = 1;
         }
@@ -166,7 +187,7 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
     const long long ntiles = (a.B + IPC - 1) / IPC;
     unsigned bad = 0;
     uint32_t sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (MODE == 1) load_fr(sc, a.scale[0], a.scale[1]);
+    if (MODE == 1 || MODE == 5) load_fr(sc, a.scale[0], a.scale[1]);
 
     // Which record feeds each of this thread's E positions is the same for every tile: position pos holds the input with
     // natural index k = bitrev(pos) (zero beyond `cols` / outside the examined id set).
@@ -176,7 +197,7 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
         const int pos = tid_i * E + e;
         const int k = (int)(__brev((unsigned)pos) >> (32 - LOGN));
         k_of[e] = k;
-        rec_of[e] = (k < a.cols) ? (((MODE == 1 || MODE == 2) && a.in_map) ? a.in_map[k] : k) : -1;
+        rec_of[e] = (MODE != 5 && k < a.cols) ? (((MODE == 1 || MODE == 2) && a.in_map) ? a.in_map[k] : k) : -1;
     }
     uint4 *myIn = sIn + threadIdx.x;
     // `gate` carries a data dependence on the values just read from the staging slots, so the asynchronous copies that
@@ -222,6 +243,17 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[e][i] = 0;
+                if (MODE == 5 && active) {  // sparse input: the q-th set bit of rootmask[b] carries in[b][q] at its domain position
+                    const int k = k_of[e];
+                    const unsigned int *mk = a.rootmask + b * 8;
+                    const unsigned int w = mk[k >> 5];
+                    if ((w >> (k & 31)) & 1u) {
+                        int q = __popc(w & ((1u << (k & 31)) - 1u));
+                        for (int i = 0; i < (k >> 5); ++i) q += __popc(mk[i]);
+                        const uint4 *p = a.in + (b * a.in_sb + (long long)q * a.in_sc) * 2;
+                        load_fr(x[e], p[0], p[1]);
+                    }
+                }
             }
         }
         if ((MODE == 1 || MODE == 2) && a.path && active && tid_i == 0) a.path[b] = 0;

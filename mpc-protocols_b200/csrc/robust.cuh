@@ -77,6 +77,8 @@ struct RobustArgs {
     unsigned int *fail_any;     // set to 1 when any item fails to decode
     uint4 *ws;                  // workspace: ws_elems Fr per thread, strided by total thread count
     int ws_elems;
+    int hist_only;              // scout pass ahead of any other stage: only the per-sender error histogram is updated
+    int skip_coeffs;            // staged decoder, all N points supplied: the coefficients are corrected by a transform afterwards
 };
 
 struct FrWs {
@@ -433,6 +435,11 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
 // the scout histogram and the path.  rootpos[0..L) = sorted positions of the errors, load_ev(e, q) = canonical error value q.
 template <typename EvLoad>
 __device__ __forceinline__ void robust_store_item(const RobustArgs &a, long long b, int L, const int *rootpos, int path, int Pused, EvLoad load_ev) {
+    if (a.hist_only) {
+        if (path >= 0)
+            for (int q = 0; q < L; ++q) atomicAdd(&a.hist[a.order[rootpos[q]]], 1u);
+        return;
+    }
     uint4 *co = a.coeffs + b * a.mout * 2;
     unsigned long long *fl = a.flags ? a.flags + b * a.flag_words : nullptr;
     if (path < 0) {
@@ -444,7 +451,7 @@ __device__ __forceinline__ void robust_store_item(const RobustArgs &a, long long
         return;
     }
     // corrected coefficients by linearity (Lc*y first when the optimistic stage did not provide it)
-    for (int k = 0; k < a.mout; ++k) {
+    for (int k = 0; k < (a.skip_coeffs ? 0 : a.mout); ++k) {
         if (a.need_lc) {
             acc_t A0;
             acc_zero(A0);
@@ -606,28 +613,34 @@ __global__ void spec_finalize_kernel(const SpecArgs a) {
 // Staged decoder for large failing sets (the throughput path of K4).  robust_kernel above keeps one codeword per thread
 // from start to finish: its lanes diverge with the error count of their codewords (Berlekamp-Massey trip counts) and its
 // transforms run serially through a global workspace.  Here the fast attempt (all S shares, see the header) is cut into
-// uniform stages over a WAVE of failing items, each with per-slot state in global memory (item-major, one 32-byte sector
-// per field element):
+// uniform stages over a WAVE of failing items ("slots"):
 //   1. syndromes        ntt_kernel<LOGN,2> on the weighted word (warp-cooperative transform, item_list indirection)
-//   2. Berlekamp-Massey bm_segment_kernel, one thread per slot, in segments of a few iterations; between segments the
-//                       slots are re-sorted by their current locator degree L (counting sort), so the lanes of a warp
-//                       run the same trip counts: codewords with few errors reveal themselves early (L stops growing)
-//                       and no longer ride along with the longest one
-//   3. Omega, Lambda'   omega_kernel (sorted by L)
+//   2. Berlekamp-Massey bm_segment_kernel, one thread per slot, in segments of a few iterations.  Between segments the
+//                       slots are re-sorted by their current locator degree L (counting sort) and their state is moved to
+//                       the new position (permute_kernel), so the lanes of a warp run the same trip counts: codewords
+//                       with few errors reveal themselves early (L stops growing) and no longer ride along with the
+//                       longest one.  BM state lives in a group-interleaved layout (32 consecutive positions interleaved
+//                       at 16-byte granularity), so every per-lane access of a warp is one coalesced 512-byte request.
+//   3. Omega, Lambda'   omega_kernel; leaves Lambda, Lambda', Omega item-major per slot for the transforms
 //   4. Chien search     ntt_kernel<LOGN,3> on Lambda -> bit mask of the roots among the supplied ids
 //   5. Forney values    ntt_kernel<LOGN,4> on Omega and Lambda' -> values at the roots only
 //   6. finish           staged_finish_kernel (sorted by L): error values, path rule, corrected coefficients, flags
 // Items whose fast attempt fails (more than maxL errors overall, a locator without enough roots) are appended to a second
 // list and go through robust_kernel's exact path (fast = 0): outcomes are bit-identical by construction, whatever the route.
 struct StagedArgs {
-    uint4 *syn;                 // [W][syn_ld] syndromes (Montgomery form)
-    uint4 *lam, *bp, *om;       // [W][tp]     Lambda, B (later Lambda'), Omega
+    // Berlekamp-Massey state by POSITION (group-interleaved), ping-pong: [0] current, [1] destination of the next permute
+    uint4 *synG[2], *lamG[2], *bpG[2];   // [W/32][ld][2][32]
+    uint4 *bdisP[2];                     // [W/32][1][2][32]
+    int4 *stateP[2];                     // [W] (L, lenB, shift, dead)
+    unsigned int *originP[2];            // [W] slot of the item at this position
+    unsigned char *keyP;                 // [W] sort key of the position: L, 255 = dead
+    // per SLOT (item-major): inputs / outputs of the Chien / Forney transforms
+    uint4 *lam, *bp, *om;       // [W][tp]     Lambda, Lambda', Omega (zero padded)
     uint4 *num, *den;           // [W][tp]     Omega / Lambda' at the roots (later: canonical error values in num)
-    uint4 *bdis;                // [W]         discrepancy at the last length change
-    int4 *state;                // [W]         (L, lenB, shift, dead)
+    int4 *state;                // [W]         final (L, -, -, dead)
     unsigned int *rootmask;     // [W][8]
-    unsigned char *key;         // [W]         sort key: L, 255 = dead
-    const unsigned int *perm;   // [W]         slots in sorted order (nullptr: identity)
+    unsigned char *key;         // [W]         final sort key
+    const unsigned int *perm;   // [W]         permute: old position of new position q; finish: slots in sorted order
     unsigned int W;
     int syn_ld, tp, nsyn, maxL, j0, j1;
     // finish
@@ -635,6 +648,10 @@ struct StagedArgs {
     const int *pos_of_dom;      // [N] sorted position of the share with domain index k (-1: not supplied)
     const uint4 *uinv0;         // [S] attempt-0 uinv
     unsigned int *list2, *count2;  // items left to the exact path
+    uint4 *runs;                // [W] by sorted index: product of the slot's Forney denominators, then its inverse
+    unsigned char *okf;         // [W] by sorted index: the fast attempt has produced a consistent locator
+    int direct;                 // the items come straight from the all-points NTT check (no dense check has looked at the examined
+                                // prefix): no error inside the prefix means the reference's optimistic attempt succeeds (path 0)
 };
 
 __device__ __forceinline__ void ld_fr2(uint32_t (&a)[8], const uint4 *p) { load_fr(a, p[0], p[1]); }
@@ -642,27 +659,36 @@ __device__ __forceinline__ void st_fr2(uint4 *p, const uint32_t (&a)[8]) {
     p[0] = make_uint4(a[0], a[1], a[2], a[3]);
     p[1] = make_uint4(a[4], a[5], a[6], a[7]);
 }
+// element e of the thread's position in a group-interleaved array with `ld` elements per position
+struct GView {
+    uint4 *base;  // array + (group*ld*2)*32 + lane
+    __device__ __forceinline__ GView(uint4 *arr, unsigned int pos, int ld) : base(arr + ((size_t)(pos >> 5) * ld * 2) * 32 + (pos & 31)) {}
+    __device__ __forceinline__ void ld(uint32_t (&a)[8], int e) const { load_fr(a, base[(size_t)e * 64], base[(size_t)e * 64 + 32]); }
+    __device__ __forceinline__ void st(int e, const uint32_t (&a)[8]) const {
+        base[(size_t)e * 64] = make_uint4(a[0], a[1], a[2], a[3]);
+        base[(size_t)e * 64 + 32] = make_uint4(a[4], a[5], a[6], a[7]);
+    }
+};
 
-// Berlekamp-Massey iterations j0 <= j < j1 of every live slot (same recurrences as rs_attempt)
+// Berlekamp-Massey iterations j0 <= j < j1 of every live position (same recurrences as rs_attempt)
 __global__ void __launch_bounds__(128, 4) bm_segment_kernel(const StagedArgs a) {
-    const unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.W) return;
-    const unsigned int slot = a.perm ? a.perm[idx] : idx;
-    uint4 *lam = a.lam + (size_t)slot * a.tp * 2, *bp = a.bp + (size_t)slot * a.tp * 2;
-    const uint4 *syn = a.syn + (size_t)slot * a.syn_ld * 2;
+    const unsigned int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= a.W) return;
+    const GView lam(a.lamG[0], pos, a.tp), bp(a.bpG[0], pos, a.tp), syn(a.synG[0], pos, a.syn_ld), bd(a.bdisP[0], pos, 1);
     uint32_t one[8], bdis[8];
     one_mont_limbs(one);
     int L, lenB, shift;
     if (a.j0 == 0) {
         copy8(bdis, one);
-        st_fr2(lam, one);
-        st_fr2(bp, one);
+        lam.st(0, one);
+        bp.st(0, one);
         L = 0; lenB = 1; shift = 1;
+        a.originP[0][pos] = pos;
     } else {
-        const int4 st = a.state[slot];
+        const int4 st = a.stateP[0][pos];
         if (st.w) return;  // dead: the fast attempt cannot succeed
         L = st.x; lenB = st.y; shift = st.z;
-        ld_fr2(bdis, a.bdis + (size_t)slot * 2);
+        bd.ld(bdis, 0);
     }
     bool dead = false;
 #pragma unroll 1
@@ -673,14 +699,14 @@ __global__ void __launch_bounds__(128, 4) bm_segment_kernel(const StagedArgs a) 
             acc_zero(A);
             const int lim = L < j ? L : j;
             uint32_t x[8], sy[8];
-            ld_fr2(x, lam);
-            ld_fr2(sy, syn + (size_t)j * 2);
+            lam.ld(x, 0);
+            syn.ld(sy, j);
 #pragma unroll 1
             for (int l = 0; l <= lim; ++l) {
                 uint32_t xn[8], sn[8];
                 const int ln = l < lim ? l + 1 : l;  // software pipelining: the next operands are in flight during the product
-                ld_fr2(xn, lam + (size_t)ln * 2);
-                ld_fr2(sn, syn + (size_t)(j - ln) * 2);
+                lam.ld(xn, ln);
+                syn.ld(sn, j - ln);
                 acc_mac(A, x, sy);
                 copy8(x, xn);
                 copy8(sy, sn);
@@ -696,17 +722,17 @@ __global__ void __launch_bounds__(128, 4) bm_segment_kernel(const StagedArgs a) 
 #pragma unroll 1
         for (int l = newL; l >= 0; --l) {
             uint32_t lm[8], bl[8], res[8];
-            if (l <= L) ld_fr2(lm, lam + (size_t)l * 2); else set_zero(lm);
+            if (l <= L) lam.ld(lm, l); else set_zero(lm);
             const int bi = l - shift;
             const bool hasb = bi >= 0 && bi < lenB;
-            if (hasb) ld_fr2(bl, bp + (size_t)bi * 2); else set_zero(bl);
+            if (hasb) bp.ld(bl, bi); else set_zero(bl);
             acc_t A;
             acc_zero(A);
             acc_mac(A, lm, bdis);
             if (hasb) acc_mac(A, bl, nd);
             acc_reduce(A, res);
-            st_fr2(lam + (size_t)l * 2, res);
-            if (grow && l <= L) st_fr2(bp + (size_t)l * 2, lm);
+            lam.st(l, res);
+            if (grow && l <= L) bp.st(l, lm);
         }
         if (grow) {
             lenB = L + 1;
@@ -717,9 +743,38 @@ __global__ void __launch_bounds__(128, 4) bm_segment_kernel(const StagedArgs a) 
             ++shift;
         }
     }
-    a.state[slot] = make_int4(L, lenB, shift, dead ? 1 : 0);
-    st_fr2(a.bdis + (size_t)slot * 2, bdis);
-    a.key[slot] = dead ? (unsigned char)255 : (unsigned char)L;
+    a.stateP[0][pos] = make_int4(L, lenB, shift, dead ? 1 : 0);
+    bd.st(0, bdis);
+    a.keyP[pos] = dead ? (unsigned char)255 : (unsigned char)L;
+}
+
+// moves the live state of old position perm[q] to new position q (buffers [0] -> [1]); the host swaps the buffers afterwards
+__global__ void __launch_bounds__(256) permute_kernel(const StagedArgs a) {
+    const unsigned int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.W) return;
+    const unsigned int src = a.perm[q];
+    const int4 st = a.stateP[0][src];
+    a.stateP[1][q] = st;
+    a.originP[1][q] = a.originP[0][src];
+    if (st.w) return;
+    uint32_t v[8];
+    {
+        const GView s0(a.bdisP[0], src, 1), d0(a.bdisP[1], q, 1);
+        s0.ld(v, 0);
+        d0.st(0, v);
+    }
+    {
+        const GView s0(a.lamG[0], src, a.tp), d0(a.lamG[1], q, a.tp);
+        for (int e = 0; e <= st.x; ++e) { s0.ld(v, e); d0.st(e, v); }
+    }
+    {
+        const GView s0(a.bpG[0], src, a.tp), d0(a.bpG[1], q, a.tp);
+        for (int e = 0; e < st.y; ++e) { s0.ld(v, e); d0.st(e, v); }
+    }
+    {
+        const GView s0(a.synG[0], src, a.syn_ld), d0(a.synG[1], q, a.syn_ld);
+        for (int e = 0; e < a.nsyn; ++e) { s0.ld(v, e); d0.st(e, v); }
+    }
 }
 
 // counting sort of the slots by key (any order inside a bin): hist -> exclusive scan -> scatter
@@ -756,16 +811,19 @@ __global__ void sort_scatter_kernel(const unsigned char *key, unsigned int W, un
     }
 }
 
-// Omega = S*Lambda mod z^L, Lambda' coefficients l*Lambda_l (into the dead B polynomial), zero padding for the transforms
+// Omega = S*Lambda mod z^L and the Lambda' coefficients l*Lambda_l, read by position, written per slot (item-major, zero
+// padded) for the Chien / Forney transforms together with the slot's final state and sort key
 __global__ void __launch_bounds__(128, 4) omega_kernel(const StagedArgs a) {
-    const unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.W) return;
-    const unsigned int slot = a.perm ? a.perm[idx] : idx;
-    const int4 st = a.state[slot];
+    const unsigned int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= a.W) return;
+    const unsigned int slot = a.originP[0][pos];
+    const int4 st = a.stateP[0][pos];
+    a.state[slot] = st;
+    a.key[slot] = st.w ? (unsigned char)255 : (unsigned char)st.x;
     if (st.w) return;
     const int L = st.x;
+    const GView lamg(a.lamG[0], pos, a.tp), syn(a.synG[0], pos, a.syn_ld);
     uint4 *lam = a.lam + (size_t)slot * a.tp * 2, *bp = a.bp + (size_t)slot * a.tp * 2, *om = a.om + (size_t)slot * a.tp * 2;
-    const uint4 *syn = a.syn + (size_t)slot * a.syn_ld * 2;
     uint32_t zero[8], one[8], lmul[8];
     set_zero(zero);
     one_mont_limbs(one);
@@ -777,18 +835,24 @@ __global__ void __launch_bounds__(128, 4) omega_kernel(const StagedArgs a) {
 #pragma unroll 1
         for (int k = 0; k <= l; ++k) {
             uint32_t x[8], sy[8];
-            ld_fr2(x, lam + (size_t)k * 2);
-            ld_fr2(sy, syn + (size_t)(l - k) * 2);
+            lamg.ld(x, k);
+            syn.ld(sy, l - k);
             acc_mac(A, x, sy);
         }
         uint32_t o[8];
         acc_reduce(A, o);
         st_fr2(om + (size_t)l * 2, o);
     }
+    {
+        uint32_t c[8];
+        lamg.ld(c, 0);
+        st_fr2(lam, c);
+    }
 #pragma unroll 1
     for (int l = 1; l <= L; ++l) {
         uint32_t c[8], lc[8], nl[8];
-        ld_fr2(c, lam + (size_t)l * 2);
+        lamg.ld(c, l);
+        st_fr2(lam + (size_t)l * 2, c);
         mont_mul(lc, c, lmul);
         st_fr2(bp + (size_t)(l - 1) * 2, lc);
         fr_add(nl, lmul, one);
@@ -798,37 +862,42 @@ __global__ void __launch_bounds__(128, 4) omega_kernel(const StagedArgs a) {
     for (int l = L + 1; l < a.tp; ++l) st_fr2(lam + (size_t)l * 2, zero);
 }
 
-__global__ void __launch_bounds__(128, 4) staged_finish_kernel(const RobustArgs a, const StagedArgs s) {
+// error positions of a slot from its root mask; returns the number of roots (rootpos filled up to L entries)
+__device__ __forceinline__ int staged_roots(const StagedArgs &s, unsigned int slot, int N, int L, int *rootpos) {
+    const unsigned int *mk = s.rootmask + (size_t)slot * 8;
+    int nroots = 0;
+    for (int w = 0; w < (N + 31) / 32; ++w) {
+        unsigned int bits = mk[w];
+        while (bits) {
+            const int k = w * 32 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (nroots < L) rootpos[nroots] = s.pos_of_dom[k];
+            ++nroots;
+        }
+    }
+    return nroots;
+}
+
+// 6a. per slot (sorted order idx): prefix products of the Forney denominators Lambda'(x_q^-1) into `om`, their product into
+// runs[idx] (1 for slots whose fast attempt has failed, so that the batched inversion is not poisoned), verdict into okf[idx]
+__global__ void __launch_bounds__(128, 4) staged_prefix_kernel(const RobustArgs a, const StagedArgs s) {
     const unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= s.W) return;
     const unsigned int slot = s.perm ? s.perm[idx] : idx;
-    const unsigned int item = a.list[s.list_first + slot];
-    const long long b = (long long)item;
     const int4 st = s.state[slot];
     const int L = st.x;
-    int rootpos[HB_ROBUST_MAXT];
-    bool ok = !st.w && L <= s.maxL;
+    bool ok = !st.w && L <= s.maxL && !(s.direct && L == 0);
     if (ok) {
         const unsigned int *mk = s.rootmask + (size_t)slot * 8;
         int nroots = 0;
-        const int N = 1 << a.logn;
-        for (int w = 0; w < (N + 31) / 32; ++w) {
-            unsigned int bits = mk[w];
-            while (bits) {
-                const int k = w * 32 + __ffs(bits) - 1;
-                bits &= bits - 1;
-                if (nroots < L) rootpos[nroots] = s.pos_of_dom[k];
-                ++nroots;
-            }
-        }
+        for (int w = 0; w < 8; ++w) nroots += __popc(mk[w]);
         ok = nroots == L;
     }
-    uint4 *num = s.num + (size_t)slot * s.tp * 2, *den = s.den + (size_t)slot * s.tp * 2;
     uint32_t one[8], run[8];
     one_mont_limbs(one);
     copy8(run, one);
-    if (ok && L > 0) {
-        // c_q = -x_q Omega(x_q^-1) / Lambda'(x_q^-1): one inversion for all of them (prefix products kept in `den`'s partner `om`)
+    if (ok) {
+        const uint4 *den = s.den + (size_t)slot * s.tp * 2;
         uint4 *pre = s.om + (size_t)slot * s.tp * 2;
 #pragma unroll 1
         for (int q = 0; q < L; ++q) {
@@ -839,34 +908,86 @@ __global__ void __launch_bounds__(128, 4) staged_finish_kernel(const RobustArgs 
             mont_mul(nr, run, dv);
             copy8(run, nr);
         }
-        if (ok) {
-            uint32_t inv[8];
-            fr_inv_mont(inv, run);
-#pragma unroll 1
-            for (int q = L - 1; q >= 0; --q) {
-                uint32_t pr[8], dv[8], dinv[8], nv[8], xq[8], numv[8], c[8], nc[8], u[8], e[8], ninv[8];
-                ld_fr2(pr, pre + (size_t)q * 2);
-                ld_fr2(dv, den + (size_t)q * 2);
-                ld_fr2(nv, num + (size_t)q * 2);
-                ldg_fr(xq, a.xs + rootpos[q] * 2);
-                mont_mul(numv, nv, xq);
-                mont_mul(dinv, inv, pr);
-                mont_mul(ninv, inv, dv);
-                copy8(inv, ninv);
-                mont_mul(c, numv, dinv);
-                fr_neg(nc, c);
-                ldg_fr(u, s.uinv0 + rootpos[q] * 2);
-                mont_mul(e, nc, u);  // Montgomery c times canonical uinv -> canonical error value
-                st_fr2(num + (size_t)q * 2, e);
-            }
+    }
+    if (!ok) copy8(run, one);
+    st_fr2(s.runs + (size_t)idx * 2, run);
+    s.okf[idx] = ok ? 1 : 0;
+}
+
+// 6b. runs[idx] <- runs[idx]^-1, HB_INV_BATCH consecutive values per thread with one Fermat inversion (Montgomery's trick)
+#define HB_INV_BATCH 8
+__global__ void __launch_bounds__(128) staged_invert_kernel(const StagedArgs s) {
+    const unsigned int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * HB_INV_BATCH;
+    if (i0 >= s.W) return;
+    const int cnt = (int)min((unsigned int)HB_INV_BATCH, s.W - i0);
+    uint32_t pre[HB_INV_BATCH][8], run[8], inv[8];
+    one_mont_limbs(run);
+#pragma unroll
+    for (int k = 0; k < HB_INV_BATCH; ++k) {
+        copy8(pre[k], run);
+        if (k < cnt) {
+            uint32_t v[8], nr[8];
+            ld_fr2(v, s.runs + (size_t)(i0 + k) * 2);
+            mont_mul(nr, run, v);
+            copy8(run, nr);
         }
     }
-    if (!ok) {  // the fast attempt failed: this item takes the exact path
+    fr_inv_mont(inv, run);
+#pragma unroll
+    for (int k = HB_INV_BATCH - 1; k >= 0; --k) {
+        if (k < cnt) {
+            uint32_t v[8], iv[8], ninv[8];
+            ld_fr2(v, s.runs + (size_t)(i0 + k) * 2);
+            mont_mul(iv, inv, pre[k]);
+            mont_mul(ninv, inv, v);
+            copy8(inv, ninv);
+            st_fr2(s.runs + (size_t)(i0 + k) * 2, iv);
+        }
+    }
+}
+
+// 6c. error values, path rule, outputs
+__global__ void __launch_bounds__(128, 4) staged_finish_kernel(const RobustArgs a, const StagedArgs s) {
+    const unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.W) return;
+    const unsigned int slot = s.perm ? s.perm[idx] : idx;
+    const unsigned int item = a.list[s.list_first + slot];
+    const long long b = (long long)item;
+    const int L = s.state[slot].x;
+    if (!s.okf[idx]) {  // the fast attempt failed: this item takes the exact path
         s.list2[atomicAdd(s.count2, 1u)] = item;
+        if (s.direct) for (int w = 0; w < 8; ++w) s.rootmask[(size_t)slot * 8 + w] = 0u;
         return;
     }
+    int rootpos[HB_ROBUST_MAXT];
+    staged_roots(s, slot, 1 << a.logn, L, rootpos);
+    uint4 *num = s.num + (size_t)slot * s.tp * 2;
+    if (L > 0) {
+        // c_q = -x_q Omega(x_q^-1) / Lambda'(x_q^-1), e_q = c_q * uinv_q
+        const uint4 *den = s.den + (size_t)slot * s.tp * 2, *pre = s.om + (size_t)slot * s.tp * 2;
+        uint32_t inv[8];
+        ld_fr2(inv, s.runs + (size_t)idx * 2);
+#pragma unroll 1
+        for (int q = L - 1; q >= 0; --q) {
+            uint32_t pr[8], dv[8], dinv[8], nv[8], xq[8], numv[8], c[8], nc[8], u[8], e[8], ninv[8];
+            ld_fr2(pr, pre + (size_t)q * 2);
+            ld_fr2(dv, den + (size_t)q * 2);
+            ld_fr2(nv, num + (size_t)q * 2);
+            ldg_fr(xq, a.xs + rootpos[q] * 2);
+            mont_mul(numv, nv, xq);
+            mont_mul(dinv, inv, pr);
+            mont_mul(ninv, inv, dv);
+            copy8(inv, ninv);
+            mont_mul(c, numv, dinv);
+            fr_neg(nc, c);
+            ldg_fr(u, s.uinv0 + rootpos[q] * 2);
+            mont_mul(e, nc, u);  // Montgomery c times canonical uinv -> canonical error value
+            st_fr2(num + (size_t)q * 2, e);
+        }
+    }
     int path = -8;
-    {
+    if (s.direct && rootpos[0] >= a.needed) path = 0;
+    else {
         int q = 0;
         for (int r = 1; r <= a.rmax; ++r) {
             while (q < L && rootpos[q] < a.needed + r) ++q;
@@ -874,6 +995,7 @@ __global__ void __launch_bounds__(128, 4) staged_finish_kernel(const RobustArgs 
         }
     }
     robust_store_item(a, b, L, rootpos, path, a.S, [&](uint32_t (&e)[8], int q) { ld_fr2(e, num + (size_t)q * 2); });
+    if (s.direct && path < 0) for (int w = 0; w < 8; ++w) s.rootmask[(size_t)slot * 8 + w] = 0u;  // zeroed outputs stay zero
 }
 
 // items with fail[b] != 0 -> list (any order)
