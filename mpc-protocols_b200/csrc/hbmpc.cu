@@ -929,8 +929,22 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
 // direct != nullptr: the items come straight from the all-points NTT check (S == n == N); paths include 0, the coefficients
 // (INTT of the received word, left in `coeffs` by that check) are corrected by one sparse inverse transform per item, and the
 // leftovers are returned in direct[0] (list) / direct[1] (count) for the caller's dense check instead of being decoded here.
+// bytes of wave workspace per slot / slots per wave
+static size_t staged_slot_bytes(const RecoverTables &T, int t) {
+    const size_t tp = (size_t)t + 2, syn_ld = (size_t)std::max(T.nsyn0, 1);
+    return (2 * (syn_ld + 2 * tp + 1) + 5 * tp + 1) * 32 + 2 * 16 + 2 * 4 + 1 + 16 + 32 + 1 + 4 + 1;
+}
+static size_t staged_wave_slots(const hbmpc_ctx *ctx, const RecoverTables &T, int t) {
+    size_t budget = (size_t)3072 << 20;
+    if (const char *wm = getenv("HBMPC_STAGED_WS_MB")) if (atoll(wm) > 0) budget = (size_t)atoll(wm) << 20;
+    (void)ctx;
+    return std::max<size_t>(budget / staged_slot_bytes(T, t), 1024) & ~(size_t)1023;
+}
+// list2_cap: capacity of the leftover list (0: the number of items of this call); append: keep the leftovers collected by an
+// earlier call of the same capacity; hist_slots: r.hist samples the first hist_slots slots of every wave.
 static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const RobustArgs &r_in, const int *in_map, unsigned int first,
-                         unsigned int cnt, long long fb_blocks, int fb_threads, unsigned int **direct = nullptr) {
+                         unsigned int cnt, long long fb_blocks, int fb_threads, unsigned int **direct = nullptr, unsigned int list2_cap = 0,
+                         bool append = false, unsigned int hist_slots = 0) {
     if (cnt <= first) return 0;
     RobustArgs r = r_in;
     r.skip_coeffs = direct ? 1 : 0;
@@ -939,10 +953,8 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
     const int tp = r.t + 2, syn_ld = std::max(T.nsyn0, 1), seg = ctx->staged_seg;
     const int nseg = (T.nsyn0 + seg - 1) / seg;
     const size_t total = cnt - first;
-    const size_t per_slot = (2 * ((size_t)syn_ld + 2 * (size_t)tp + 1) + 5 * (size_t)tp + 1) * 32 + 2 * 16 + 2 * 4 + 1 + 16 + 32 + 1 + 4 + 1;
-    size_t budget = (size_t)3072 << 20;
-    if (const char *wm = getenv("HBMPC_STAGED_WS_MB")) if (atoll(wm) > 0) budget = (size_t)atoll(wm) << 20;
-    size_t Wmax = std::max<size_t>(budget / per_slot, 1024) & ~(size_t)1023;
+    if (list2_cap < total) list2_cap = (unsigned int)total;
+    size_t Wmax = staged_wave_slots(ctx, T, r.t);
     if (Wmax > total) Wmax = total;
     const size_t Wg = (Wmax + 31) / 32 * 32;  // group-interleaved arrays hold whole groups of 32 positions
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -966,11 +978,11 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
     int rc;
     if ((rc = scratch_get(ctx, ln, 10, off, &wsp))) return rc;
     const size_t hist_bytes = (size_t)(nseg + 1) * 256 * 4;
-    if ((rc = scratch_get(ctx, ln, 11, al(hist_bytes) + total * 4 + 256, &aux))) return rc;
+    if ((rc = scratch_get(ctx, ln, 11, al(hist_bytes) + (size_t)list2_cap * 4 + 256, &aux))) return rc;
     unsigned int *hist = (unsigned int *)aux;
     unsigned int *count2 = (unsigned int *)((char *)aux + al(hist_bytes));
     unsigned int *list2 = count2 + 4;
-    CK(cudaMemsetAsync(count2, 0, 16, st));
+    if (!append) CK(cudaMemsetAsync(count2, 0, 16, st));
     char *w8 = (char *)wsp;
     StagedArgs sa{};
     sa.lam = (uint4 *)(w8 + o_lam); sa.bp = (uint4 *)(w8 + o_bp); sa.om = (uint4 *)(w8 + o_om);
@@ -982,7 +994,18 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
     sa.uinv0 = T.uinv + T.uoff0 * 2;
     sa.list2 = list2; sa.count2 = count2;
     sa.direct = direct ? 1 : 0;
+    sa.hist_slots = r.hist ? (hist_slots ? hist_slots : 0xffffffffu) : 0u;
     sa.runs = (uint4 *)(w8 + o_runs); sa.okf = (unsigned char *)(w8 + o_okf);
+    // resident CTAs of the Berlekamp-Massey kernel are capped through its dynamic shared memory size: the live state of the
+    // resident positions should stay inside the L2 (HBMPC_BM_CTAS per SM, default 5 = the register limit)
+    size_t bm_smem = 0;
+    if (const char *bc = getenv("HBMPC_BM_CTAS")) {
+        const int c = atoi(bc);
+        if (c >= 1 && c < HB_BM_MINB) {
+            bm_smem = (size_t)(220 * 1024 / c - 2048) & ~(size_t)1023;
+            CK(cudaFuncSetAttribute(bm_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
+        }
+    }
     const bool prof = getenv("HBMPC_STAGED_PROF") != nullptr;
     cudaEvent_t pe[8] = {};
     float pms[7] = {};
@@ -1026,7 +1049,7 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
         for (int k = 0; k < nseg; ++k) {
             sa.j0 = k * seg;
             sa.j1 = std::min(T.nsyn0, sa.j0 + seg);
-            bm_segment_kernel<<<gb, 128, 0, st>>>(sa);
+            bm_segment_kernel<<<gb, 128, bm_smem, st>>>(sa);
             ctx->launches++;
             CK(cudaGetLastError());
             if (k + 1 < nseg) {
@@ -1296,36 +1319,38 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             CK(cudaMemcpyAsync(ctx->h_spec, count1, sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
             CK(cudaStreamSynchronize(ln.stream));
             const unsigned int c1 = ctx->h_spec[0];
-            bool persistent = false;
-            if (c1 >= ctx->staged_min && !ctx->no_staged_direct && !ctx->no_speculation && c1 >= 1024) {
-                // a few scouts first: when the same <= t senders are wrong in most of them, the persistent-attacker shortcut
-                // further down (dense interpolation from the senders believed honest) beats decoding every item
-                const unsigned int SC = 64;
-                void *histbuf = nullptr;
-                if ((rc = scratch_get(ctx, ln, 9, 4096, &histbuf))) return rc;
-                unsigned int *hist = (unsigned int *)histbuf;
-                CK(cudaMemsetAsync(hist, 0, S * sizeof(unsigned int), ln.stream));
-                RobustArgs rs = r;
-                rs.list = list1; rs.count = count1;
-                rs.hist = hist; rs.hist_only = 1;
-                unsigned int *unused[2] = {nullptr, nullptr};
-                if ((rc = staged_decode(ctx, ln, T, rs, P.in_map, 0, SC, blocks, threads, unused))) return rc;
-                CK(cudaMemcpyAsync(ctx->h_spec + 8, hist, S * sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
-                CK(cudaStreamSynchronize(ln.stream));
-                size_t nsus = 0;
-                for (size_t j = 0; j < S; ++j)
-                    if (ctx->h_spec[8 + j] >= SC / 2) ++nsus;
-                persistent = nsus >= 1 && nsus <= t && S - nsus >= m;
-            }
-            if (c1 >= ctx->staged_min && !ctx->no_staged_direct && !persistent) {
+            if (c1 >= ctx->staged_min && !ctx->no_staged_direct) {
+                // More than one wave of work: a few scouts first (hist_only: nothing is written).  When the same <= t senders
+                // are wrong in (almost) every scout, the persistent-attacker shortcut further down (dense interpolation from the
+                // senders believed honest) beats decoding every item.  Smaller failing sets are decoded without asking.
+                const unsigned int W1 = (unsigned int)staged_wave_slots(ctx, T, (int)t), SC = 64;
                 RobustArgs rd = r;
                 rd.list = list1;
                 rd.count = count1;
                 unsigned int *left[2] = {nullptr, nullptr};
-                if ((rc = staged_decode(ctx, ln, T, rd, P.in_map, 0, c1, blocks, threads, left))) return rc;
-                dense_list = left[0];
-                dense_count = left[1];
-                staged_direct = true;
+                bool persistent = false;
+                if (!ctx->no_speculation && c1 > W1) {
+                    void *histbuf = nullptr;
+                    if ((rc = scratch_get(ctx, ln, 9, 4096, &histbuf))) return rc;
+                    unsigned int *hist = (unsigned int *)histbuf;
+                    CK(cudaMemsetAsync(hist, 0, S * sizeof(unsigned int), ln.stream));
+                    RobustArgs rs = rd;
+                    rs.hist = hist;
+                    rs.hist_only = 1;
+                    if ((rc = staged_decode(ctx, ln, T, rs, P.in_map, 0, SC, blocks, threads, left, c1))) return rc;
+                    CK(cudaMemcpyAsync(ctx->h_spec + 8, hist, S * sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
+                    CK(cudaStreamSynchronize(ln.stream));
+                    size_t nsus = 0;
+                    for (size_t j = 0; j < S; ++j)
+                        if (ctx->h_spec[8 + j] >= SC * 3 / 4) ++nsus;  // persistent attackers are wrong (almost) every time
+                    persistent = nsus >= 1 && nsus <= t && S - nsus >= m;
+                }
+                if (!persistent) {
+                    if ((rc = staged_decode(ctx, ln, T, rd, P.in_map, 0, c1, blocks, threads, left))) return rc;
+                    staged_direct = true;
+                    dense_list = left[0];
+                    dense_count = left[1];
+                }  // else: every failing item takes the dense check and the shortcut
             }
         }
 

@@ -434,7 +434,8 @@ __device__ __noinline__ int rs_attempt(const RobustArgs &a, int att, long long b
 // linearity, the flag bits (error positions + shares beyond the examined prefix that disagree with the decoded polynomial),
 // the scout histogram and the path.  rootpos[0..L) = sorted positions of the errors, load_ev(e, q) = canonical error value q.
 template <typename EvLoad>
-__device__ __forceinline__ void robust_store_item(const RobustArgs &a, long long b, int L, const int *rootpos, int path, int Pused, EvLoad load_ev) {
+__device__ __forceinline__ void robust_store_item(const RobustArgs &a, long long b, int L, const int *rootpos, int path, int Pused, EvLoad load_ev,
+                                                  bool do_hist = true) {
     if (a.hist_only) {
         if (path >= 0)
             for (int q = 0; q < L; ++q) atomicAdd(&a.hist[a.order[rootpos[q]]], 1u);
@@ -512,7 +513,7 @@ __device__ __forceinline__ void robust_store_item(const RobustArgs &a, long long
             if (!fr_eq(fv, y)) fl[j >> 6] |= 1ull << (j & 63);
         }
     }
-    if (a.hist)
+    if (a.hist && do_hist)
         for (int q = 0; q < L; ++q) atomicAdd(&a.hist[a.order[rootpos[q]]], 1u);
     if (a.clear_fail) a.clear_fail[b] = 0;
     a.path[b] = path;
@@ -633,7 +634,7 @@ struct StagedArgs {
     uint4 *bdisP[2];                     // [W/32][1][2][32]
     int4 *stateP[2];                     // [W] (L, lenB, shift, dead)
     unsigned int *originP[2];            // [W] slot of the item at this position
-    unsigned char *keyP;                 // [W] sort key of the position: L, 255 = dead
+    unsigned char *keyP;                 // [W] sort key of the position: maxL - L (descending L), 255 = dead
     // per SLOT (item-major): inputs / outputs of the Chien / Forney transforms
     uint4 *lam, *bp, *om;       // [W][tp]     Lambda, Lambda', Omega (zero padded)
     uint4 *num, *den;           // [W][tp]     Omega / Lambda' at the roots (later: canonical error values in num)
@@ -648,6 +649,7 @@ struct StagedArgs {
     const int *pos_of_dom;      // [N] sorted position of the share with domain index k (-1: not supplied)
     const uint4 *uinv0;         // [S] attempt-0 uinv
     unsigned int *list2, *count2;  // items left to the exact path
+    unsigned int hist_slots;    // the per-sender error histogram (RobustArgs::hist) samples the slots below this number
     uint4 *runs;                // [W] by sorted index: product of the slot's Forney denominators, then its inverse
     unsigned char *okf;         // [W] by sorted index: the fast attempt has produced a consistent locator
     int direct;                 // the items come straight from the all-points NTT check (no dense check has looked at the examined
@@ -671,7 +673,10 @@ struct GView {
 };
 
 // Berlekamp-Massey iterations j0 <= j < j1 of every live position (same recurrences as rs_attempt)
-__global__ void __launch_bounds__(128, 4) bm_segment_kernel(const StagedArgs a) {
+#ifndef HB_BM_MINB
+#define HB_BM_MINB 5
+#endif
+__global__ void __launch_bounds__(128, HB_BM_MINB) bm_segment_kernel(const StagedArgs a) {
     const unsigned int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= a.W) return;
     const GView lam(a.lamG[0], pos, a.tp), bp(a.bpG[0], pos, a.tp), syn(a.synG[0], pos, a.syn_ld), bd(a.bdisP[0], pos, 1);
@@ -698,18 +703,19 @@ __global__ void __launch_bounds__(128, 4) bm_segment_kernel(const StagedArgs a) 
             acc_t A;
             acc_zero(A);
             const int lim = L < j ? L : j;
-            uint32_t x[8], sy[8];
-            lam.ld(x, 0);
-            syn.ld(sy, j);
+            // software pipelining with two operand sets (no register moves): the next operands are in flight during a product
+            uint32_t x0[8], s0[8], x1[8], s1[8];
+            lam.ld(x0, 0);
+            syn.ld(s0, j);
 #pragma unroll 1
-            for (int l = 0; l <= lim; ++l) {
-                uint32_t xn[8], sn[8];
-                const int ln = l < lim ? l + 1 : l;  // software pipelining: the next operands are in flight during the product
-                lam.ld(xn, ln);
-                syn.ld(sn, j - ln);
-                acc_mac(A, x, sy);
-                copy8(x, xn);
-                copy8(sy, sn);
+            for (int l = 0; l <= lim; l += 2) {
+                const int l1 = l + 1 <= lim ? l + 1 : lim, l2 = l + 2 <= lim ? l + 2 : lim;
+                lam.ld(x1, l1);
+                syn.ld(s1, j - l1);
+                acc_mac(A, x0, s0);
+                lam.ld(x0, l2);
+                syn.ld(s0, j - l2);
+                if (l + 1 <= lim) acc_mac(A, x1, s1);
             }
             acc_reduce(A, delta);
         }
@@ -719,18 +725,29 @@ __global__ void __launch_bounds__(128, 4) bm_segment_kernel(const StagedArgs a) 
         const bool grow = 2 * L <= j;
         const int newL = grow ? j + 1 - L : L;
         if (newL > a.maxL) { dead = true; break; }
+        uint32_t lmn[8], bln[8];  // operands of the next coefficient, loaded one step ahead
+        if (newL <= L) lam.ld(lmn, newL); else set_zero(lmn);
+        if (newL - shift >= 0 && newL - shift < lenB) bp.ld(bln, newL - shift); else set_zero(bln);
 #pragma unroll 1
         for (int l = newL; l >= 0; --l) {
             uint32_t lm[8], bl[8], res[8];
-            if (l <= L) lam.ld(lm, l); else set_zero(lm);
+            copy8(lm, lmn);
+            copy8(bl, bln);
             const int bi = l - shift;
             const bool hasb = bi >= 0 && bi < lenB;
-            if (hasb) bp.ld(bl, bi); else set_zero(bl);
-            acc_t A;
-            acc_zero(A);
-            acc_mac(A, lm, bdis);
-            if (hasb) acc_mac(A, bl, nd);
-            acc_reduce(A, res);
+            if (l >= 1) {
+                if (l - 1 <= L) lam.ld(lmn, l - 1); else set_zero(lmn);
+                if (bi - 1 >= 0 && bi - 1 < lenB) bp.ld(bln, bi - 1); else set_zero(bln);
+            }
+            // two interleaved-row products and a modular addition: fewer multiply-pipe instructions than two lazy products
+            // followed by a reduction of the 512-bit sum
+            mont_mul(res, lm, bdis);
+            if (hasb) {
+                uint32_t p2[8], sm[8];
+                mont_mul(p2, bl, nd);
+                fr_add(sm, res, p2);
+                copy8(res, sm);
+            }
             lam.st(l, res);
             if (grow && l <= L) bp.st(l, lm);
         }
@@ -745,7 +762,7 @@ __global__ void __launch_bounds__(128, 4) bm_segment_kernel(const StagedArgs a) 
     }
     a.stateP[0][pos] = make_int4(L, lenB, shift, dead ? 1 : 0);
     bd.st(0, bdis);
-    a.keyP[pos] = dead ? (unsigned char)255 : (unsigned char)L;
+    a.keyP[pos] = dead ? (unsigned char)255 : (unsigned char)(a.maxL - L);  // longest locators first: their CTAs must not start last
 }
 
 // moves the live state of old position perm[q] to new position q (buffers [0] -> [1]); the host swaps the buffers afterwards
@@ -819,7 +836,7 @@ __global__ void __launch_bounds__(128, 4) omega_kernel(const StagedArgs a) {
     const unsigned int slot = a.originP[0][pos];
     const int4 st = a.stateP[0][pos];
     a.state[slot] = st;
-    a.key[slot] = st.w ? (unsigned char)255 : (unsigned char)st.x;
+    a.key[slot] = st.w ? (unsigned char)255 : (unsigned char)(a.maxL - st.x);
     if (st.w) return;
     const int L = st.x;
     const GView lamg(a.lamG[0], pos, a.tp), syn(a.synG[0], pos, a.syn_ld);
@@ -994,7 +1011,7 @@ __global__ void __launch_bounds__(128, 4) staged_finish_kernel(const RobustArgs 
             if (q <= r) { path = r; break; }
         }
     }
-    robust_store_item(a, b, L, rootpos, path, a.S, [&](uint32_t (&e)[8], int q) { ld_fr2(e, num + (size_t)q * 2); });
+    robust_store_item(a, b, L, rootpos, path, a.S, [&](uint32_t (&e)[8], int q) { ld_fr2(e, num + (size_t)q * 2); }, slot < s.hist_slots);
     if (s.direct && path < 0) for (int w = 0; w < 8; ++w) s.rootmask[(size_t)slot * 8 + w] = 0u;  // zeroed outputs stay zero
 }
 

@@ -164,6 +164,7 @@ def test_staged_equals_per_thread_decoder_large(hb, orc, monkeypatch):
     bad = _corrupt(shares, rng, nerr)
     ids = np.arange(n)
     monkeypatch.setenv("HBMPC_SCAN_MAX", "0")
+    monkeypatch.setenv("HBMPC_STAGED_WS_MB", "40")   # several waves: the first one samples the wrong senders, the others append leftovers
     c_new = hb.Context(0)
     monkeypatch.setenv("HBMPC_STAGED_MIN", str(1 << 40))
     c_old = hb.Context(0)
@@ -190,7 +191,7 @@ def test_staged_equals_per_thread_decoder_large(hb, orc, monkeypatch):
 def test_staged_after_speculation(staged_ctx, orc):
     """persistent attackers plus scattered errors: the shortcut explains most items, the rest reach the staged decoder."""
     n, t, d, B, S = 16, 5, 5, 3000, 16
-    c = staged_ctx(speculation=True)
+    c = staged_ctx(speculation=True, ws_mb=1)   # 1024-slot waves: the first wave's sample finds the attackers, the rest takes the shortcut
     rng = np.random.default_rng(99)
     coeffs, shares = _codewords(orc, n, d, B, 0x5EED7300)
     words = shares.copy()
