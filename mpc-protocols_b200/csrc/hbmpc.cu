@@ -935,7 +935,7 @@ static size_t staged_slot_bytes(const RecoverTables &T, int t) {
     return (2 * (syn_ld + 2 * tp + 1) + 5 * tp + 1) * 32 + 2 * 16 + 2 * 4 + 1 + 16 + 32 + 1 + 4 + 1;
 }
 static size_t staged_wave_slots(const hbmpc_ctx *ctx, const RecoverTables &T, int t) {
-    size_t budget = (size_t)3072 << 20;
+    size_t budget = (size_t)6144 << 20;  // of 180 GB
     if (const char *wm = getenv("HBMPC_STAGED_WS_MB")) if (atoll(wm) > 0) budget = (size_t)atoll(wm) << 20;
     (void)ctx;
     return std::max<size_t>(budget / staged_slot_bytes(T, t), 1024) & ~(size_t)1023;
