@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--log2-e2e-batch", type=int, default=20, help="secrets per rank per step (host-buffer leg)")
     ap.add_argument("--cpu-log2-batch", type=int, default=17, help="secrets per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-robust-leg", action="store_true", help="skip the secondary K4 measurement (BASELINE configs[3] shape)")
+    ap.add_argument("--log2-robust", type=int, default=17, help="codewords of the K4 leg (n=128, t=42, e ~ U{0..42} errors each)")
     return ap.parse_args()
 
 
@@ -315,6 +317,42 @@ def run_b200(args):
         gather_ms = g0.elapsed_time(g1)
         assert torch.equal(allsec[lo:hi], coeffs[:, 0, :])
 
+    # ---- secondary leg (rank 0, N=1 only, outside the timed region): robust interpolation with injected errors, BASELINE
+    # configs[3] shape (n=128, t=42) at 2^log2_robust codewords, e ~ U{0..42} errors at uniform positions in each codeword
+    robust = None
+    if rank == 0 and n_gpus == 1 and not args.no_robust_leg:
+        n4, t4 = 128, 42
+        B4 = 1 << args.log2_robust
+        ids4 = np.arange(n4)
+        c4 = random_fr_device(torch, (B4, t4 + 1), 0x5EED0004, dev)
+        s4 = torch.empty((B4, n4, 4), dtype=torch.int64, device=dev)
+        ctx.set_async(True)
+        ctx.compute_shares_batch(c4, n4, out=s4)
+        g = torch.Generator(device=dev)
+        g.manual_seed(44)
+        e4 = torch.randint(0, t4 + 1, (B4,), device=dev, generator=g)
+        perm = torch.rand((B4, n4), device=dev, generator=g).argsort(dim=1)
+        mask = torch.zeros((B4, n4), dtype=torch.bool, device=dev)
+        mask.scatter_(1, perm, torch.arange(n4, device=dev)[None, :] < e4[:, None])
+        s4[..., 0] = torch.where(mask, s4[..., 0] ^ 0x5A5A5, s4[..., 0])
+        o4 = (torch.empty((B4, t4 + 1, 4), dtype=torch.int64, device=dev), torch.empty((B4, 4), dtype=torch.int64, device=dev),
+              torch.empty((B4,), dtype=torch.int32, device=dev), torch.empty((B4, 2), dtype=torch.int64, device=dev))
+        ctx.set_async(False)   # synchronous calls: large failing sets take the staged decoder
+        l4 = ctx.launch_count
+        ctx.robust_interpolate_batch(ids4, s4, n4, t4, t4, out=o4)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        for _ in range(3):
+            ctx.robust_interpolate_batch(ids4, s4, n4, t4, t4, out=o4)
+        k1.record(stream)
+        torch.cuda.synchronize()
+        ms4 = k0.elapsed_time(k1) / 3
+        assert torch.equal(o4[0], c4), "robust interpolation did not return the original polynomials"
+        robust = {"workload": "robust_interpolate n=128 t=42, e ~ U{0..42} injected errors per codeword (BASELINE configs[3] shape)", "codewords": B4,
+                  "ms": ms4, "codewords_per_s": B4 / (ms4 * 1e-3), "decoded_with_errors": int((o4[2] != 0).sum()), "max_oec_round": int(o4[2].max()),
+                  "gpu_launches_per_call": int((ctx.launch_count - l4) // 4)}
+        del c4, s4, o4, mask, perm
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -360,7 +398,7 @@ def run_b200(args):
             "breakdown": {"gen_ms": 1e3 * t_gen / args.steps, "recon_ms": 1e3 * t_rec / args.steps,
                           "gen_shares_per_s": n_gpus * args.steps * B * N_PARTIES / t_gen, "recon_shares_per_s": n_gpus * args.steps * B * N_PARTIES / t_rec,
                           "alg_modmul_per_s": n_gpus * args.steps * B * (ALG_MODMUL_GEN + ALG_MODMUL_REC) / t_tot, "gather_ms": gather_ms,
-                          "recon_43_senders_ms": 1e3 * t_gen43, "recon_43_senders_dense_ms": 1e3 * t_dense,
+                          "recon_43_senders_ms": 1e3 * t_gen43, "recon_43_senders_dense_ms": 1e3 * t_dense, "robust_n128_t42": robust,
                           "recon_note": "recon_ms: all 64 senders supplied -> inverse NTT + degree check (bit-identical; items that fail fall back to the dense check); recon_43_senders_ms: only d+t+1 senders supplied -> erasure-weighted inverse NTT + triangular recovery; recon_43_senders_dense_ms: same call with flags -> dense matvec_kernel"},
             "roofline": roof("ntt_kernel<6,1> (K3 batch_recover launch, all 64 senders: inverse 64-point NTT + degree check per chunk)", rec_alg_imad, rec_exec_wide,
                              rec_launch_s, B * (N_PARTIES * 32 + M * 32 + 5),

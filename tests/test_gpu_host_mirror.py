@@ -51,3 +51,27 @@ def test_reference_c_abi_test_restated(tmp_path):
     res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "all C-ABI round trips passed" in res.stdout
+
+
+def _compile_batch_recon(tmp_path):
+    exe = tmp_path / "batch_recon_test"
+    lib_dir = os.path.join(ROOT, "mpc-protocols_b200")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "host", "batch_recon_test.cpp"),
+           "-L", lib_dir, "-lhbmpc_b200", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def test_batch_recon_mirror_compiles_and_links(tmp_path):
+    """CPU: the C++ BatchReconNode mirror (include/hbmpc_batch_recon.hpp) compiles and links against the built library."""
+    _compile_batch_recon(tmp_path)
+
+
+@pytest.mark.gpu
+def test_batch_recon_node_over_fake_network(tmp_path):
+    """mpc/tests/batchrecon_test.rs restated: n parties run BatchReconNode over an in-process FakeNetwork, every decode on the GPU;
+    single-value and batched arms, t Byzantine senders arriving first."""
+    exe = _compile_batch_recon(tmp_path)
+    res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "all batch reconstruction tests passed" in res.stdout
