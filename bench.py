@@ -377,10 +377,10 @@ def run_b200(args):
         rec_alg_imad = B * ALG_MODMUL_REC * IMAD_PER_MODMUL
         gen_alg_imad = B * ALG_MODMUL_GEN * IMAD_PER_MODMUL
         # executed IMAD.WIDE (32x32->64 multiply-add) counts per secret: one Montgomery product = 8 rows x 16 = 128 wide;
-        # 64-point radix-2 NTT: 129 non-trivial twiddle products (+22 scalings by 1/N in the inverse); dense: 64 per term + 64 per reduction
+        # 64-point radix-2 NTT: 129 non-trivial twiddle products (the inverse scales its 22 coefficients by 1/N with a shift, not a product); dense: 64 per term + 64 per reduction
         NTT_MULS = 129
         gen_exec_wide = B * NTT_MULS * 128
-        rec_exec_wide = B * (NTT_MULS + M) * 128
+        rec_exec_wide = B * (NTT_MULS * 128 + M * 8)   # the 1/N scaling of the 22 coefficients is 8 narrow multiplies + a shift each (fr_div_pow2)
         dense_exec_wide = B * ((T_FAULTS + M) * M + (T_FAULTS + M)) * 64
         traffic = ncu_traffic()
         def roof(kernel, alg_imad, exec_wide, secs, nbytes, note, tkey):

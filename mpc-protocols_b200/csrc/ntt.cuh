@@ -29,7 +29,7 @@ struct NttArgs {
     unsigned int *err;
     // MODE 1 (inverse transform + degree check, the all-shares-present fast path of K3):
     const int *in_map;     // domain index j -> record index of the share with id j (nullptr: identity)
-    const uint4 *scale;    // N^{-1} in Montgomery form
+    const uint4 *scale;    // N^{-1} in Montgomery form (unused by the kernels since the scaling is a shift: fr_div_pow2)
     int m, mout;           // coefficients k < mout are stored (scaled), coefficients k >= m must vanish
     unsigned char *fail;   // fail[b] = 1 when some coefficient k >= m is non-zero
     // MODE 2 (inverse transform of an erasure-weighted word, the general optimistic check of K3): the share with id k is
@@ -108,13 +108,38 @@ __device__ __forceinline__ void ntt_stages(uint32_t (&x)[E][8], const uint4 *tw,
 template <int LOGN>
 __host__ __device__ constexpr int ntt_g() { return LOGN < HB_NTT_G ? LOGN : (LOGN >= 8 ? 3 : HB_NTT_G); }
 
+// c = v * 2^-LOGN mod r without a product: r = 1 mod 2^32, so k = -v mod 2^LOGN makes v + k*r divisible by 2^LOGN, and
+// (v + k*r) >> LOGN < r is the canonical quotient (8 narrow multiplies and a funnel shift instead of a 106-multiply CIOS product
+// by the Montgomery form of 1/N; same value bit for bit).
+template <int LOGN>
+__device__ __forceinline__ void fr_div_pow2(uint32_t (&c)[8], const uint32_t (&v)[8]) {
+    if (LOGN == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = v[i];
+        return;
+    }
+    const uint32_t k = (0u - v[0]) & ((1u << LOGN) - 1u);
+    const uint32_t rl[8] = {HB_R0, HB_R1, HB_R2, HB_R3, HB_R4, HB_R5, HB_R6, HB_R7};
+    uint32_t t[9];
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        acc += (unsigned long long)k * rl[i] + v[i];
+        t[i] = (uint32_t)acc;
+        acc >>= 32;
+    }
+    t[8] = (uint32_t)acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = __funnelshift_r(t[i], t[i + 1], LOGN);
+}
+
 // one transformed value at natural-order position `pos` of item b
-template <int MODE>
-__device__ __forceinline__ void ntt_emit(const NttArgs &a, long long b, int pos, const uint32_t (&v)[8], const uint32_t (&sc)[8]) {
+template <int MODE, int LOGN>
+__device__ __forceinline__ void ntt_emit(const NttArgs &a, long long b, int pos, const uint32_t (&v)[8]) {
     if (MODE == 5) {
         if (pos < a.mout) {
             uint32_t c[8], cur[8], r[8];
-            mont_mul(c, v, sc);
+            fr_div_pow2<LOGN>(c, v);
             const long long ob = (long long)a.item_list[b];
             uint4 *o = a.out + (ob * a.out_sb + (long long)pos * a.out_sr) * 2;
             load_fr(cur, o[0], o[1]);
@@ -145,7 +170,7 @@ __device__ __forceinline__ void ntt_emit(const NttArgs &a, long long b, int pos,
     } else {
         if (pos < a.mout) {
             uint32_t c[8];
-            if (MODE == 1) mont_mul(c, v, sc);
+            if (MODE == 1) fr_div_pow2<LOGN>(c, v);
             else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) c[i] = v[i];
@@ -186,8 +211,6 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
     uint4 *myD = sD + (size_t)item_l * 2 * PADN;
     const long long ntiles = (a.B + IPC - 1) / IPC;
     unsigned bad = 0;
-    uint32_t sc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (MODE == 1 || MODE == 5) load_fr(sc, a.scale[0], a.scale[1]);
 
     // Which record feeds each of this thread's E positions is the same for every tile: position pos holds the input with
     // natural index k = bitrev(pos) (zero beyond `cols` / outside the examined id set).
@@ -264,7 +287,7 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int pos = tid_i * E + e;
-                if (active) ntt_emit<MODE>(a, b, pos, x[e], sc);
+                if (active) ntt_emit<MODE, LOGN>(a, b, pos, x[e]);
             }
         } else {
 #pragma unroll
@@ -309,7 +332,7 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
 #pragma unroll
                 for (int e = 0; e < EL; ++e) {
                     const int pos = base + e * h0;
-                    if (active) ntt_emit<MODE>(a, b, pos, y[e], sc);
+                    if (active) ntt_emit<MODE, LOGN>(a, b, pos, y[e]);
                 }
             }
             __syncwarp();  // the tile's buffer is reused by the next tile's pass 0 writes
