@@ -207,7 +207,7 @@ struct hbmpc_ctx {
     bool no_staged_direct = false;                  // HBMPC_NO_STAGED_DIRECT=1: failing items of the all-points check take the dense check first
     bool no_speculation = false;                    // HBMPC_NO_SPECULATION=1: never try the persistent-attacker shortcut
     size_t staged_min = 4096;                       // HBMPC_STAGED_MIN: failing sets of at least this many items use the staged decoder
-    int staged_seg = 8;                             // HBMPC_STAGED_SEG: Berlekamp-Massey iterations between two re-sorts
+    int staged_seg = 16;                            // HBMPC_STAGED_SEG: Berlekamp-Massey iterations between two re-sorts
     unsigned int *h_spec = nullptr;                 // pinned: failing-item count + per-sender error histogram of the scout pass
     bool no_fastpath = false;                       // HBMPC_NO_FASTPATH=1: K3 never takes the all-shares-present inverse-NTT path
     bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
@@ -956,27 +956,35 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
     if (list2_cap < total) list2_cap = (unsigned int)total;
     size_t Wmax = staged_wave_slots(ctx, T, r.t);
     if (Wmax > total) Wmax = total;
-    const size_t Wg = (Wmax + 31) / 32 * 32;  // group-interleaved arrays hold whole groups of 32 positions
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off = al(off + bytes); return o; };
     size_t o_synG[2], o_lamG[2], o_bpG[2], o_bdisP[2], o_stateP[2], o_originP[2];
-    for (int i = 0; i < 2; ++i) {
-        o_synG[i] = take(Wg * syn_ld * 32);
-        o_lamG[i] = take(Wg * tp * 32);
-        o_bpG[i] = take(Wg * tp * 32);
-        o_bdisP[i] = take(Wg * 32);
-        o_stateP[i] = take(Wg * 16);
-        o_originP[i] = take(Wg * 4);
-    }
-    const size_t o_keyP = take(Wg);
-    const size_t o_lam = take(Wmax * tp * 32), o_bp = take(Wmax * tp * 32), o_om = take(Wmax * tp * 32);
-    const size_t o_num = take(Wmax * tp * 32), o_den = take(Wmax * tp * 32);
-    const size_t o_state = take(Wmax * 16), o_mask = take(Wmax * 32), o_perm = take(Wmax * 4), o_key = take(Wmax);
-    const size_t o_runs = take(Wmax * 32), o_okf = take(Wmax);
+    size_t o_keyP, o_lam, o_bp, o_om, o_num, o_den, o_state, o_mask, o_perm, o_key, o_runs, o_okf;
     void *wsp = nullptr, *aux = nullptr;
     int rc;
-    if ((rc = scratch_get(ctx, ln, 10, off, &wsp))) return rc;
+    for (;;) {  // the wave shrinks when the device cannot spare the workspace
+        const size_t Wg = (Wmax + 31) / 32 * 32;  // group-interleaved arrays hold whole groups of 32 positions
+        off = 0;
+        for (int i = 0; i < 2; ++i) {
+            o_synG[i] = take(Wg * syn_ld * 32);
+            o_lamG[i] = take(Wg * tp * 32);
+            o_bpG[i] = take(Wg * tp * 32);
+            o_bdisP[i] = take(Wg * 32);
+            o_stateP[i] = take(Wg * 16);
+            o_originP[i] = take(Wg * 4);
+        }
+        o_keyP = take(Wg);
+        o_lam = take(Wmax * tp * 32); o_bp = take(Wmax * tp * 32); o_om = take(Wmax * tp * 32);
+        o_num = take(Wmax * tp * 32); o_den = take(Wmax * tp * 32);
+        o_state = take(Wmax * 16); o_mask = take(Wmax * 32); o_perm = take(Wmax * 4); o_key = take(Wmax);
+        o_runs = take(Wmax * 32); o_okf = take(Wmax);
+        rc = scratch_get(ctx, ln, 10, off, &wsp);
+        if (!rc) break;
+        cudaGetLastError();
+        if (Wmax <= 4096) return rc;
+        Wmax = std::max<size_t>((Wmax / 2) & ~(size_t)1023, 1024);
+    }
     const size_t hist_bytes = (size_t)(nseg + 1) * 256 * 4;
     if ((rc = scratch_get(ctx, ln, 11, al(hist_bytes) + (size_t)list2_cap * 4 + 256, &aux))) return rc;
     unsigned int *hist = (unsigned int *)aux;

@@ -195,7 +195,18 @@ static void test_message_framing() {
     std::puts("test_message_framing ok");
 }
 
-int main() {
+int main(int argc, char **argv) {
+    if (argc > 1 && std::string(argv[1]) == "--host-only") {  // no device: wire framing and payload validation only
+        test_message_framing();
+        try { detail::deser_bounded_vec(std::vector<uint8_t>(4, 0), 4); REQUIRE(false); } catch (const BatchReconError &e) { REQUIRE(e.kind == BatchReconError::ArkDeserialization); }
+        std::vector<uint8_t> big(8 + 32, 0);
+        big[0] = 200;  // claims 200 elements in a 40-byte payload
+        try { detail::deser_bounded_vec(big, big.size()); REQUIRE(false); } catch (const BatchReconError &e) { REQUIRE(e.kind == BatchReconError::ArkDeserialization); }
+        std::vector<U256> two = {fr_from_u64(5), fr_from_u64(6)};
+        REQUIRE(detail::deser_bounded_vec(detail::ser_vec(two), 72) == two);
+        std::puts("host-only checks passed");
+        return 0;
+    }
     Context ctx(0);
     test_message_framing();
     test_batch_reconstruction(ctx);

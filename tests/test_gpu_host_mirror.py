@@ -63,8 +63,12 @@ def _compile_batch_recon(tmp_path):
 
 
 def test_batch_recon_mirror_compiles_and_links(tmp_path):
-    """CPU: the C++ BatchReconNode mirror (include/hbmpc_batch_recon.hpp) compiles and links against the built library."""
-    _compile_batch_recon(tmp_path)
+    """CPU: the C++ BatchReconNode mirror (include/hbmpc_batch_recon.hpp) compiles and links against the built library; its wire
+    framing (WrappedMessage::BatchRecon under bincode, ark-serialize Vec<F>) and payload validation run without a device."""
+    exe = _compile_batch_recon(tmp_path)
+    res = subprocess.run([str(exe), "--host-only"], capture_output=True, text=True, timeout=60)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "host-only checks passed" in res.stdout
 
 
 @pytest.mark.gpu
