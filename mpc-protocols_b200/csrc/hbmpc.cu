@@ -1006,12 +1006,14 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
     sa.runs = (uint4 *)(w8 + o_runs); sa.okf = (unsigned char *)(w8 + o_okf);
     // resident CTAs of the Berlekamp-Massey kernel are capped through its dynamic shared memory size: the live state of the
     // resident positions should stay inside the L2 (HBMPC_BM_CTAS per SM, default 5 = the register limit)
-    size_t bm_smem = (size_t)HB_BM_DEPTH * 4 * 128 * 16;  // the kernel's operand ring
+    size_t bm_smem = 0;
     if (const char *bc = getenv("HBMPC_BM_CTAS")) {
         const int c = atoi(bc);
-        if (c >= 1 && c < HB_BM_MINB) bm_smem = std::max(bm_smem, (size_t)(220 * 1024 / c - 2048) & ~(size_t)1023);
+        if (c >= 1 && c < HB_BM_MINB) {
+            bm_smem = (size_t)(220 * 1024 / c - 2048) & ~(size_t)1023;
+            CK(cudaFuncSetAttribute(bm_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
+        }
     }
-    CK(cudaFuncSetAttribute(bm_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
     const bool prof = getenv("HBMPC_STAGED_PROF") != nullptr;
     cudaEvent_t pe[8] = {};
     float pms[7] = {};

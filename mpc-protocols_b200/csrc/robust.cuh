@@ -663,7 +663,7 @@ __device__ __forceinline__ void st_fr2(uint4 *p, const uint32_t (&a)[8]) {
 }
 // element e of the thread's position in a group-interleaved array with `ld` elements per position
 struct GView {
-    uint4 *base;  // array + (group*ld*2)*32 + lane; element e: lo at base[e*64], hi at base[e*64 + 32]
+    uint4 *base;  // array + (group*ld*2)*32 + lane
     __device__ __forceinline__ GView(uint4 *arr, unsigned int pos, int ld) : base(arr + ((size_t)(pos >> 5) * ld * 2) * 32 + (pos & 31)) {}
     __device__ __forceinline__ void ld(uint32_t (&a)[8], int e) const { load_fr(a, base[(size_t)e * 64], base[(size_t)e * 64 + 32]); }
     __device__ __forceinline__ void st(int e, const uint32_t (&a)[8]) const {
@@ -672,29 +672,11 @@ struct GView {
     }
 };
 
-// Operand ring of bm_segment_kernel: HB_BM_DEPTH stages of two field elements per thread in shared memory, filled with
-// cp.async (LDGSTS) several terms ahead of their use.  One thread per codeword runs a serial chain of products; in the late
-// segments few threads are left per SM and an L2 round trip is longer than a product, so a one-term register prefetch left
-// the multiply pipe half idle.  The ring costs no registers.  Element (stage, q) of a thread sits at ring[(stage*4 + q)*128]
-// (q: 0/1 = first operand lo/hi, 2/3 = second operand lo/hi): conflict-free 128-bit accesses, thread-private columns (no barrier).
-#ifndef HB_BM_DEPTH
-#define HB_BM_DEPTH 4
-#endif
-__device__ __forceinline__ void bm_cp16(uint4 *smem_dst, const uint4 *gmem_src) {
-    const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void bm_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bm_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(HB_BM_DEPTH - 1) : "memory"); }
-__device__ __forceinline__ void bm_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 // Berlekamp-Massey iterations j0 <= j < j1 of every live position (same recurrences as rs_attempt)
 #ifndef HB_BM_MINB
 #define HB_BM_MINB 5
 #endif
 __global__ void __launch_bounds__(128, HB_BM_MINB) bm_segment_kernel(const StagedArgs a) {
-    extern __shared__ __align__(16) unsigned char bm_smem_raw[];
-    uint4 *ring = reinterpret_cast<uint4 *>(bm_smem_raw) + threadIdx.x;
     const unsigned int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= a.W) return;
     const GView lam(a.lamG[0], pos, a.tp), bp(a.bpG[0], pos, a.tp), syn(a.synG[0], pos, a.syn_ld), bd(a.bdisP[0], pos, 1);
@@ -714,10 +696,6 @@ __global__ void __launch_bounds__(128, HB_BM_MINB) bm_segment_kernel(const Stage
         bd.ld(bdis, 0);
     }
     bool dead = false;
-    // `gate` carries a data dependence on the values last read from the ring, so that the asynchronous copy that reuses their
-    // stage cannot be issued before those reads have completed (it is never equal to `never`: limbs 7 are below 2^31)
-    const unsigned int never = 0xfffffff0u + (unsigned int)a.tp;
-    unsigned int gate = 0;
 #pragma unroll 1
     for (int j = a.j0; j < a.j1; ++j) {
         uint32_t delta[8];
@@ -725,29 +703,19 @@ __global__ void __launch_bounds__(128, HB_BM_MINB) bm_segment_kernel(const Stage
             acc_t A;
             acc_zero(A);
             const int lim = L < j ? L : j;
-            auto issue = [&](int l) {  // operands of term l: Lambda_l and S_{j-l}
-                if (l <= lim && gate != never) {
-                    uint4 *st = ring + (size_t)((l % HB_BM_DEPTH) * 4) * 128;
-                    const uint4 *pl = lam.base + (size_t)l * 64, *ps = syn.base + (size_t)(j - l) * 64;
-                    bm_cp16(st, pl);
-                    bm_cp16(st + 128, pl + 32);
-                    bm_cp16(st + 256, ps);
-                    bm_cp16(st + 384, ps + 32);
-                }
-                bm_commit();
-            };
-#pragma unroll
-            for (int l = 0; l < HB_BM_DEPTH - 1; ++l) issue(l);
+            // software pipelining with two operand sets (no register moves): the next operands are in flight during a product
+            uint32_t x0[8], s0[8], x1[8], s1[8];
+            lam.ld(x0, 0);
+            syn.ld(s0, j);
 #pragma unroll 1
-            for (int l = 0; l <= lim; ++l) {
-                issue(l + HB_BM_DEPTH - 1);  // reuses the stage of term l - 1
-                bm_wait();                   // term l has landed
-                const uint4 *st = ring + (size_t)((l % HB_BM_DEPTH) * 4) * 128;
-                uint32_t x[8], sy[8];
-                load_fr(x, st[0], st[128]);
-                load_fr(sy, st[256], st[384]);
-                gate = x[7] | sy[7];
-                acc_mac(A, x, sy);
+            for (int l = 0; l <= lim; l += 2) {
+                const int l1 = l + 1 <= lim ? l + 1 : lim, l2 = l + 2 <= lim ? l + 2 : lim;
+                lam.ld(x1, l1);
+                syn.ld(s1, j - l1);
+                acc_mac(A, x0, s0);
+                lam.ld(x0, l2);
+                syn.ld(s0, j - l2);
+                if (l + 1 <= lim) acc_mac(A, x1, s1);
             }
             acc_reduce(A, delta);
         }
@@ -757,49 +725,31 @@ __global__ void __launch_bounds__(128, HB_BM_MINB) bm_segment_kernel(const Stage
         const bool grow = 2 * L <= j;
         const int newL = grow ? j + 1 - L : L;
         if (newL > a.maxL) { dead = true; break; }
-        {
-            auto issue = [&](int l) {  // operands of coefficient l (descending): Lambda_l and B_{l-shift}, where they exist
-                if (l >= 0 && gate != never) {
-                    uint4 *st = ring + (size_t)(((newL - l) % HB_BM_DEPTH) * 4) * 128;
-                    if (l <= L) {
-                        const uint4 *pl = lam.base + (size_t)l * 64;
-                        bm_cp16(st, pl);
-                        bm_cp16(st + 128, pl + 32);
-                    }
-                    const int bi = l - shift;
-                    if (bi >= 0 && bi < lenB) {
-                        const uint4 *pb = bp.base + (size_t)bi * 64;
-                        bm_cp16(st + 256, pb);
-                        bm_cp16(st + 384, pb + 32);
-                    }
-                }
-                bm_commit();
-            };
-#pragma unroll
-            for (int k = 0; k < HB_BM_DEPTH - 1; ++k) issue(newL - k);
+        uint32_t lmn[8], bln[8];  // operands of the next coefficient, loaded one step ahead
+        if (newL <= L) lam.ld(lmn, newL); else set_zero(lmn);
+        if (newL - shift >= 0 && newL - shift < lenB) bp.ld(bln, newL - shift); else set_zero(bln);
 #pragma unroll 1
-            for (int l = newL; l >= 0; --l) {
-                issue(l - (HB_BM_DEPTH - 1));
-                bm_wait();
-                const uint4 *st = ring + (size_t)(((newL - l) % HB_BM_DEPTH) * 4) * 128;
-                uint32_t lm[8], bl[8], res[8];
-                const int bi = l - shift;
-                const bool hasb = bi >= 0 && bi < lenB;
-                if (l <= L) load_fr(lm, st[0], st[128]); else set_zero(lm);
-                if (hasb) load_fr(bl, st[256], st[384]); else set_zero(bl);
-                gate = lm[7] | bl[7];
-                // two interleaved-row products and a modular addition: fewer multiply-pipe instructions than two lazy products
-                // followed by a reduction of the 512-bit sum
-                mont_mul(res, lm, bdis);
-                if (hasb) {
-                    uint32_t p2[8], sm[8];
-                    mont_mul(p2, bl, nd);
-                    fr_add(sm, res, p2);
-                    copy8(res, sm);
-                }
-                lam.st(l, res);
-                if (grow && l <= L) bp.st(l, lm);
+        for (int l = newL; l >= 0; --l) {
+            uint32_t lm[8], bl[8], res[8];
+            copy8(lm, lmn);
+            copy8(bl, bln);
+            const int bi = l - shift;
+            const bool hasb = bi >= 0 && bi < lenB;
+            if (l >= 1) {
+                if (l - 1 <= L) lam.ld(lmn, l - 1); else set_zero(lmn);
+                if (bi - 1 >= 0 && bi - 1 < lenB) bp.ld(bln, bi - 1); else set_zero(bln);
             }
+            // two interleaved-row products and a modular addition: fewer multiply-pipe instructions than two lazy products
+            // followed by a reduction of the 512-bit sum
+            mont_mul(res, lm, bdis);
+            if (hasb) {
+                uint32_t p2[8], sm[8];
+                mont_mul(p2, bl, nd);
+                fr_add(sm, res, p2);
+                copy8(res, sm);
+            }
+            lam.st(l, res);
+            if (grow && l <= L) bp.st(l, lm);
         }
         if (grow) {
             lenB = L + 1;
@@ -810,7 +760,6 @@ __global__ void __launch_bounds__(128, HB_BM_MINB) bm_segment_kernel(const Stage
             ++shift;
         }
     }
-    bm_wait_all();
     a.stateP[0][pos] = make_int4(L, lenB, shift, dead ? 1 : 0);
     bd.st(0, bdis);
     a.keyP[pos] = dead ? (unsigned char)255 : (unsigned char)(a.maxL - L);  // longest locators first: their CTAs must not start last
