@@ -202,7 +202,11 @@ struct hbmpc_ctx {
     std::string err;
     int num_sms = 148;
     int matvec_regs = 0;
-    int ntt_ctas[6][9] = {};                        // resident CTAs per SM of ntt_kernel<LOGN, MODE>
+    int ntt_ctas[6][9] = {};
+    int ntt64_ctas[2] = {};                         // resident CTAs per SM of ntt64_cta_kernel<MODE>
+    bool ntt_cta = true;                            // HBMPC_NTT_CTA=0: never use ntt64_cta_kernel; 2: use it for every 64-point transform of any size
+    bool ntt_cta_all = false;
+    long long ntt_cta_min = 1024;                        // resident CTAs per SM of ntt_kernel<LOGN, MODE>
     size_t scan_max = 65536;                        // HBMPC_SCAN_MAX: batches up to this size skip the compaction pass
     bool no_staged_direct = false;                  // HBMPC_NO_STAGED_DIRECT=1: failing items of the all-points check take the dense check first
     bool no_speculation = false;                    // HBMPC_NO_SPECULATION=1: never try the persistent-attacker shortcut
@@ -306,6 +310,8 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
         if (sx) ctx->scan_max = (size_t)atoll(sx);
         const char *ns = getenv("HBMPC_NO_SPECULATION");
         ctx->no_speculation = ns && ns[0] == '1';
+        const char *nc = getenv("HBMPC_NTT_CTA");
+        if (nc) { ctx->ntt_cta = nc[0] == '1' || nc[0] == '2'; if (nc[0] == '2') { ctx->ntt_cta_min = 1; ctx->ntt_cta_all = true; } }
         const char *nd = getenv("HBMPC_NO_STAGED_DIRECT");
         ctx->no_staged_direct = nd && nd[0] == '1';
         const char *sm = getenv("HBMPC_STAGED_MIN");
@@ -595,7 +601,31 @@ static int launch_ntt_t(hbmpc_ctx *ctx, cudaStream_t st, const NttArgs &a) {
     return 0;
 }
 template <int MODE>
+static int launch_ntt64_cta(hbmpc_ctx *ctx, cudaStream_t st, const NttArgs &a) {
+    const size_t smem = ntt64_cta_smem_bytes();
+    int &ctas = ctx->ntt64_ctas[MODE];
+    if (ctas == 0) {
+        CK(cudaFuncSetAttribute(ntt64_cta_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ntt64_cta_kernel<MODE>, HB_NTT64_IPC * 16, smem));
+        ctas = nb > 0 ? nb : 1;
+    }
+    const long long ntiles = (a.B + HB_NTT64_IPC - 1) / HB_NTT64_IPC;
+    const long long grid = std::min<long long>(ntiles, (long long)ctx->num_sms * ctas);
+    ntt64_cta_kernel<MODE><<<(unsigned)grid, HB_NTT64_IPC * 16, smem, st>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+template <int MODE>
 static int launch_ntt(hbmpc_ctx *ctx, cudaStream_t st, int logn, const NttArgs &a) {
+    if constexpr (MODE == 0 || MODE == 1) {
+        // measured (profiles/r01i_*): the CTA-cooperative kernel wins where whole warps can skip products -- zero-padded inputs
+        // (share generation: 22 or 43 coefficients of 64... up to half the domain) and the inverse transform; the full-width
+        // forward transform (64 columns) is faster in the warp-per-item kernel
+        if (logn == 6 && ctx->ntt_cta && a.B >= ctx->ntt_cta_min && (ctx->ntt_cta_all || MODE == 1 || a.cols <= 32))
+            return launch_ntt64_cta<MODE>(ctx, st, a);
+    }
     switch (logn) {
         case 1: return launch_ntt_t<1, MODE>(ctx, st, a);
         case 2: return launch_ntt_t<2, MODE>(ctx, st, a);

@@ -342,6 +342,191 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
     if (bad) *(volatile unsigned int *)a.err = 1u;  // mapped host memory: plain store, every writer stores 1
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// ntt64_cta_kernel<MODE>: the 64-point transform (the headline shape: n = 64) with the work of a 16-item tile regrouped
+// ACROSS the warps of the CTA, so that twiddle factors that are trivial -- or operands that are known to be zero -- are so
+// for every lane of a warp and the product is skipped by the whole warp (ntt_kernel keeps one item inside one warp: there a
+// trivial twiddle only idles a quarter of the lanes and saves nothing).
+//   pass 0 (stages 0,1): thread = (item, r): the 16 thread indices are ordered so that those whose only product (w^16 * x3) has a
+//                        possibly non-zero operand come first: with 22 coefficients of 64 only 3 of the 8 warps multiply
+//   pass 1 (stages 2,3): thread = (item, hi, low) with `low` (the twiddle index) constant per warp: the two warps with low = 0
+//                        run one product instead of four
+//   pass 2 (stages 4,5): thread = (item, tid) as in ntt_kernel (lane-dependent twiddles, coalesced natural-order outputs)
+// Passes exchange through shared memory with __syncthreads (3 per tile); items are `ISTR` = odd number of uint4 apart so that
+// the 8 items of a quarter warp fall into different banks.  MODE 0 / 1 as in ntt_kernel; bit-identical results.
+// Executed products per item: 122 (MODE 0, 22 coefficients) / 132 (all 64 inputs) instead of 144.
+#ifndef HB_NTT64_IPC
+#define HB_NTT64_IPC 8   // items per CTA tile (8: four warps per barrier, six CTAs per SM; 16: eight warps, three CTAs)
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(HB_NTT64_IPC * 16, 768 / (HB_NTT64_IPC * 16)) ntt64_cta_kernel(const NttArgs a) {
+    constexpr int LOGN = 6, N = 64, E = 4, IPC = HB_NTT64_IPC, PADN = N + N / 8, ISTR = 2 * PADN + 1, BLOCK = IPC * 16;
+    constexpr int LI = IPC == 16 ? 4 : 3;  // log2(IPC)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4 *sTw = reinterpret_cast<uint4 *>(smem_raw);   // [N/2][2]
+    uint4 *sD = sTw + N;                                 // [IPC][ISTR]
+    uint4 *sIn = sD + (size_t)IPC * ISTR;                // [E][2][BLOCK] per-thread input staging (prefetch)
+    const int t = threadIdx.x;
+    for (int i = t; i < N; i += BLOCK) sTw[i] = a.tw[i];
+
+    // ---- pass-0 role.  Position pos = tid*4 + e holds the input with natural index bitrev(pos); the product of pass 0 is
+    // w^16 * x3 where x3 = (input e=2) - (input e=3): thread indices whose inputs 2 and 3 do not exist are ranked last.
+    auto rec_for = [&](int tid, int e) -> int {
+        const int k = (int)(__brev((unsigned)(tid * E + e)) >> (32 - LOGN));
+        return (k < a.cols) ? ((MODE == 1 && a.in_map) ? a.in_map[k] : k) : -1;
+    };
+    const int item0 = t & (IPC - 1), r0 = t >> LI;
+    int tid0 = 0;
+    {
+        int rank = 0, found = -1;
+        for (int pass = 0; pass < 2 && found < 0; ++pass)      // first the indices that need the product, then the others
+            for (int c = 0; c < 16 && found < 0; ++c) {
+                const bool need = rec_for(c, 2) >= 0 || rec_for(c, 3) >= 0;
+                if (need == (pass == 0)) {
+                    if (rank == r0) found = c;
+                    ++rank;
+                }
+            }
+        tid0 = found;
+    }
+    int rec_of[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) rec_of[e] = rec_for(tid0, e);
+    const unsigned FULL = 0xffffffffu;
+    const bool has1 = __any_sync(FULL, rec_of[1] >= 0), has2 = __any_sync(FULL, rec_of[2] >= 0), has3 = __any_sync(FULL, rec_of[3] >= 0);
+    // ---- pass-1 role: low (twiddle index) per warp
+    const int item1 = t & (IPC - 1), low1 = t >> (LI + 2), tid1 = (((t >> LI) & 3) << 2) | low1;
+    const int base1 = ((tid1 >> 2) << 4) | low1;   // positions base1 + e*4
+    // ---- pass-2 role
+    const int item2 = t >> 4, tid2 = t & 15;        // positions tid2 + e*16
+    __syncthreads();
+
+    const long long ntiles = (a.B + IPC - 1) / IPC;
+    unsigned bad = 0;
+    uint4 *myIn = sIn + t;
+    const unsigned int never = (unsigned int)a.n + 0x7fff0000u;
+    auto prefetch = [&](long long tl, unsigned int gate) {
+        const long long bb = tl * IPC + item0;
+        if (tl < ntiles && bb < a.B && gate != never) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                if (rec_of[e] < 0) continue;
+                const uint4 *p = a.in + (bb * a.in_sb + (long long)rec_of[e] * a.in_sc) * 2;
+                cp_async16(myIn + (e * 2) * BLOCK, p);
+                cp_async16(myIn + (e * 2 + 1) * BLOCK, p + 1);
+            }
+        }
+        cp_async_commit();
+    };
+    auto bfly = [&](uint32_t (&u)[8], uint32_t (&v)[8], int twidx, bool mul) {  // mul == false: twiddle 1, or v known to be zero
+        uint32_t tt[8], sm[8], df[8];
+        if (mul) {
+            uint32_t w[8];
+            load_fr(w, sTw[twidx * 2], sTw[twidx * 2 + 1]);
+            mont_mul(tt, v, w);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tt[i] = v[i];
+        }
+        fr_add(sm, u, tt);
+        fr_sub(df, u, tt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { u[i] = sm[i]; v[i] = df[i]; }
+    };
+    auto idx_of = [](int pos) { return pos + (pos >> 3); };
+    prefetch(blockIdx.x, 0u);
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint32_t x[E][8];
+        // ---- pass 0
+        {
+            const long long b = tile * IPC + item0;
+            const bool active = b < a.B;
+            cp_async_wait_all();
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                if (active && rec_of[e] >= 0) {
+                    load_fr(x[e], myIn[(e * 2) * BLOCK], myIn[(e * 2 + 1) * BLOCK]);
+                    bad |= geq_mod(x[e]) ? 1u : 0u;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[e][i] = 0;
+                }
+            }
+            prefetch(tile + gridDim.x, bad);
+            // stage 0: (x0,x1), (x2,x3) with twiddle 1; stage 1: (x0,x2) with 1, (x1,x3) with w^16
+            if (has1) bfly(x[0], x[1], 0, false);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[1][i] = x[0][i];
+            }
+            if (has3) bfly(x[2], x[3], 0, false);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[3][i] = x[2][i];
+            }
+            if (has2 || has3) {
+                bfly(x[0], x[2], 0, false);
+                bfly(x[1], x[3], N / 4, true);
+            } else {  // x2 == x3 == 0 in every lane of the warp
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { x[2][i] = x[0][i]; x[3][i] = x[1][i]; }
+            }
+            uint4 *d = sD + (size_t)item0 * ISTR;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int ix = idx_of(tid0 * E + e);
+                d[ix] = make_uint4(x[e][0], x[e][1], x[e][2], x[e][3]);
+                d[PADN + ix] = make_uint4(x[e][4], x[e][5], x[e][6], x[e][7]);
+            }
+        }
+        __syncthreads();
+        // ---- pass 1: half = 4, 8; twiddle exponent (pos mod half) * N/(2*half)
+        {
+            uint4 *d = sD + (size_t)item1 * ISTR;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int ix = idx_of(base1 + e * 4);
+                load_fr(x[e], d[ix], d[PADN + ix]);
+            }
+            const bool nz = low1 != 0;  // warp-uniform
+            bfly(x[0], x[1], low1 << 3, nz);
+            bfly(x[2], x[3], low1 << 3, nz);
+            bfly(x[0], x[2], low1 << 2, nz);
+            bfly(x[1], x[3], (low1 + 4) << 2, true);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int ix = idx_of(base1 + e * 4);
+                d[ix] = make_uint4(x[e][0], x[e][1], x[e][2], x[e][3]);
+                d[PADN + ix] = make_uint4(x[e][4], x[e][5], x[e][6], x[e][7]);
+            }
+        }
+        __syncthreads();
+        // ---- pass 2: half = 16, 32; natural-order outputs
+        {
+            const long long b = tile * IPC + item2;
+            const bool active = b < a.B;
+            const uint4 *d = sD + (size_t)item2 * ISTR;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int ix = idx_of(tid2 + e * 16);
+                load_fr(x[e], d[ix], d[PADN + ix]);
+            }
+            if (MODE == 1 && a.path && active && tid2 == 0) a.path[b] = 0;
+            bfly(x[0], x[1], tid2 << 1, true);
+            bfly(x[2], x[3], tid2 << 1, true);
+            bfly(x[0], x[2], tid2, true);
+            bfly(x[1], x[3], tid2 + 16, true);
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+                if (active) ntt_emit<MODE, LOGN>(a, b, tid2 + e * 16, x[e]);
+        }
+        __syncthreads();  // the tile's buffer is rewritten by the next tile's pass 0
+    }
+    if (bad) *(volatile unsigned int *)a.err = 1u;
+}
+inline size_t ntt64_cta_smem_bytes() { return (size_t)(64 + HB_NTT64_IPC * (2 * 72 + 1) + 4 * 2 * HB_NTT64_IPC * 16) * 16 + 16; }
+
 template <int LOGN>
 inline size_t ntt_smem_bytes() {
     constexpr int N = 1 << LOGN;
