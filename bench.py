@@ -400,11 +400,11 @@ def run_b200(args):
                           "alg_modmul_per_s": n_gpus * args.steps * B * (ALG_MODMUL_GEN + ALG_MODMUL_REC) / t_tot, "gather_ms": gather_ms,
                           "recon_43_senders_ms": 1e3 * t_gen43, "recon_43_senders_dense_ms": 1e3 * t_dense, "robust_n128_t42": robust,
                           "recon_note": "recon_ms: all 64 senders supplied -> inverse NTT + degree check (bit-identical; items that fail fall back to the dense check); recon_43_senders_ms: only d+t+1 senders supplied -> erasure-weighted inverse NTT + triangular recovery; recon_43_senders_dense_ms: same call with flags -> dense matvec_kernel"},
-            "roofline": roof("ntt_kernel<6,1> (K3 batch_recover launch, all 64 senders: inverse 64-point NTT + degree check per chunk)", rec_alg_imad, rec_exec_wide,
+            "roofline": roof("ntt64_cta_kernel<1> (K3 batch_recover launch, all 64 senders: inverse 64-point NTT + degree check per chunk)", rec_alg_imad, rec_exec_wide,
                              rec_launch_s, B * (N_PARTIES * 32 + M * 32 + 5),
                              "achieved = algorithmic IMAD (B * 1430 modmul * 256, SURVEY 8d dense count) / CUDA-event launch time; peak = mad.lo.u32 probe measured in this run; executed_* = IMAD.WIDE actually issued vs the IMAD.WIDE probe",
                              "ntt_inv"),
-            "roofline_gen": roof("ntt_kernel<6,0> (K1 compute_shares launch: zero-padded 64-point NTT per secret)", gen_alg_imad, gen_exec_wide, gen_launch_s, B * BYTES_GEN,
+            "roofline_gen": roof("ntt64_cta_kernel<0> (K1 compute_shares launch: zero-padded 64-point NTT per secret)", gen_alg_imad, gen_exec_wide, gen_launch_s, B * BYTES_GEN,
                                  "algorithmic IMAD = B * 1344 modmul * 256 (dense Horner count of SURVEY 8d)", "ntt_fwd"),
             "roofline_dense": roof("matvec_kernel<4> (K3 batch_recover launch with flags, 43 senders: 43x22 check+coefficient matrix per chunk)", rec_alg_imad, dense_exec_wide, t_dense,
                                    B * (BYTES_REC + 8), "same algorithmic count, dense path", "matvec"),
