@@ -6,11 +6,18 @@
 // Residues are unique, so a radix-2 NTT returns bit-identical shares with ~N/2*log2(N) modular products per item instead
 // of n*cols (n=64, d=21: ~130 products against 1408 multiply-accumulates + 64 reductions).
 //
-// Mapping: decimation in time.  N/8 threads (all in one warp) own one item; each thread holds 8 elements in registers
-// and runs up to 3 butterfly stages per pass; passes exchange through a padded shared-memory buffer (conflict-free
-// 128-bit accesses) with __syncwarp only.  Pass 0 gathers the input in bit-reversed order straight from global memory
-// (zero padding beyond `cols` costs no loads), the last pass writes natural-order outputs j < n.  Data stays canonical,
-// twiddles are in Montgomery form (fr.cuh), so there is no conversion pass.
+// ntt_kernel<LOGN, MODE> -- decimation in time.  N/4 threads (N/8 for N = 256; all in one warp) own one item; each thread holds
+// 4 (8) elements in registers and runs 2 (3) butterfly stages per pass; passes exchange through a padded shared-memory buffer
+// (conflict-free 128-bit accesses) with __syncwarp only.  Pass 0 takes the input in bit-reversed order from per-thread staging slots
+// that cp.async fills one tile ahead (zero padding beyond `cols` costs no loads), the last pass writes natural-order outputs j < n.
+// Data stays canonical, twiddles are in Montgomery form (fr.cuh), so there is no conversion pass.
+//   MODE 0  forward transform (K1 share generation, K2 Vandermonde apply)
+//   MODE 1  inverse transform of all N supplied shares + "top coefficients vanish" check (K3 fast path, a10 degree check)
+//   MODE 2  inverse/forward transform of a weighted word with missing ids (K3 erasure check; syndromes of the staged decoder)
+//   MODE 3/4/5  transforms of the staged robust decoder (robust.cuh): Chien search into a root mask, Forney values gathered at the
+//           roots, sparse inverse transform subtracted from the coefficients
+// ntt64_cta_kernel<MODE> (MODE 0/1, N = 64, large batches) regroups a tile's work across the warps of the CTA so that trivial
+// twiddles and known-zero operands are skipped by whole warps (see its header below).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
