@@ -13,7 +13,10 @@
  *   - every data pointer may be a host pointer or a device pointer (detected with cudaPointerGetAttributes).
  *     Calls with a host buffer are pipelined in chunks over internal streams (host->device copy, kernels and
  *     device->host copy of neighbouring chunks overlap; use pinned memory for full PCIe speed) and return after the
- *     results are in the caller's buffers; calls with device buffers only run on the context's stream;
+ *     results are in the caller's buffers; calls with device buffers only run on the context's stream.  That stream is
+ *     created non-blocking: device buffers written on another stream must be complete (or ordered by an event, or the
+ *     context moved onto that stream with hbmpc_ctx_set_stream) before the call -- the library does not synchronize with
+ *     streams it does not own;
  *   - outputs are CALLER-allocated (the reference leaks Vecs to C and frees them through free_* helpers);
  *   - no hidden RNG: share generation takes the polynomial coefficients, so results are reproducible;
  *   - there is no CPU fallback: every call fails with HBMPC_NO_DEVICE if no CUDA device is usable.

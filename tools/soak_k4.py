@@ -57,6 +57,7 @@ def main():
         arrival = rng.permutation(S)
         ids_arr = ids[arrival]
         coeffs = random_fr_device(torch, (B, d + 1), int(rng.integers(1 << 30)), dev)
+        torch.cuda.synchronize()   # torch's stream and the contexts' streams are not ordered with each other
         shares = ctxs["staged"].compute_shares_batch(coeffs, n)
         words = shares[:, torch.as_tensor(ids_arr, device=dev)].contiguous()      # [B][S] in arrival order
         rmax = min(t, S - needed)
@@ -86,6 +87,7 @@ def main():
         bump = torch.randint(1, 1 << 20, (B, S), device=dev, generator=g)
         words[..., 0] = torch.where(mask, words[..., 0] ^ bump, words[..., 0])
         evals = words.permute(1, 0, 2).contiguous()
+        torch.cuda.synchronize()   # the contexts run on their own (non-blocking) streams: the inputs must be complete before the calls
         outs = {}
         for name, c in ctxs.items():
             for fl in (True, False):
