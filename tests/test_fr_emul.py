@@ -28,3 +28,23 @@ def test_fr_cuh_limb_logic(tmp_path):
                 assert vals[-1] == acc * RINV % R, f"terms={terms}"
                 n_acc += 1
         assert n_acc == 10 and n_ops == 64
+
+
+def test_division_by_power_of_two_identity():
+    """The inverse transforms scale by 1/N with a shift (ntt.cuh: fr_div_pow2): r = 1 mod 2^32, so with k = -v mod N the sum v + k*r is
+    divisible by N = 2^logn and (v + k*r) >> logn is the canonical v * N^-1 mod r.  Checked here with big ints for every domain size the
+    kernels support, on edge values and random ones (the device code is covered bit for bit by the GPU parity tests of K3)."""
+    import random
+
+    assert R % (1 << 32) == 1
+    rnd = random.Random(5)
+    for logn in range(0, 9):
+        n = 1 << logn
+        ninv = pow(n, -1, R)
+        for v in [0, 1, 2, n - 1, n, n + 1, R - 1, R - 2, R - n, (R - 1) // 2] + [rnd.randrange(R) for _ in range(200)]:
+            k = (-v) % n
+            s = v + k * R
+            assert s % n == 0
+            q = s >> logn
+            assert q < R and q == v * ninv % R
+            assert s < 1 << 288   # nine 32-bit limbs hold the sum
