@@ -265,7 +265,28 @@ def run_b200(args):
         return d0.elapsed_time(d1) / 3 * 1e-3
 
     t_gen43 = timed3(lambda: ctx.batch_recover(ids43, ev43, N_PARTIES, DEG, T_FAULTS, out=(rec, path, None)))
-    t_dense = timed3(lambda: ctx.batch_recover(ids43, ev43, N_PARTIES, DEG, T_FAULTS, out=(rec, path, flags43)))
+    t_flags43 = timed3(lambda: ctx.batch_recover(ids43, ev43, N_PARTIES, DEG, T_FAULTS, out=(rec, path, flags43)))
+    # the dense kernel on its own (roofline_dense): a context that sends calls with flags straight to the dense check, as every
+    # chunk with a disagreeing share goes (HBMPC_NO_ER_FLAGS is a test knob read at context creation)
+    os.environ["HBMPC_NO_ER_FLAGS"] = "1"
+    ctx_dense = hb.Context(local)
+    del os.environ["HBMPC_NO_ER_FLAGS"]
+    ctx_dense.set_stream(stream.cuda_stream)
+    ctx_dense.set_async(True)
+
+    def timed3_dense():
+        fn = lambda: ctx_dense.batch_recover(ids43, ev43, N_PARTIES, DEG, T_FAULTS, out=(rec, path, flags43))
+        fn()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record(stream)
+        for _ in range(3):
+            fn()
+        d1.record(stream)
+        assert ctx_dense.synchronize() == 0 and torch.equal(rec, coeffs)
+        return d0.elapsed_time(d1) / 3 * 1e-3
+
+    t_dense = timed3_dense()
+    ctx_dense.close()
 
     # ---- end-to-end leg: same calls with HOST (pinned) buffers, copies inside the timed region
     Be = 1 << args.log2_e2e_batch
@@ -398,15 +419,15 @@ def run_b200(args):
             "breakdown": {"gen_ms": 1e3 * t_gen / args.steps, "recon_ms": 1e3 * t_rec / args.steps,
                           "gen_shares_per_s": n_gpus * args.steps * B * N_PARTIES / t_gen, "recon_shares_per_s": n_gpus * args.steps * B * N_PARTIES / t_rec,
                           "alg_modmul_per_s": n_gpus * args.steps * B * (ALG_MODMUL_GEN + ALG_MODMUL_REC) / t_tot, "gather_ms": gather_ms,
-                          "recon_43_senders_ms": 1e3 * t_gen43, "recon_43_senders_dense_ms": 1e3 * t_dense, "robust_n128_t42": robust,
-                          "recon_note": "recon_ms: all 64 senders supplied -> inverse NTT + degree check (bit-identical; items that fail fall back to the dense check); recon_43_senders_ms: only d+t+1 senders supplied -> erasure-weighted inverse NTT + triangular recovery; recon_43_senders_dense_ms: same call with flags -> dense matvec_kernel"},
+                          "recon_43_senders_ms": 1e3 * t_gen43, "recon_43_senders_flags_ms": 1e3 * t_flags43, "recon_43_senders_dense_ms": 1e3 * t_dense, "robust_n128_t42": robust,
+                          "recon_note": "recon_ms: all 64 senders supplied -> inverse NTT + degree check (bit-identical; items that fail fall back to the dense check); recon_43_senders_ms: only d+t+1 senders supplied -> erasure-weighted inverse NTT + triangular recovery; recon_43_senders_flags_ms: same call with flags -> the erasure-weighted transform over all supplied senders, dense check only for chunks it rejects; recon_43_senders_dense_ms: the dense matvec_kernel on every chunk (HBMPC_NO_ER_FLAGS=1)"},
             "roofline": roof("ntt64_cta_kernel<1> (K3 batch_recover launch, all 64 senders: inverse 64-point NTT + degree check per chunk)", rec_alg_imad, rec_exec_wide,
                              rec_launch_s, B * (N_PARTIES * 32 + M * 32 + 5),
                              "achieved = algorithmic IMAD (B * 1430 modmul * 256, SURVEY 8d dense count) / CUDA-event launch time; peak = mad.lo.u32 probe measured in this run; executed_* = IMAD.WIDE actually issued vs the IMAD.WIDE probe",
                              "ntt_inv"),
             "roofline_gen": roof("ntt64_cta_kernel<0> (K1 compute_shares launch: zero-padded 64-point NTT per secret)", gen_alg_imad, gen_exec_wide, gen_launch_s, B * BYTES_GEN,
                                  "algorithmic IMAD = B * 1344 modmul * 256 (dense Horner count of SURVEY 8d)", "ntt_fwd"),
-            "roofline_dense": roof("matvec_kernel<4> (K3 batch_recover launch with flags, 43 senders: 43x22 check+coefficient matrix per chunk)", rec_alg_imad, dense_exec_wide, t_dense,
+            "roofline_dense": roof("matvec_kernel<4> (K3 dense check with flags, 43 senders: 43x22 check+coefficient matrix per chunk; the route of every chunk with a disagreeing share)", rec_alg_imad, dense_exec_wide, t_dense,
                                    B * (BYTES_REC + 8), "same algorithmic count, dense path", "matvec"),
             "cpu_baseline": cpu,
             "e2e": {"value": n_gpus * e2e_steps * 2 * Be * N_PARTIES / t_e2e, "unit": "shares/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

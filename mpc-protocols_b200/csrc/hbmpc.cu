@@ -188,6 +188,7 @@ struct RecoverTables {
     uint4 *itw = nullptr, *iscale = nullptr;
     // general optimistic check without flags: erasure-weighted inverse NTT + triangular coefficient recovery
     int er_logn = 0, er_zero_from = 0;
+    bool er_all = false;  // tables built over ALL supplied ids (calls with flags): a chunk that passes has every flag clear
     int *er_row_len = nullptr;
     uint4 *er_wt = nullptr, *er_tri = nullptr;
     std::vector<void *> allocs;  // device memory of this entry (freed when the entry is evicted)
@@ -213,6 +214,7 @@ struct hbmpc_ctx {
     size_t staged_min = 4096;                       // HBMPC_STAGED_MIN: failing sets of at least this many items use the staged decoder
     int staged_seg = 16;                            // HBMPC_STAGED_SEG: Berlekamp-Massey iterations between two re-sorts
     unsigned int *h_spec = nullptr;                 // pinned: failing-item count + per-sender error histogram of the scout pass
+    bool no_er_flags = false;                       // HBMPC_NO_ER_FLAGS=1: calls with flags on a sender subset go straight to the dense check
     bool no_fastpath = false;                       // HBMPC_NO_FASTPATH=1: K3 never takes the all-shares-present inverse-NTT path
     bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
     size_t chunk_bytes = 16u << 20;                 // HBMPC_CHUNK_MB: target bytes per pipelined host copy
@@ -304,6 +306,8 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
     {
         const char *fd = getenv("HBMPC_FORCE_DENSE");
         ctx->force_dense = fd && fd[0] == '1';
+        const char *ne = getenv("HBMPC_NO_ER_FLAGS");
+        ctx->no_er_flags = ne && ne[0] == '1';
         const char *nf = getenv("HBMPC_NO_FASTPATH");
         ctx->no_fastpath = nf && nf[0] == '1';
         const char *sx = getenv("HBMPC_SCAN_MAX");
@@ -907,9 +911,13 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
     // Zc(x) = prod_{k < N, k not in X} (x - w^k), the word y'_k = y_k*Zc(w^k) (k in X, zero elsewhere) is the evaluation
     // vector of Q = P_X*Zc where P_X interpolates the examined shares; deg P_X <= d  <=>  the coefficients N-t .. N-1 of
     // Q = INTT(y') vanish, and then P = Q*(N*Zc)^{-1} mod x^(d+1): a (d+1) x (d+1) triangular matrix.
-    if (!ctx->no_fastpath && !want_flags && T.fast_logn == 0 && N >= 2) {
+    // With flags the same transform runs over ALL S supplied ids (Zc over the ids that are absent): a chunk in which every supplied
+    // share lies on one degree-d polynomial has path 0 and no flag set; the others go to the dense check, which examines the prefix.
+    if (!ctx->no_fastpath && T.fast_logn == 0 && N >= 2 && !(want_flags && ctx->no_er_flags)) {
+        const size_t xcount = want_flags ? S : needed;
+        T.er_all = want_flags;
         std::vector<char> inX(N, 0);
-        for (size_t i = 0; i < needed; ++i) inX[sorted_ids[i]] = 1;
+        for (size_t i = 0; i < xcount; ++i) inX[sorted_ids[i]] = 1;
         std::vector<HFr> domN = domain_elements((size_t)N, (size_t)N);
         std::vector<HFr> Z(1, hfr::ONE);  // coefficients of Zc, low degree first
         for (int k = 0; k < N; ++k) {
@@ -947,7 +955,7 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
         if ((rc = upload_fr(ctx, wt, &T.er_wt, &T.allocs))) return rc;
         if ((rc = upload_fr(ctx, tri, &T.er_tri, &T.allocs))) return rc;
         if (!T.itw && (rc = get_inverse_twiddles(ctx, N, &T.itw, &T.iscale))) return rc;
-        T.er_zero_from = N - (int)t;
+        T.er_zero_from = N - (int)(xcount - m);  // deg Q <= d + N - |X|
         while ((1 << T.er_logn) < N) ++T.er_logn;
     }
     return 0;
@@ -1392,8 +1400,9 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             }
         }
 
-        const bool erasure = T.er_logn > 0 && !fastN;
-        if (erasure) {
+        const bool er_any = T.er_logn > 0 && !fastN, er_all = er_any && T.er_all;
+        const bool erasure = er_any && !er_all;   // the erasure check replaces the dense check (no flags wanted)
+        if (er_any) {
             void *tmp = nullptr;
             if ((rc = scratch_get(ctx, ln, 7, Bc * (size_t)T.mout * 32, &tmp))) return rc;
             NttArgs na{};
@@ -1406,11 +1415,11 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             na.cols = 1 << T.er_logn;
             na.n = 1 << T.er_logn;
             na.err = ctx->d_status;
-            na.in_map = P.er_in_map;
+            na.in_map = er_all ? P.in_map : P.er_in_map;
             na.wt = T.er_wt;
             na.m = T.er_zero_from;
             na.mout = T.mout;
-            na.fail = fail;
+            na.fail = er_all ? fail1 : fail;
             na.path = (int *)vp.dev;
             if ((rc = launch_ntt<2>(ctx, ln.stream, T.er_logn, na))) return rc;
             MatvecArgs tr{};
@@ -1424,9 +1433,14 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             tr.out_sb = T.mout; tr.out_sr = 1;
             tr.row_len = T.er_row_len;
             if ((rc = launch_matvec(ctx, ln, tr, 0))) return rc;
+            if (er_all) {  // like the all-points check: only the chunks it rejects see the dense check (which sets the flags)
+                compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail1, (long long)Bc, list1, count1);
+                ctx->launches++;
+                CK(cudaGetLastError());
+            }
         }
         MatvecArgs a{};
-        if (fastN) { a.item_list = dense_list; a.item_count = dense_count; }
+        if (fastN || er_all) { a.item_list = dense_list; a.item_count = dense_count; }
         a.M = T.M;
         a.in = (const uint4 *)vi.dev;
         a.out = (uint4 *)vc.dev;

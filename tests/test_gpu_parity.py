@@ -729,3 +729,37 @@ def test_persistent_attacker_speculation_is_exact(hb, orc, monkeypatch, n, t, S)
     finally:
         c.close()
         c_off.close()
+
+
+@pytest.mark.parametrize("n,t,S", [(16, 5, 13), (64, 21, 50), (100, 33, 100)])
+def test_flags_on_sender_subsets_both_routes(hb, orc, monkeypatch, n, t, S):
+    """Calls with flags on a sender subset: by default the erasure-weighted transform over ALL supplied senders settles the chunks in
+    which every share agrees (path 0, no flag) and only the others take the dense check; HBMPC_NO_ER_FLAGS=1 sends every chunk to
+    the dense check.  Both must equal the oracle: clean chunks, errors inside and beyond the examined prefix, > t errors."""
+    d = t
+    B = 600
+    rng = np.random.default_rng(n + S)
+    coeffs, shares = _codewords(orc, n, d, B, 0x5EED9000 + n + S)
+    ids = np.sort(rng.choice(n, size=S, replace=False))
+    arrival = rng.permutation(S)
+    words = shares[:, ids[arrival]]
+    nerr = np.where(rng.random(B) < 0.5, 0, rng.integers(1, t + 3, size=B))
+    bad = _corrupt(words, rng, np.minimum(nerr, S))
+    evals = np.ascontiguousarray(bad.transpose(1, 0, 2))
+    want = orc.batch_recover_secret(ids[arrival], evals, n, d, t, threads=orc.max_threads())
+    c0 = hb.Context(0)
+    monkeypatch.setenv("HBMPC_NO_ER_FLAGS", "1")
+    c1 = hb.Context(0)
+    try:
+        l0, l1 = c0.launch_count, c1.launch_count
+        _compare_recover(c0.batch_recover(ids[arrival], evals, n, d, t, want_flags=True), want, B)
+        _compare_recover(c1.batch_recover(ids[arrival], evals, n, d, t, want_flags=True), want, B)
+        assert c0.launch_count - l0 > c1.launch_count - l1, "the erasure-weighted check did not run ahead of the dense check"
+        w2 = orc.robust_interpolate_batch(ids[arrival], bad, n, d, t, threads=orc.max_threads())
+        for c in (c0, c1):
+            rc, co, sec, path, flags = c.robust_interpolate_batch(ids[arrival], bad, n, d, t, want_flags=True)
+            assert rc == w2["rc"] and np.array_equal(path, w2["path"]) and np.array_equal(co, w2["coeffs"])
+            assert np.array_equal(flags, w2["flags"][:, : flags.shape[1]])
+    finally:
+        c0.close()
+        c1.close()
