@@ -1,0 +1,39 @@
+"""Where does the staged decoder start to pay?  K4 on B codewords (all of them with errors, e ~ U{1..t}) and the honest call of the same
+size, with the compaction/staged route (HBMPC_SCAN_MAX small) and with the scan route (robust_kernel looks at the fail flags itself)."""
+import importlib, json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from bench import random_fr_device
+hb = importlib.import_module("mpc-protocols_b200")
+dev = torch.device("cuda", 0)
+def ctx_with(env):
+    os.environ.update(env)
+    c = hb.Context(0)
+    for k in env: del os.environ[k]
+    c.set_stream(torch.cuda.current_stream().cuda_stream)
+    return c
+routes = {"scan": ctx_with({"HBMPC_SCAN_MAX": str(1 << 30)}), "staged": ctx_with({"HBMPC_SCAN_MAX": "1024", "HBMPC_STAGED_MIN": "1024"})}
+out = {}
+for n, t in ((64, 21), (128, 42)):
+    for B in (2048, 4096, 8192, 16384, 32768, 65536):
+        coeffs = random_fr_device(torch, (B, t + 1), 5, dev)
+        shares = routes["scan"].compute_shares_batch(coeffs, n)
+        g = torch.Generator(device=dev); g.manual_seed(B)
+        e = torch.randint(1, t + 1, (B,), device=dev, generator=g)
+        rank = torch.rand((B, n), device=dev, generator=g).argsort(dim=1).argsort(dim=1)
+        bad = shares.clone(); bad[..., 0] = torch.where(rank < e[:, None], bad[..., 0] ^ 0x5A5A5, bad[..., 0])
+        ids = np.arange(n)
+        row = {}
+        for name, c in routes.items():
+            for label, words in (("attack", bad), ("honest", shares)):
+                o = c.robust_interpolate_batch(ids, words, n, t, t)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(5): o = c.robust_interpolate_batch(ids, words, n, t, t)
+                torch.cuda.synchronize()
+                row[f"{name}_{label}_us"] = round((time.perf_counter() - t0) / 5 * 1e6, 1)
+                assert torch.equal(o[1], coeffs)
+        out[f"n{n}_B{B}"] = row
+print(json.dumps(out, indent=1))
