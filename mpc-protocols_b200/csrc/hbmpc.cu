@@ -214,6 +214,7 @@ struct hbmpc_ctx {
     size_t staged_min = 4096;                       // HBMPC_STAGED_MIN: failing sets of at least this many items use the staged decoder
     int staged_seg = 16;                            // HBMPC_STAGED_SEG: Berlekamp-Massey iterations between two re-sorts
     unsigned int *h_spec = nullptr;                 // pinned: failing-item count + per-sender error histogram of the scout pass
+    bool attack_seen = false;                       // the last recovery calls met large failing sets: batches <= scan_max are compacted too
     bool no_er_flags = false;                       // HBMPC_NO_ER_FLAGS=1: calls with flags on a sender subset go straight to the dense check
     bool no_fastpath = false;                       // HBMPC_NO_FASTPATH=1: K3 never takes the all-shares-present inverse-NTT path
     bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
@@ -407,6 +408,10 @@ static int collect_status(hbmpc_ctx *ctx) {
     CK(cudaStreamSynchronize(ctx->main_stream()));
     volatile unsigned int *hs = ctx->h_status;
     const unsigned int bad = hs[0], undecodable = hs[2];
+    if (hs[1]) {  // robust_kernel met a densely failing batch in scan mode: the next recovery call counts its failing items
+        ctx->attack_seen = true;
+        hs[1] = 0;
+    }
     hs[0] = 0;
     hs[2] = 0;
     if (bad) return HBMPC_INVALID_INPUT;
@@ -1359,12 +1364,17 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         // Large failing sets of the all-points check (synchronous calls): straight to the staged decoder, which settles path 0
         // (errors beyond the examined prefix only), the OEC round and the flags from the error positions; only what it cannot
         // decode takes the dense check below.
+        // session-sized batches: no compaction pass -- the decoder's threads look at fail[] themselves and compute Lc*y; unless the
+        // context has just seen an attack (large failing sets): then the count is worth a synchronisation, because it opens the
+        // staged decoder
+        const bool scan = Bc <= ctx->scan_max && !lean_phase && !(ctx->attack_seen && !ctx->async && Bc >= 2048);
         bool staged_direct = false;
         unsigned int *dense_list = list1, *dense_count = count1;
-        if (fastN && T.fast && !ctx->async && Bc > ctx->scan_max) {
+        if (fastN && T.fast && !ctx->async && !scan) {
             CK(cudaMemcpyAsync(ctx->h_spec, count1, sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
             CK(cudaStreamSynchronize(ln.stream));
             const unsigned int c1 = ctx->h_spec[0];
+            if (Bc <= ctx->scan_max && c1 < ctx->staged_min / 2) ctx->attack_seen = false;  // the attack is over
             if (c1 >= ctx->staged_min && !ctx->no_staged_direct) {
                 // More than one wave of work: a few scouts first (hist_only: nothing is written).  When the same <= t senders
                 // are wrong in (almost) every scout, the persistent-attacker shortcut further down (dense interpolation from the
@@ -1459,8 +1469,6 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         a.flags = want_flags ? (unsigned long long *)vf.dev : nullptr;
         if (!erasure && (rc = launch_matvec(ctx, ln, a, fw))) return rc;
 
-        // session-sized batches: no compaction pass -- the decoder's threads look at fail[] themselves and compute Lc*y
-        const bool scan = Bc <= ctx->scan_max && !lean_phase;
         if (!scan) {
             compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail, (long long)Bc, list, count);
             ctx->launches++;
@@ -1489,6 +1497,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             return chunk_commit(ctx, ln, bp, b0, Bc, vp);
         }
         r.fail_scan = scan ? fail : nullptr;
+        r.dense_fail_flag = (scan && !ctx->async && Bc >= 2048) ? ctx->d_status + 1 : nullptr;
         r.need_lc = (scan && erasure) ? 1 : 0;
         void *ws = nullptr;
         if ((rc = scratch_get(ctx, ln, 6, (size_t)blocks * threads * lay.total * 32 + 64, &ws))) return rc;
@@ -1517,6 +1526,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             CK(cudaMemcpyAsync(ctx->h_spec, count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
             CK(cudaStreamSynchronize(ln.stream));
             cnt_host = ctx->h_spec[0];
+            if (Bc <= ctx->scan_max && cnt_host < ctx->staged_min / 2 && !staged_direct) ctx->attack_seen = false;  // the attack is over
         }
         if (cnt_host != UINT_MAX && !ctx->no_speculation) {
             const unsigned int cnt = cnt_host;

@@ -77,6 +77,7 @@ struct RobustArgs {
     unsigned int *fail_any;     // set to 1 when any item fails to decode
     uint4 *ws;                  // workspace: ws_elems Fr per thread, strided by total thread count
     int ws_elems;
+    unsigned int *dense_fail_flag;  // scan mode: set to 1 when some warp finds at least half of its items failing
     int hist_only;              // scout pass ahead of any other stage: only the per-sender error histogram is updated
     int skip_coeffs;            // staged decoder, all N points supplied: the coefficients are corrected by a transform afterwards
 };
@@ -538,7 +539,13 @@ __global__ void __launch_bounds__(128, HB_ROBUST_MINB) robust_kernel(const Robus
     int rootpos[HB_ROBUST_MAXT];
 
     for (size_t idx = g + (a.fail_scan ? 0 : a.list_first); idx < cnt; idx += T) {
-        if (a.fail_scan && !a.fail_scan[idx]) continue;
+        if (a.fail_scan) {
+            const bool mine = a.fail_scan[idx] != 0;
+            // half of a warp's items failing in a batch that was not compacted: tell the host (mapped word, plain store), so that
+            // the next call of this context counts its failing items and can take the staged decoder (attacks persist)
+            if (a.dense_fail_flag && __popc(__ballot_sync(__activemask(), mine)) >= 16) *(volatile unsigned int *)a.dense_fail_flag = 1u;
+            if (!mine) continue;
+        }
         const long long b = a.fail_scan ? (long long)idx : (long long)a.list[idx];
         int L = -1, path = -8, used_att = -1;
         if (a.fast) {

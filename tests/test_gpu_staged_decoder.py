@@ -204,3 +204,36 @@ def test_staged_after_speculation(staged_ctx, orc):
             for p in bad_senders:
                 words[b, p, 0] ^= np.uint64(rng.integers(1, 1 << 30))
     _check_all_entry_points(c, orc, np.arange(n), words, n, d, t)
+
+
+def test_mid_size_batches_switch_to_the_staged_decoder_under_attack(hb, orc):
+    """Batches below HBMPC_SCAN_MAX are not compacted (no host-visible failing count), so the first attacked call decodes with
+    robust_kernel; it reports the densely failing batch, and the next calls of the context count their failing items and take the
+    staged decoder, until a call finds (almost) nothing to decode.  Every call equals the oracle whatever the route."""
+    n, t, d, B = 16, 5, 5, 6000
+    rng = np.random.default_rng(2024)
+    coeffs, shares = _codewords(orc, n, d, B, 0x5EED7400)
+    bad = _corrupt(shares, rng, rng.integers(1, t + 1, size=B))
+    ids = np.arange(n)
+    want_bad = orc.robust_interpolate_batch(ids, bad, n, d, t, threads=orc.max_threads())
+    c = hb.Context(0)
+    try:
+        def call(words, want=None):
+            l0 = c.launch_count
+            rc, co, sec, path, flags = c.robust_interpolate_batch(ids, words, n, d, t, want_flags=True)
+            if want is not None:
+                assert rc == want["rc"] and np.array_equal(path, want["path"]) and np.array_equal(co, want["coeffs"])
+                assert np.array_equal(flags, want["flags"][:, : flags.shape[1]])
+            else:
+                assert rc == 0 and not path.any() and np.array_equal(co, coeffs)
+            return c.launch_count - l0
+        honest0 = call(shares)
+        first = call(bad, want_bad)          # scan route: robust_kernel, few launches
+        second = call(bad, want_bad)         # the context has seen the attack: compaction + staged decoder
+        third = call(bad, want_bad)
+        assert second >= first + 8 and third == second, (honest0, first, second, third)
+        after = call(shares)                 # counted, nothing to decode: the attack is over
+        honest1 = call(shares)
+        assert honest1 == honest0 and after >= honest0, (honest0, after, honest1)
+    finally:
+        c.close()
