@@ -661,6 +661,8 @@ int orc_gao_rs_decode(size_t n, size_t k, const uint64_t *received /*[n]*/, cons
 int orc_lagrange_interpolate(size_t k, const uint64_t *xs, const uint64_t *ys, uint64_t *coeffs_out /*[k]*/, size_t *coeff_len) {
     if (k > MAXN) return ORC_INVALID_INPUT;
     fr x[MAXN], y[MAXN];
+    memset(x, 0, sizeof x);
+    memset(y, 0, sizeof y);
     for (size_t i = 0; i < k; ++i) if (!fr_from_canon(xs + 4 * i, &x[i]) || !fr_from_canon(ys + 4 * i, &y[i])) return ORC_INVALID_INPUT;
     poly *p = (poly *)malloc(sizeof(poly));
     int rc = lagrange_interpolate(x, y, (int)k, p);
