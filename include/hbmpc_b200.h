@@ -133,6 +133,10 @@ int hbmpc_pack_share_records(hbmpc_ctx *ctx, size_t count, const uint64_t *value
  * 1 = IMAD.WIDE.U32(.X) carry chains (the 32x32->64 multiply-add the product kernels issue), 2 = DFMA (FP64 pipe). */
 int hbmpc_measure_imad_peak(hbmpc_ctx *ctx, int variant, double *giga_inst_per_s, double *elapsed_ms);
 
+/* Latency probe behind the kernels' occupancy choices: `chains` (1, 2, 4, 8) independent serial IMAD.WIDE.U32.X carry chains per
+ * thread at `warps_per_smsp` (1 .. 16) resident warps per SM sub-partition; returns 1e9 thread-level multiply-adds per second. */
+int hbmpc_measure_wide_chains(hbmpc_ctx *ctx, int chains, int warps_per_smsp, double *giga_inst_per_s);
+
 #ifdef __cplusplus
 }
 #endif

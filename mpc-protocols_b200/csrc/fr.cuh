@@ -36,6 +36,15 @@ namespace hb {
 #define HB_R5 0x3339d808u
 #define HB_R6 0x299d7d48u
 #define HB_R7 0x73eda753u
+// modulus limbs as PTX immediates (PTX does not accept the C "u" suffix)
+#define HB_PR0 "0x00000001"
+#define HB_PR1 "0xffffffff"
+#define HB_PR2 "0xfffe5bfe"
+#define HB_PR3 "0x53bda402"
+#define HB_PR4 "0x09a1d805"
+#define HB_PR5 "0x3339d808"
+#define HB_PR6 "0x299d7d48"
+#define HB_PR7 "0x73eda753"
 // -r^{-1} mod 2^32 == 0xffffffff  =>  Montgomery quotient digit m = -T[i] mod 2^32 (no multiply)
 
 struct fr_t {
@@ -221,29 +230,97 @@ HB_DEV bool geq_mod(const uint32_t (&x)[8]) {
     mod_limbs(r);
     return sub8(d, x, r) == 0;
 }
-// x in [0, 2r) -> x mod r
-HB_DEV void cond_sub_mod(uint32_t (&x)[8]) {
-    uint32_t r[8], d[8];
+// x in [0, 2r) -> x mod r, exact.  The decision is taken on the top limb alone: x_7 > r_7 means x >= (r_7 + 1)*2^224 > r (subtract),
+// x_7 < r_7 means x < r (keep); only x_7 == r_7 (one value in 2^31 for the pseudo-random values of this path) needs the full-width
+// comparison, behind a branch that is practically never taken.  One compare + 8 predicated subtractions on the ALU pipe instead of
+// 8 subtractions, a borrow capture and 8 selects (which ptxas lowers to MOV / IMAD.MOV, the latter on the multiplier pipe).
+#if defined(__CUDACC__)
+#define HB_DEV_COLD __device__ __noinline__
+#else
+#define HB_DEV_COLD static
+#endif
+HB_DEV_COLD void cond_sub_mod_slow(uint32_t *x) {  // out of line: one copy of the rare path per kernel
+    uint32_t r[8], d[8], v[8];
     mod_limbs(r);
-    uint32_t br = sub8(d, x, r);
+    for (int i = 0; i < 8; ++i) v[i] = x[i];
+    uint32_t br = sub8(d, v, r);
     if (!br) {
-#pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = d[i];
     }
+}
+HB_DEV void cond_sub_mod(uint32_t (&x)[8]) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.gt.u32 p, %7, " HB_PR7 ";\n\t"
+        "@p sub.cc.u32 %0, %0, " HB_PR0 ";\n\t"
+        "@p subc.cc.u32 %1, %1, " HB_PR1 ";\n\t"
+        "@p subc.cc.u32 %2, %2, " HB_PR2 ";\n\t"
+        "@p subc.cc.u32 %3, %3, " HB_PR3 ";\n\t"
+        "@p subc.cc.u32 %4, %4, " HB_PR4 ";\n\t"
+        "@p subc.cc.u32 %5, %5, " HB_PR5 ";\n\t"
+        "@p subc.cc.u32 %6, %6, " HB_PR6 ";\n\t"
+        "@p subc.u32 %7, %7, " HB_PR7 ";\n\t"
+        "}"
+        : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]));
+    // after a subtraction x_7 < r_7 (x < 2r), so this test only fires for inputs with x_7 == r_7
+    if (__builtin_expect(x[7] == HB_R7, 0)) {
+        uint32_t tmp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tmp[i] = x[i];
+        cond_sub_mod_slow(tmp);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = tmp[i];
+    }
+#else
+    if (x[7] > HB_R7) {
+        uint32_t r[8], d[8];
+        mod_limbs(r);
+        sub8(d, x, r);
+        for (int i = 0; i < 8; ++i) x[i] = d[i];
+    }
+    if (x[7] == HB_R7) cond_sub_mod_slow(x);
+#endif
 }
 HB_DEV void fr_add(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
     add8(d, a, b);  // a,b < r < 2^255: no carry out
     cond_sub_mod(d);
 }
+// a, b < r < 2^255: the 256-bit difference is negative exactly when its top bit is set (no borrow capture needed)
 HB_DEV void fr_sub(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "sub.cc.u32 %0, %8, %16;\n\t"
+        "subc.cc.u32 %1, %9, %17;\n\t"
+        "subc.cc.u32 %2, %10, %18;\n\t"
+        "subc.cc.u32 %3, %11, %19;\n\t"
+        "subc.cc.u32 %4, %12, %20;\n\t"
+        "subc.cc.u32 %5, %13, %21;\n\t"
+        "subc.cc.u32 %6, %14, %22;\n\t"
+        "subc.u32 %7, %15, %23;\n\t"
+        "setp.lt.s32 p, %7, 0;\n\t"
+        "@p add.cc.u32 %0, %0, " HB_PR0 ";\n\t"
+        "@p addc.cc.u32 %1, %1, " HB_PR1 ";\n\t"
+        "@p addc.cc.u32 %2, %2, " HB_PR2 ";\n\t"
+        "@p addc.cc.u32 %3, %3, " HB_PR3 ";\n\t"
+        "@p addc.cc.u32 %4, %4, " HB_PR4 ";\n\t"
+        "@p addc.cc.u32 %5, %5, " HB_PR5 ";\n\t"
+        "@p addc.cc.u32 %6, %6, " HB_PR6 ";\n\t"
+        "@p addc.u32 %7, %7, " HB_PR7 ";\n\t"
+        "}"
+        : "=&r"(d[0]), "=&r"(d[1]), "=&r"(d[2]), "=&r"(d[3]), "=&r"(d[4]), "=&r"(d[5]), "=&r"(d[6]), "=&r"(d[7])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]), "r"(b[1]),
+          "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
     uint32_t br = sub8(d, a, b);
     if (br) {
         uint32_t r[8], e[8];
         mod_limbs(r);
         add8(e, d, r);
-#pragma unroll
         for (int i = 0; i < 8; ++i) d[i] = e[i];
     }
+#endif
 }
 HB_DEV bool fr_eq(const uint32_t (&a)[8], const uint32_t (&b)[8]) {
     uint32_t x = 0;
@@ -340,15 +417,6 @@ HB_DEV void mont_mul_acc(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_
 // and shifts by one limb by swapping the roles of the two arrays.  ~30 live registers instead of the ~50 of the lazy
 // 512-bit accumulator, so kernels built on it keep twice as many warps resident.  Inputs < 2^256 with a*b < r*2^256.
 // ----------------------------------------------------------------------------------------------
-// modulus limbs as PTX immediates (PTX does not accept the C "u" suffix)
-#define HB_PR0 "0x00000001"
-#define HB_PR1 "0xffffffff"
-#define HB_PR2 "0xfffe5bfe"
-#define HB_PR3 "0x53bda402"
-#define HB_PR4 "0x09a1d805"
-#define HB_PR5 "0x3339d808"
-#define HB_PR6 "0x299d7d48"
-#define HB_PR7 "0x73eda753"
 // row i >= 1:  (E: current even lanes with E0 == 0, O: current odd lanes)  ->  roles swapped (E holds the new odd lanes)
 HB_DEV void cios_row(unsigned long long &e0, unsigned long long &e1, unsigned long long &e2, unsigned long long &e3,
                      unsigned long long &o0, unsigned long long &o1, unsigned long long &o2, unsigned long long &o3,

@@ -16,6 +16,7 @@
 #include "fr.cuh"
 #include "matvec.cuh"
 #include "ntt.cuh"
+#include "ntt16x.cuh"
 #include "robust.cuh"
 #include "tables.hpp"
 
@@ -152,6 +153,34 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(unsigned int *sink, uns
     }
 }
 
+// Latency probe of the multi-limb multiply-add: CH independent carry chains per thread (each a serial IMAD.WIDE.U32.X chain, as one
+// row of a Montgomery product is), launched at a chosen number of resident warps per SM sub-partition.  Tells how much
+// instruction-level parallelism x occupancy a product kernel needs before the multiplier pipe, not the chain latency, is the bound.
+template <int CH>
+__global__ void __launch_bounds__(128) wide_chain_probe_kernel(unsigned int *sink, unsigned int seed, int iters) {
+    unsigned long long l[CH][4];
+    unsigned int k = 0, m1 = seed * 77u + 5u;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) l[c][i] = (unsigned long long)(threadIdx.x * 2654435761u + i + 4 * c) << 7;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+                chain4w(l[c][0], l[c][1], l[c][2], l[c][3], k, (unsigned int)l[c][3], (unsigned int)l[c][2], (unsigned int)l[c][1], (unsigned int)l[c][0], m1 + u);
+        }
+    }
+    unsigned long long s = k;
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s ^= l[c][i];
+    if (s == 0x12345ull) sink[0] = (unsigned int)s;
+}
+
 }  // namespace hb
 
 // ------------------------------------------------------------------------------------------------ context
@@ -194,6 +223,38 @@ struct RecoverTables {
     std::vector<void *> allocs;  // device memory of this entry (freed when the entry is evicted)
 };
 
+// a10 tables of one (n, deg, id SET): rows over the ids in ascending order; arrival order enters through per-call maps
+struct NonRobustTables {
+    uint4 *M = nullptr;
+    int *chk_map = nullptr;
+    int R = 0, n_chk = 0;
+    // every domain point supplied (S == n == N): interpolation through all points is one inverse NTT
+    int fast_logn = 0;
+    uint4 *itw = nullptr, *iscale = nullptr;
+    std::vector<void *> allocs;  // device memory of this entry (freed when the entry is evicted)
+};
+
+// Cache key of the constant tables of one (n, d, t, id SET, variant): the set is a 256-bit bitmap, so building and comparing a
+// key costs a few words per call (arrival order is not part of it: it only changes the small per-call index maps).
+struct TableKey {
+    uint32_t kind = 0, n = 0, d = 0, t = 0;  // kind: bit0 flags wanted, bit1 secrets only, bit2 non-robust (a10) tables
+    uint64_t idset[4] = {0, 0, 0, 0};
+    bool operator<(const TableKey &o) const { return memcmp(this, &o, sizeof(TableKey)) < 0; }
+};
+static_assert(sizeof(TableKey) == 48, "TableKey must not contain padding (it is compared with memcmp)");
+
+// Per-call index maps (arrival order -> sorted position and back) travel through a small ring of pinned host blocks, each with
+// its own device block: the copy is a true asynchronous DMA from pinned memory, and a block is only refilled after the copy
+// that read it has completed (event per block).  Device blocks are reused in stream order.
+struct MapRing {
+    static const int SLOTS = 8, INTS = 2048;
+    int *h[SLOTS] = {};
+    int *d[SLOTS] = {};
+    cudaEvent_t ev[SLOTS] = {};
+    bool used[SLOTS] = {};
+    int next = 0;
+};
+
 struct hbmpc_ctx {
     int device = 0;
     Lane lanes[NLANES];
@@ -205,6 +266,8 @@ struct hbmpc_ctx {
     int matvec_regs = 0;
     int ntt_ctas[6][9] = {};
     int ntt64_ctas[2] = {};                         // resident CTAs per SM of ntt64_cta_kernel<MODE>
+    int ntt16x_ctas[3][8] = {};                     // resident CTAs per SM of ntt16x_kernel<LOGN, MODE>
+    long long ntt16x_min = 16384;                   // HBMPC_NTT16X: 0 never use ntt16x_kernel, 2 use it for every batch size (tests); default: batches >= 16384
     bool ntt_cta = true;                            // HBMPC_NTT_CTA=0: never use ntt64_cta_kernel; 2: use it for every 64-point transform of any size
     bool ntt_cta_all = false;
     long long ntt_cta_min = 1024;                        // resident CTAs per SM of ntt_kernel<LOGN, MODE>
@@ -227,10 +290,11 @@ struct hbmpc_ctx {
     unsigned int *h_counts = nullptr;  // pinned: per-chunk count of items that failed the optimistic check (lean host path)
     size_t h_counts_cap = 0;
     std::map<std::string, uint4 *> matrices;          // Vandermonde / twiddle tables keyed by "V n cols" / "W N"
-    std::map<std::string, RecoverTables> recover;     // keyed by (n, d, t, ids, variant)
-    std::map<std::string, struct NonRobustTables> *nonrobust = nullptr;
+    std::map<TableKey, RecoverTables> recover;        // keyed by (n, d, t, id set, variant); bounded (256 entries)
+    std::map<TableKey, struct NonRobustTables> *nonrobust = nullptr;   // same for the a10 tables
     std::vector<void *> owned;                        // device allocations freed at destroy
-    DevBuf maps;                                      // per-call arrival-order index maps (order, col_map, chk_map, in_map)
+    MapRing maps;                                     // per-call arrival-order index maps (order, col_map, chk_map, in_map)
+    unsigned int deferred_bad = 0, deferred_undec = 0;  // async mode: status of earlier enqueue-only calls, reported by hbmpc_ctx_synchronize
     cudaStream_t main_stream() const { return lanes[0].stream; }
 };
 
@@ -276,8 +340,33 @@ static int upload(hbmpc_ctx *ctx, const std::vector<T> &v, T **out, std::vector<
     size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
     CK(cudaMalloc(&p, bytes));
     (owner ? *owner : ctx->owned).push_back(p);
-    if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (!v.empty()) {
+        // the consumers run on non-blocking streams that are not ordered against the legacy stream of a plain cudaMemcpy (which
+        // may return before a pageable copy has landed): copy on the context's stream and wait for it -- tables are built once
+        CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->main_stream()));
+        CK(cudaStreamSynchronize(ctx->main_stream()));
+    }
     *out = (T *)p;
+    return 0;
+}
+
+// one block of the per-call map ring: fills it through `fill(int *host)` (returns the number of ints) and enqueues the copy
+template <typename Fill>
+static int maps_upload(hbmpc_ctx *ctx, Fill fill, const int **dev) {
+    MapRing &r = ctx->maps;
+    const int i = r.next;
+    r.next = (r.next + 1) % MapRing::SLOTS;
+    if (!r.h[i]) {
+        CK(cudaMallocHost((void **)&r.h[i], MapRing::INTS * sizeof(int)));
+        CK(cudaMalloc((void **)&r.d[i], MapRing::INTS * sizeof(int)));
+        CK(cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming));
+    }
+    if (r.used[i]) CK(cudaEventSynchronize(r.ev[i]));
+    const size_t count = fill(r.h[i]);
+    CK(cudaMemcpyAsync(r.d[i], r.h[i], count * sizeof(int), cudaMemcpyHostToDevice, ctx->main_stream()));
+    CK(cudaEventRecord(r.ev[i], ctx->main_stream()));
+    r.used[i] = true;
+    *dev = r.d[i];
     return 0;
 }
 
@@ -317,6 +406,8 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
         ctx->no_speculation = ns && ns[0] == '1';
         const char *nc = getenv("HBMPC_NTT_CTA");
         if (nc) { ctx->ntt_cta = nc[0] == '1' || nc[0] == '2'; if (nc[0] == '2') { ctx->ntt_cta_min = 1; ctx->ntt_cta_all = true; } }
+        const char *nx = getenv("HBMPC_NTT16X");
+        if (nx) ctx->ntt16x_min = nx[0] == '0' ? LLONG_MAX : (nx[0] == '2' ? 1 : ctx->ntt16x_min);
         const char *nd = getenv("HBMPC_NO_STAGED_DIRECT");
         ctx->no_staged_direct = nd && nd[0] == '1';
         const char *sm = getenv("HBMPC_STAGED_MIN");
@@ -374,11 +465,18 @@ extern "C" void hbmpc_ctx_destroy(hbmpc_ctx *ctx) {
         for (auto &b : ln.scratch)
             if (b.p) cudaFree(b.p);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
-    if (ctx->maps.p) cudaFree(ctx->maps.p);
+    for (int i = 0; i < MapRing::SLOTS; ++i) {
+        if (ctx->maps.h[i]) cudaFreeHost(ctx->maps.h[i]);
+        if (ctx->maps.d[i]) cudaFree(ctx->maps.d[i]);
+        if (ctx->maps.ev[i]) cudaEventDestroy(ctx->maps.ev[i]);
+    }
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_spec) cudaFreeHost(ctx->h_spec);
     note_destroy_error("host buffers");
     if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
+    if (ctx->nonrobust)
+        for (auto &e : *ctx->nonrobust)
+            for (void *q : e.second.allocs) cudaFree(q);
     delete ctx->nonrobust;
     for (int i = 0; i < NLANES; ++i)
         if (ctx->lanes[i].stream && (i > 0 || ctx->own_stream)) cudaStreamDestroy(ctx->lanes[i].stream);
@@ -402,27 +500,64 @@ extern "C" int hbmpc_ctx_set_async(hbmpc_ctx *ctx, int async) {
     return HBMPC_SUCCESS;
 }
 
-// reads the device status words, folds them into a ShareErrorCode and clears them (all lanes must be quiescent or
-// ordered before the main stream)
-static int collect_status(hbmpc_ctx *ctx) {
+// Device status words (mapped pinned memory): [0] non-canonical input seen, [1] densely failing batch seen by robust_kernel in
+// scan mode, [2] some item failed to decode.  read_status waits for the context's stream, reads and clears them.
+static int read_status(hbmpc_ctx *ctx, unsigned int &bad, unsigned int &undec) {
     CK(cudaStreamSynchronize(ctx->main_stream()));
     volatile unsigned int *hs = ctx->h_status;
-    const unsigned int bad = hs[0], undecodable = hs[2];
-    if (hs[1]) {  // robust_kernel met a densely failing batch in scan mode: the next recovery call counts its failing items
+    bad = hs[0];
+    undec = hs[2];
+    if (hs[1]) {  // the next recovery call counts its failing items (staged decoder)
         ctx->attack_seen = true;
         hs[1] = 0;
     }
     hs[0] = 0;
     hs[2] = 0;
+    return 0;
+}
+// status of the call that has just been enqueued and awaited (synchronous calls, calls with host buffers)
+static int collect_status(hbmpc_ctx *ctx) {
+    unsigned int bad = 0, undec = 0;
+    int rc = read_status(ctx, bad, undec);
+    if (rc) return rc;
     if (bad) return HBMPC_INVALID_INPUT;
-    if (undecodable) return HBMPC_DECODING_ERROR;
+    if (undec) return HBMPC_DECODING_ERROR;
     return HBMPC_SUCCESS;
+}
+// asynchronous mode: what the status words hold BEFORE a call with host buffers starts belongs to the enqueue-only calls issued
+// earlier; it is kept for hbmpc_ctx_synchronize instead of being reported by (and blamed on) the host-buffer call
+static int fold_deferred(hbmpc_ctx *ctx) {
+    unsigned int bad = 0, undec = 0;
+    int rc = read_status(ctx, bad, undec);
+    if (rc) return rc;
+    ctx->deferred_bad |= bad;
+    ctx->deferred_undec |= undec;
+    return 0;
+}
+// a call that failed half-way (CUDA error, allocation failure): nothing it left in the status words may surface in a later call
+static int abandon_call(hbmpc_ctx *ctx, int rc) {
+    for (auto &ln : ctx->lanes)
+        if (ln.stream) cudaStreamSynchronize(ln.stream);
+    cudaGetLastError();
+    volatile unsigned int *hs = ctx->h_status;
+    hs[0] = 0;
+    hs[1] = 0;
+    hs[2] = 0;
+    return rc;
 }
 
 extern "C" int hbmpc_ctx_synchronize(hbmpc_ctx *ctx) {
     if (!ctx) return HBMPC_INVALID_INPUT;
     cudaSetDevice(ctx->device);
-    return collect_status(ctx);
+    unsigned int bad = 0, undec = 0;
+    int rc = read_status(ctx, bad, undec);
+    if (rc) return rc;
+    bad |= ctx->deferred_bad;
+    undec |= ctx->deferred_undec;
+    ctx->deferred_bad = ctx->deferred_undec = 0;
+    if (bad) return HBMPC_INVALID_INPUT;
+    if (undec) return HBMPC_DECODING_ERROR;
+    return HBMPC_SUCCESS;
 }
 
 extern "C" uint64_t hbmpc_ctx_launch_count(const hbmpc_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -510,8 +645,12 @@ template <typename Body>
 static int run_batched(hbmpc_ctx *ctx, size_t B, bool any_host, size_t max_item_bytes, Body body, bool collect = true) {
     if (!any_host) {
         int rc = body(ctx->lanes[0], (size_t)0, B);
-        if (rc) return rc;
+        if (rc) return abandon_call(ctx, rc);
         return ctx->async ? HBMPC_SUCCESS : collect_status(ctx);
+    }
+    if (ctx->async) {
+        int rc = fold_deferred(ctx);
+        if (rc) return rc;
     }
     const size_t Bc = pick_chunk(ctx, B, max_item_bytes);
     CK(cudaEventRecord(ctx->ev_main, ctx->main_stream()));
@@ -529,7 +668,7 @@ static int run_batched(hbmpc_ctx *ctx, size_t B, bool any_host, size_t max_item_
             rc = HBMPC_CUDA_ERROR;
         }
     }
-    if (rc) return rc;
+    if (rc) return abandon_call(ctx, rc);
     return collect ? collect_status(ctx) : HBMPC_SUCCESS;
 }
 
@@ -626,8 +765,37 @@ static int launch_ntt64_cta(hbmpc_ctx *ctx, cudaStream_t st, const NttArgs &a) {
     CK(cudaGetLastError());
     return 0;
 }
+template <int LOGN, int MODE>
+static int launch_ntt16x_t(hbmpc_ctx *ctx, cudaStream_t st, const NttArgs &a) {
+    const size_t smem = ntt16x_smem_bytes<LOGN, MODE>();
+    int &ctas = ctx->ntt16x_ctas[MODE][LOGN];
+    if (ctas == 0) {
+        CK(cudaFuncSetAttribute(ntt16x_kernel<LOGN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ntt16x_kernel<LOGN, MODE>, NTT16X_WARPS * 32, smem));
+        ctas = nb > 0 ? nb : 1;
+    }
+    const int ipc = NTT16X_WARPS * (32 >> (LOGN - 4));
+    const long long ntiles = (a.B + ipc - 1) / ipc;
+    const long long grid = std::min<long long>(ntiles, (long long)ctx->num_sms * ctas);
+    ntt16x_kernel<LOGN, MODE><<<(unsigned)grid, NTT16X_WARPS * 32, smem, st>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
 template <int MODE>
 static int launch_ntt(hbmpc_ctx *ctx, cudaStream_t st, int logn, const NttArgs &a) {
+    if constexpr (MODE <= 2) {
+        // large batches of 16..128-point transforms: the barrier-free single-product-site kernel (ntt16x.cuh)
+        if (logn >= 4 && logn <= 7 && a.B >= ctx->ntt16x_min && !a.item_list && !a.out_group32 && a.cols <= (1 << logn)) {
+            switch (logn) {
+                case 4: return launch_ntt16x_t<4, MODE>(ctx, st, a);
+                case 5: return launch_ntt16x_t<5, MODE>(ctx, st, a);
+                case 6: return launch_ntt16x_t<6, MODE>(ctx, st, a);
+                case 7: return launch_ntt16x_t<7, MODE>(ctx, st, a);
+            }
+        }
+    }
     if constexpr (MODE == 0 || MODE == 1) {
         // measured (profiles/r01i_*): the CTA-cooperative kernel wins where whole warps can skip products -- zero-padded inputs
         // (share generation: 22 or 43 coefficients of 64... up to half the domain) and the inverse transform; the full-width
@@ -798,8 +966,9 @@ extern "C" int hbmpc_apply_matrix_batch(hbmpc_ctx *ctx, size_t rows, size_t cols
     void *dM = nullptr;
     int rc = scratch_get(ctx, ctx->lanes[0], 9, w.size() * 4, &dM);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->main_stream()));  // a previous async call may still read the old matrix
-    CK(cudaMemcpy(dM, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    // stream-ordered after earlier calls that may still read the old matrix; w is pageable and freed on return, so wait for the copy
+    CK(cudaMemcpyAsync(dM, w.data(), w.size() * 4, cudaMemcpyHostToDevice, ctx->main_stream()));
+    CK(cudaStreamSynchronize(ctx->main_stream()));
     return apply_map(ctx, (const uint4 *)dM, nullptr, 0, rows, cols, B, in, out, recipient_major);
 }
 
@@ -1213,9 +1382,10 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
     cudaSetDevice(ctx->device);
 
     const bool want_flags = flags != nullptr;
-    std::string key = "R " + std::to_string(n) + " " + std::to_string(d) + " " + std::to_string(t) + (want_flags ? " f" : " -") +
-                      (secrets_only ? " s" : " c");
-    for (size_t i = 0; i < S; ++i) key += " " + std::to_string(sorted_ids[i]);  // the field tables depend on the id SET only
+    TableKey key;
+    key.kind = (want_flags ? 1u : 0u) | (secrets_only ? 2u : 0u);
+    key.n = (uint32_t)n; key.d = (uint32_t)d; key.t = (uint32_t)t;
+    for (size_t i = 0; i < S; ++i) key.idset[ids[i] >> 6] |= 1ull << (ids[i] & 63);  // the field tables depend on the id SET only
     auto it = ctx->recover.find(key);
     if (it == ctx->recover.end()) {
         if (ctx->recover.size() >= 256) {  // bounded cache: sender sets differ from session to session
@@ -1226,7 +1396,10 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         }
         RecoverTables T;
         int rc = build_recover_tables(ctx, n, d, t, S, sorted_ids, want_flags, secrets_only, T);
-        if (rc) return rc;
+        if (rc) {
+            for (void *q : T.allocs) cudaFree(q);
+            return abandon_call(ctx, rc);
+        }
         it = ctx->recover.emplace(key, T).first;
     }
     const RecoverTables &T = it->second;
@@ -1234,27 +1407,17 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
     struct { const int *order, *col_map, *chk_map, *in_map, *er_in_map; } P{};
     {
         const int N = domain_size(n);
-        std::vector<int> blk;
-        blk.reserve(2 * S + 2 * (size_t)N + 8);
-        blk.insert(blk.end(), order.begin(), order.end());                               // [0, S): order; col_map = its first m entries
-        const size_t off_in = blk.size();
-        std::vector<int> in_map((size_t)N, -1), er_map((size_t)N, -1);
-        for (size_t i = 0; i < S; ++i) in_map[sorted_ids[i]] = order[i];
-        for (size_t i = 0; i < needed; ++i) er_map[sorted_ids[i]] = order[i];
-        blk.insert(blk.end(), in_map.begin(), in_map.end());
-        const size_t off_er = blk.size();
-        blk.insert(blk.end(), er_map.begin(), er_map.end());
-        const size_t bytes = blk.size() * sizeof(int);
-        if (ctx->maps.cap < bytes) {
-            CK(cudaStreamSynchronize(ctx->main_stream()));
-            if (ctx->maps.p) CK(cudaFree(ctx->maps.p));
-            ctx->maps.p = nullptr;
-            CK(cudaMalloc(&ctx->maps.p, bytes + 4096));
-            ctx->maps.cap = bytes + 4096;
-        }
-        // pageable source: the runtime stages the bytes before returning, stream order protects kernels of earlier calls
-        CK(cudaMemcpyAsync(ctx->maps.p, blk.data(), bytes, cudaMemcpyHostToDevice, ctx->main_stream()));
-        const int *base = (const int *)ctx->maps.p;
+        const size_t off_in = S, off_er = S + (size_t)N;
+        const int *base = nullptr;
+        int rc = maps_upload(ctx, [&](int *blk) -> size_t {
+            for (size_t i = 0; i < S; ++i) blk[i] = order[i];                  // [0, S): order; col_map = its first m entries
+            int *in_map = blk + off_in, *er_map = blk + off_er;
+            for (int k = 0; k < 2 * N; ++k) in_map[k] = -1;
+            for (size_t i = 0; i < S; ++i) in_map[sorted_ids[i]] = order[i];
+            for (size_t i = 0; i < needed; ++i) er_map[sorted_ids[i]] = order[i];
+            return S + 2 * (size_t)N;
+        }, &base);
+        if (rc) return abandon_call(ctx, rc);
         P.order = base;
         P.col_map = base;            // column c of the optimistic matrix reads the share of sorted position c
         P.chk_map = base + m;        // check row r compares with the share of sorted position m + r
@@ -1676,17 +1839,8 @@ extern "C" int hbmpc_robust_interpolate_batch(hbmpc_ctx *ctx, size_t n, size_t d
 }
 
 // ------------------------------------------------------------------------------------------------ a10: NonRobustShare::recover_secret, batched
-struct NonRobustTables {
-    uint4 *M = nullptr;
-    int *chk_map = nullptr;
-    int R = 0, n_chk = 0;
-    // every domain point supplied (S == n == N): interpolation through all points is one inverse NTT
-    int fast_logn = 0;
-    int *in_map = nullptr;
-    uint4 *itw = nullptr, *iscale = nullptr;
-};
-static std::map<std::string, NonRobustTables> &nr_cache(hbmpc_ctx *ctx) {
-    if (!ctx->nonrobust) ctx->nonrobust = new std::map<std::string, NonRobustTables>();
+static std::map<TableKey, NonRobustTables> &nr_cache(hbmpc_ctx *ctx) {
+    if (!ctx->nonrobust) ctx->nonrobust = new std::map<TableKey, NonRobustTables>();
     return *ctx->nonrobust;
 }
 
@@ -1696,12 +1850,11 @@ extern "C" int hbmpc_nonrobust_recover_batch(hbmpc_ctx *ctx, size_t n, size_t de
     // validation order of common/share/shamir.rs:204-232
     if (S == 0 || !ids) return HBMPC_INVALID_INPUT;
     if (S > 256) return HBMPC_INVALID_INPUT;
-    {
-        std::vector<size_t> srt(ids, ids + S);
-        std::sort(srt.begin(), srt.end());
-        for (size_t i = 1; i < S; ++i)
-            if (srt[i] == srt[i - 1]) return HBMPC_INVALID_INPUT;
-    }
+    std::vector<int> order(S);  // order[i] = arrival index of the share with the i-th smallest id
+    for (size_t i = 0; i < S; ++i) order[i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return ids[a] < ids[b]; });
+    for (size_t i = 1; i < S; ++i)
+        if (ids[order[i]] == ids[order[i - 1]]) return HBMPC_INVALID_INPUT;
     if (S < deg + 1) return HBMPC_INSUFFICIENT_SHARES;
     if (!domain_size(n)) return HBMPC_NO_SUITABLE_DOMAIN;
     for (size_t i = 0; i < S; ++i)
@@ -1710,14 +1863,24 @@ extern "C" int hbmpc_nonrobust_recover_batch(hbmpc_ctx *ctx, size_t n, size_t de
     if (!shares || !coeffs || !status) return HBMPC_INVALID_INPUT;
     cudaSetDevice(ctx->device);
     const size_t m = deg + 1;
-    std::string key = "N " + std::to_string(n) + " " + std::to_string(deg);
-    for (size_t i = 0; i < S; ++i) key += " " + std::to_string(ids[i]);
+    // Tables are keyed by the id SET (like K3): interpolation through all supplied points does not depend on the order in which
+    // they arrived, which is network- and adversary-influenced; the order only enters through the per-call column map.
+    TableKey key;
+    key.kind = 4u;
+    key.n = (uint32_t)n; key.d = (uint32_t)deg;
+    for (size_t i = 0; i < S; ++i) key.idset[ids[i] >> 6] |= 1ull << (ids[i] & 63);
     auto &cache = nr_cache(ctx);
     auto it = cache.find(key);
     if (it == cache.end()) {
+        if (cache.size() >= 256) {  // bounded, like the K3 cache
+            for (auto &ln : ctx->lanes) CK(cudaStreamSynchronize(ln.stream));
+            for (auto &e : cache)
+                for (void *q : e.second.allocs) cudaFree(q);
+            cache.clear();
+        }
         std::vector<HFr> dom = domain_elements(n, n), xs(S);
-        for (size_t i = 0; i < S; ++i) xs[i] = dom[ids[i]];
-        Lagrange L = lagrange_basis(xs);  // Lc[k][i]: coefficient k of the basis polynomial of arrival i
+        for (size_t i = 0; i < S; ++i) xs[i] = dom[ids[order[i]]];
+        Lagrange L = lagrange_basis(xs);  // Lc[k][i]: coefficient k of the basis polynomial of the i-th smallest id
         // rows: coefficients deg+1 .. S-1 (must vanish: the DegreeMismatch check of shamir.rs:234-237), then 0 .. deg
         std::vector<HFr> M(L.Lc.begin() + m * S, L.Lc.end());
         M.insert(M.end(), L.Lc.begin(), L.Lc.begin() + m * S);
@@ -1726,19 +1889,33 @@ extern "C" int hbmpc_nonrobust_recover_batch(hbmpc_ctx *ctx, size_t n, size_t de
         T.R = (int)S;
         std::vector<int> chk(std::max<size_t>(S - m, 1), -1);
         int rc;
-        if ((rc = upload_fr(ctx, M, &T.M))) return rc;
-        if ((rc = upload(ctx, chk, &T.chk_map))) return rc;
+        if ((rc = upload_fr(ctx, M, &T.M, &T.allocs)) || (rc = upload(ctx, chk, &T.chk_map, &T.allocs))) {
+            for (void *q : T.allocs) cudaFree(q);
+            return abandon_call(ctx, rc);
+        }
         const int N = domain_size(n);
         if (!ctx->no_fastpath && S == n && (size_t)N == n && N >= 2) {
-            std::vector<int> in_map(N);
-            for (size_t i = 0; i < S; ++i) in_map[ids[i]] = (int)i;
-            if ((rc = upload(ctx, in_map, &T.in_map))) return rc;
-            if ((rc = get_inverse_twiddles(ctx, N, &T.itw, &T.iscale))) return rc;
+            if ((rc = get_inverse_twiddles(ctx, N, &T.itw, &T.iscale))) return abandon_call(ctx, rc);
             while ((1 << T.fast_logn) < N) ++T.fast_logn;
         }
         it = cache.emplace(key, T).first;
     }
     const NonRobustTables &T = it->second;
+    // per-call maps: column c (sorted position) reads arrival order[c]; domain index -> arrival index for the inverse transform
+    const int *d_order = nullptr, *d_in_map = nullptr;
+    {
+        const int N = domain_size(n);
+        const int *base = nullptr;
+        int rc = maps_upload(ctx, [&](int *blk) -> size_t {
+            for (size_t i = 0; i < S; ++i) blk[i] = order[i];
+            for (int k = 0; k < N; ++k) blk[S + k] = -1;
+            for (size_t i = 0; i < S; ++i) blk[S + ids[i]] = (int)i;
+            return S + (size_t)N;
+        }, &base);
+        if (rc) return abandon_call(ctx, rc);
+        d_order = base;
+        d_in_map = base + S;
+    }
     BatchBuf bi = make_buf(shares, B, (long long)S, sender_major != 0), bc = make_buf(coeffs, B, (long long)m, false);
     BatchBuf bs = make_buf(secrets, B, 1, false), bst = make_buf(status, B, 1, false, 4);
     auto body = [&](Lane &ln, size_t b0, size_t Bc) -> int {
@@ -1763,29 +1940,30 @@ extern "C" int hbmpc_nonrobust_recover_batch(hbmpc_ctx *ctx, size_t n, size_t de
             na.cols = (int)S;
             na.n = (int)S;
             na.err = ctx->d_status;
-            na.in_map = T.in_map;
+            na.in_map = d_in_map;
             na.scale = T.iscale;
             na.m = (int)m;
             na.mout = (int)m;
             na.fail = (unsigned char *)aux;
             if ((rc = launch_ntt<1>(ctx, ln.stream, T.fast_logn, na))) return rc;
         } else {
-        MatvecArgs a{};
-        a.M = T.M;
-        a.in = (const uint4 *)vi.dev;
-        a.out = (uint4 *)vc.dev;
-        a.R = T.R;
-        a.C = (int)S;
-        a.B = (long long)Bc;
-        a.in_sb = vi.sb; a.in_sc = vi.sj;
-        a.in_chunk_major = sender_major ? 0 : 1;
-        a.out_sb = (long long)m;
-        a.out_sr = 1;
-        a.n_chk = T.n_chk;
-        a.n_gate = T.n_chk;
-        a.chk_map = T.chk_map;
-        a.fail = (unsigned char *)aux;
-        if ((rc = launch_matvec(ctx, ln, a, 0))) return rc;
+            MatvecArgs a{};
+            a.M = T.M;
+            a.in = (const uint4 *)vi.dev;
+            a.out = (uint4 *)vc.dev;
+            a.R = T.R;
+            a.C = (int)S;
+            a.B = (long long)Bc;
+            a.in_sb = vi.sb; a.in_sc = vi.sj;
+            a.in_chunk_major = sender_major ? 0 : 1;
+            a.out_sb = (long long)m;
+            a.out_sr = 1;
+            a.col_map = d_order;
+            a.n_chk = T.n_chk;
+            a.n_gate = T.n_chk;
+            a.chk_map = T.chk_map;
+            a.fail = (unsigned char *)aux;
+            if ((rc = launch_matvec(ctx, ln, a, 0))) return rc;
         }
         degree_status_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>((long long)Bc, (int)m, (uint4 *)vc.dev, (const unsigned char *)aux, (int *)vst.dev,
                                                                      secrets ? (uint4 *)vs.dev : nullptr);
@@ -1912,6 +2090,42 @@ extern "C" int hbmpc_measure_imad_peak(hbmpc_ctx *ctx, int variant, double *giga
     double total = 64.0 * iters * (double)blocks * threads;
     *giga_inst_per_s = total / (best * 1e-3) / 1e9;
     if (elapsed_ms) *elapsed_ms = best;
+    return HBMPC_SUCCESS;
+}
+
+// chains in {1, 2, 4, 8} independent carry chains per thread, warps_per_smsp resident warps per sub-partition (1 .. 16)
+extern "C" int hbmpc_measure_wide_chains(hbmpc_ctx *ctx, int chains, int warps_per_smsp, double *giga_inst_per_s) {
+    if (!ctx || !giga_inst_per_s || warps_per_smsp < 1 || warps_per_smsp > 16) return HBMPC_INVALID_INPUT;
+    cudaSetDevice(ctx->device);
+    void *sink = nullptr;
+    int rc = scratch_get(ctx, ctx->lanes[0], 8, 256, &sink);
+    if (rc) return rc;
+    const int iters = 2048, blocks = ctx->num_sms * warps_per_smsp, threads = 128;   // one CTA = one warp per sub-partition
+    cudaStream_t st = ctx->main_stream();
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0, st));
+        switch (chains) {
+            case 1: wide_chain_probe_kernel<1><<<blocks, threads, 0, st>>>((unsigned int *)sink, 12345u + rep, iters); break;
+            case 2: wide_chain_probe_kernel<2><<<blocks, threads, 0, st>>>((unsigned int *)sink, 12345u + rep, iters); break;
+            case 4: wide_chain_probe_kernel<4><<<blocks, threads, 0, st>>>((unsigned int *)sink, 12345u + rep, iters); break;
+            case 8: wide_chain_probe_kernel<8><<<blocks, threads, 0, st>>>((unsigned int *)sink, 12345u + rep, iters); break;
+            default: cudaEventDestroy(e0); cudaEventDestroy(e1); return HBMPC_INVALID_INPUT;
+        }
+        ctx->launches++;
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double total = 8.0 * 4 * chains * iters * (double)blocks * threads;   // IMAD.WIDE per thread: 8 per chain call
+    *giga_inst_per_s = total / (best * 1e-3) / 1e9;
     return HBMPC_SUCCESS;
 }
 

@@ -362,6 +362,9 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
 // Passes exchange through shared memory with __syncthreads (3 per tile); items are `ISTR` = odd number of uint4 apart so that
 // the 8 items of a quarter warp fall into different banks.  MODE 0 / 1 as in ntt_kernel; bit-identical results.
 // Executed products per item: 122 (MODE 0, 22 coefficients) / 132 (all 64 inputs) instead of 144.
+#ifndef HB_NTT64_ROT
+#define HB_NTT64_ROT 1   // rotate the warps' roles from tile to tile (0: fixed roles, the first version)
+#endif
 #ifndef HB_NTT64_IPC
 #define HB_NTT64_IPC 8   // items per CTA tile (8: four warps per barrier, six CTAs per SM; 16: eight warps, three CTAs)
 #endif
@@ -376,35 +379,36 @@ __global__ void __launch_bounds__(HB_NTT64_IPC * 16, 768 / (HB_NTT64_IPC * 16)) 
     const int t = threadIdx.x;
     for (int i = t; i < N; i += BLOCK) sTw[i] = a.tw[i];
 
-    // ---- pass-0 role.  Position pos = tid*4 + e holds the input with natural index bitrev(pos); the product of pass 0 is
-    // w^16 * x3 where x3 = (input e=2) - (input e=3): thread indices whose inputs 2 and 3 do not exist are ranked last.
-    auto rec_for = [&](int tid, int e) -> int {
-        const int k = (int)(__brev((unsigned)(tid * E + e)) >> (32 - LOGN));
-        return (k < a.cols) ? ((MODE == 1 && a.in_map) ? a.in_map[k] : k) : -1;
-    };
-    const int item0 = t & (IPC - 1), r0 = t >> LI;
-    int tid0 = 0;
-    {
+    // ---- roles.  A thread's share of the tile's work depends on its LOGICAL index tl = lw*32 + lane, where the logical warp
+    // lw = (warp + tile iteration) & 3 rotates from tile to tile: the light roles (the warp whose pass-1 twiddle is trivial, the
+    // warps whose pass-0 product has zero operands) would otherwise always sit on the same SM sub-partition (warp w of every
+    // CTA is scheduled on sub-partition w & 3) and leave its multiplier idle while the other three are the bottleneck.
+    // pass 0: position pos = tid*4 + e holds the input with natural index bitrev(pos); the product of pass 0 is w^16 * x3 where
+    // x3 = (input e=2) - (input e=3): thread indices whose inputs 2 and 3 do not exist are ranked last (sRank / sRec tables).
+    int *sRank = reinterpret_cast<int *>(sIn + (size_t)E * 2 * BLOCK);   // [16] rank -> pass-0 thread index
+    int *sRec = sRank + 16;                                             // [16][4] pass-0 thread index -> record of element e (-1: zero)
+    if (t < 16) {
+        auto rec_for = [&](int tid, int e) -> int {
+            const int k = (int)(__brev((unsigned)(tid * E + e)) >> (32 - LOGN));
+            return (k < a.cols) ? ((MODE == 1 && a.in_map) ? a.in_map[k] : k) : -1;
+        };
         int rank = 0, found = -1;
         for (int pass = 0; pass < 2 && found < 0; ++pass)      // first the indices that need the product, then the others
             for (int c = 0; c < 16 && found < 0; ++c) {
                 const bool need = rec_for(c, 2) >= 0 || rec_for(c, 3) >= 0;
                 if (need == (pass == 0)) {
-                    if (rank == r0) found = c;
+                    if (rank == t) found = c;
                     ++rank;
                 }
             }
-        tid0 = found;
-    }
-    int rec_of[E];
+        sRank[t] = found;
 #pragma unroll
-    for (int e = 0; e < E; ++e) rec_of[e] = rec_for(tid0, e);
+        for (int e = 0; e < E; ++e) sRec[t * E + e] = rec_for(t, e);
+    }
+    const int lane = t & 31, warp = t >> 5;
+    constexpr int NW = BLOCK / 32;
     const unsigned FULL = 0xffffffffu;
-    const bool has1 = __any_sync(FULL, rec_of[1] >= 0), has2 = __any_sync(FULL, rec_of[2] >= 0), has3 = __any_sync(FULL, rec_of[3] >= 0);
-    // ---- pass-1 role: low (twiddle index) per warp
-    const int item1 = t & (IPC - 1), low1 = t >> (LI + 2), tid1 = (((t >> LI) & 3) << 2) | low1;
-    const int base1 = ((tid1 >> 2) << 4) | low1;   // positions base1 + e*4
-    // ---- pass-2 role
+    // ---- pass-2 role (every warp does the same amount of work there: no rotation)
     const int item2 = t >> 4, tid2 = t & 15;        // positions tid2 + e*16
     __syncthreads();
 
@@ -412,13 +416,18 @@ __global__ void __launch_bounds__(HB_NTT64_IPC * 16, 768 / (HB_NTT64_IPC * 16)) 
     unsigned bad = 0;
     uint4 *myIn = sIn + t;
     const unsigned int never = (unsigned int)a.n + 0x7fff0000u;
-    auto prefetch = [&](long long tl, unsigned int gate) {
-        const long long bb = tl * IPC + item0;
+    // role of this thread in tile iteration `it`: logical thread index
+    auto logical = [&](unsigned it) -> int { return HB_NTT64_ROT ? ((((warp + (int)it) & (NW - 1)) << 5) | lane) : t; };
+    auto prefetch = [&](long long tl, unsigned it, unsigned int gate) {
+        const int tlg = logical(it);
+        const long long bb = tl * IPC + (tlg & (IPC - 1));
         if (tl < ntiles && bb < a.B && gate != never) {
+            const int c0 = sRank[tlg >> LI];
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                if (rec_of[e] < 0) continue;
-                const uint4 *p = a.in + (bb * a.in_sb + (long long)rec_of[e] * a.in_sc) * 2;
+                const int rec = sRec[c0 * E + e];
+                if (rec < 0) continue;
+                const uint4 *p = a.in + (bb * a.in_sb + (long long)rec * a.in_sc) * 2;
                 cp_async16(myIn + (e * 2) * BLOCK, p);
                 cp_async16(myIn + (e * 2 + 1) * BLOCK, p + 1);
             }
@@ -441,10 +450,19 @@ __global__ void __launch_bounds__(HB_NTT64_IPC * 16, 768 / (HB_NTT64_IPC * 16)) 
         for (int i = 0; i < 8; ++i) { u[i] = sm[i]; v[i] = df[i]; }
     };
     auto idx_of = [](int pos) { return pos + (pos >> 3); };
-    prefetch(blockIdx.x, 0u);
+    prefetch(blockIdx.x, 0u, 0u);
 
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    unsigned it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         uint32_t x[E][8];
+        const int tlg = logical(it);
+        const int item0 = tlg & (IPC - 1), tid0 = sRank[tlg >> LI];
+        int rec_of[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) rec_of[e] = sRec[tid0 * E + e];
+        const bool has1 = __any_sync(FULL, rec_of[1] >= 0), has2 = __any_sync(FULL, rec_of[2] >= 0), has3 = __any_sync(FULL, rec_of[3] >= 0);
+        const int item1 = item0, low1 = tlg >> (LI + 2), tid1 = (((tlg >> LI) & 3) << 2) | low1;
+        const int base1 = ((tid1 >> 2) << 4) | low1;   // pass-1 positions base1 + e*4; low1 (the twiddle index) is constant per warp
         // ---- pass 0
         {
             const long long b = tile * IPC + item0;
@@ -460,7 +478,7 @@ __global__ void __launch_bounds__(HB_NTT64_IPC * 16, 768 / (HB_NTT64_IPC * 16)) 
                     for (int i = 0; i < 8; ++i) x[e][i] = 0;
                 }
             }
-            prefetch(tile + gridDim.x, bad);
+            prefetch(tile + gridDim.x, it + 1, bad);
             // stage 0: (x0,x1), (x2,x3) with twiddle 1; stage 1: (x0,x2) with 1, (x1,x3) with w^16
             if (has1) bfly(x[0], x[1], 0, false);
             else {
@@ -532,7 +550,7 @@ __global__ void __launch_bounds__(HB_NTT64_IPC * 16, 768 / (HB_NTT64_IPC * 16)) 
     }
     if (bad) *(volatile unsigned int *)a.err = 1u;
 }
-inline size_t ntt64_cta_smem_bytes() { return (size_t)(64 + HB_NTT64_IPC * (2 * 72 + 1) + 4 * 2 * HB_NTT64_IPC * 16) * 16 + 16; }
+inline size_t ntt64_cta_smem_bytes() { return (size_t)(64 + HB_NTT64_IPC * (2 * 72 + 1) + 4 * 2 * HB_NTT64_IPC * 16) * 16 + 16 + 5 * 16 * 4; }
 
 template <int LOGN>
 inline size_t ntt_smem_bytes() {

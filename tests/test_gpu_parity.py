@@ -441,6 +441,34 @@ def test_nonrobust_recover_batch(ctx, orc, hb, n, t):
     assert e.value.code == hb.INVALID_INPUT
 
 
+def test_nonrobust_table_cache_is_keyed_by_the_id_set(hb, orc):
+    """RanDouSha checkers see a new arrival order every session: the a10 tables are keyed by the sorted id set (per-call order
+    maps), so a thousand random arrival orders of the same senders must leave free device memory flat -- and stay exact."""
+    import torch
+
+    n, deg, S, B = 16, 5, 12, 8
+    c = hb.Context(0)
+    rng = np.random.default_rng(10)
+    coeffs, shares = _codewords(orc, n, deg, B, 0x5EED0510)
+    ids = np.sort(rng.choice(n, size=S, replace=False))
+    first = c.nonrobust_recover_batch(ids, shares[:, ids], n, deg)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for it in range(1000):
+        arr = rng.permutation(S)
+        co, sec, st = c.nonrobust_recover_batch(ids[arr], shares[:, ids[arr]], n, deg)
+        assert np.array_equal(co, first[0]) and np.array_equal(sec, first[1]) and (st == deg).all()
+    torch.cuda.synchronize()
+    assert torch.cuda.mem_get_info()[0] >= free0 - (1 << 20), "table cache grows with the arrival order"
+    # more id sets than the cache bound: entries are evicted and their device memory returned
+    for it in range(300):
+        sub = np.sort(rng.choice(n, size=S, replace=False))
+        c.nonrobust_recover_batch(sub, shares[:, sub], n, deg)
+    torch.cuda.synchronize()
+    assert torch.cuda.mem_get_info()[0] >= free0 - (64 << 20)
+    c.close()
+
+
 # ------------------------------------------------------------------ edges
 def test_vandermonde_more_columns_than_domain(ctx, orc):
     """cols > N (the exponent wraps, w^N = 1): the NTT does not apply, the dense kernel must take over."""
