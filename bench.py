@@ -7,9 +7,16 @@ One step = one pass of the hot path over one batch of B synthetic secrets on eve
     recon : hbmpc_batch_recover          evals[64][B] (all 64 senders) -> coeffs[B][22], path[B]   (K3, batch_recover_secret)
     value = N * (B*64 + B*64) / max-over-ranks(t_gen + t_rec)
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--log2-batch 22]
-For N > 1 launch under torchrun (one rank per GPU); the batch of independent secrets is sharded (weak scaling: every
-rank owns B secrets), no collective on the data path; NCCL only gathers the reconstructed secrets after the timed region.
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--log2-batch 22] [--scaling weak|strong]
+For N > 1 launch under torchrun (one rank per GPU); the batch of independent secrets is sharded (weak scaling: every rank owns
+B secrets; --scaling strong: 2^log2-batch secrets in total), no collective on the data path; NCCL only gathers the reconstructed
+secrets after the timed region.
+
+Beside the headline the JSON line carries `configs` -- every BASELINE.json configuration measured outside the timed region, each
+with a sample of its outputs compared against the CPU oracle (`parity_sample`): c2 (n=16,t=5, 2^20 secrets), c3_first_call (the
+43-sender call a batch-reconstruction handler makes first: coefficients / secrets only / with flags), c3_strong (2^22 secrets in
+total over all ranks), c4 (n=128,t=42, 2^20 codewords clean / uniform / adversarial errors), c5 (one party's field work for
+2^21 Beaver triples per rank: 2^24 on 8 GPUs).
 """
 from __future__ import annotations
 
@@ -32,12 +39,15 @@ if ROOT not in sys.path:
 N_PARTIES, T_FAULTS = 64, 21
 DEG = T_FAULTS
 M = DEG + 1
+NEEDED = DEG + T_FAULTS + 1
 # algorithmic (dense, reference-faithful) modmul per secret and IMAD per modmul
 ALG_MODMUL_GEN = N_PARTIES * DEG                      # 1344 (Horner count)
 ALG_MODMUL_REC = (DEG + T_FAULTS + 1) * M + M * M     # 946 + 484 = 1430
 IMAD_PER_MODMUL = 256
 BYTES_GEN = M * 32 + N_PARTIES * 32                   # 704 R + 2048 W
 BYTES_REC = (DEG + T_FAULTS + 1) * 32 + M * 32 + 4    # 1376 R + 704 W + path
+METRIC = "Fr shares generated+reconstructed per second (n=64,t=21)"
+DTYPE = "u32x8 (Fr, 255-bit Montgomery)"
 
 
 def parse_args():
@@ -46,12 +56,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: 2^log2-batch secrets in total, split over the ranks")
     ap.add_argument("--log2-batch", type=int, default=22, help="secrets per rank per step (device-resident leg)")
     ap.add_argument("--log2-e2e-batch", type=int, default=20, help="secrets per rank per step (host-buffer leg)")
     ap.add_argument("--cpu-log2-batch", type=int, default=17, help="secrets per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-robust-leg", action="store_true", help="skip the secondary K4 measurement (BASELINE configs[3] shape)")
-    ap.add_argument("--log2-robust", type=int, default=17, help="codewords of the K4 leg (n=128, t=42, e ~ U{0..42} errors each)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the legs of the other BASELINE configurations")
+    ap.add_argument("--no-robust-leg", action="store_true", help="(kept for older scripts) same as --no-configs")
+    ap.add_argument("--log2-c2", type=int, default=20)
+    ap.add_argument("--log2-c4", type=int, default=20, help="codewords of the n=128, t=42 leg")
+    ap.add_argument("--log2-c5", type=int, default=21, help="Beaver triples per rank of the preprocessing leg (2^24 over 8 ranks)")
     return ap.parse_args()
 
 
@@ -70,7 +84,7 @@ def load_oracle_native():
     return cmodel
 
 
-def cpu_step(cm, coeffs, threads):
+def cpu_step(cm, coeffs, threads, keep=None):
     """One pass of the same hot path on the CPU oracle (FFT share generation + batch_recover_secret)."""
     t0 = time.perf_counter()
     rc, shares = cm.compute_shares(coeffs, N_PARTIES, threads=threads)
@@ -80,7 +94,17 @@ def cpu_step(cm, coeffs, threads):
     out = cm.batch_recover_secret(np.arange(N_PARTIES), evals, N_PARTIES, DEG, T_FAULTS, threads=threads)
     t3 = time.perf_counter()
     assert rc == 0 and out["rc"] == 0 and np.array_equal(out["coeffs"], coeffs)
+    if keep is not None:
+        keep["shares"], keep["coeffs"], keep["path"] = shares, out["coeffs"], out["path"]
     return (t1 - t0) + (t3 - t2)
+
+
+def cpu_rate(cm, coeffs, threads, budget_s, keep=None):
+    reps, tcpu = 0, 0.0
+    while reps < 2 or (tcpu < budget_s and reps < 64):
+        tcpu += cpu_step(cm, coeffs, threads, keep if reps == 0 else None)
+        reps += 1
+    return reps * 2 * coeffs.shape[0] * N_PARTIES / tcpu, reps, tcpu
 
 
 def run_reference(args):
@@ -96,30 +120,35 @@ def run_reference(args):
     times = [cpu_step(cm, coeffs, threads) for _ in range(args.steps)]
     total = sum(times)
     value = args.steps * 2 * B * N_PARTIES / total
-    sample = f"{args.steps} steps x 2^{args.cpu_log2_batch} secrets (n=64,t=21): FFT compute_shares + batch_recover_secret, C oracle port, {threads} threads"
+    one = cm.random_fr((1 << 13, M), 0x5EED0013)
+    v1, _, _ = cpu_rate(cm, one, 1, 1.0)   # the reference node itself is single-threaded: print that figure too
+    sample = (f"{args.steps} steps, each a bounded sample of 2^{args.cpu_log2_batch} secrets of the workload in `config` (n=64,t=21): FFT compute_shares + "
+              f"batch_recover_secret, C oracle port -march=native, {threads} threads")
     line = {
-        "impl": "reference", "metric": "Fr shares generated+reconstructed per second (n=64,t=21)", "value": value, "unit": "shares/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "shares/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (Fr, 255-bit Montgomery)", "data": "synthetic",
-        "config": workload_config(args.cpu_log2_batch, None),
-        "cpu_baseline": {"value": value, "unit": "shares/s", "cores": threads, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "shares/s", "cores": threads, "kind": "port", "sample": sample,
+                         "value_1_thread": v1, "sample_secrets_per_step": B},
         "e2e": {"value": value, "unit": "shares/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the Rust reference cannot be built here (no rustc/cargo, arkworks not vendored): this arm times the C oracle port on all host cores",
+        "note": "the Rust reference cannot be built here (no rustc/cargo, arkworks not vendored): this arm times the C oracle port on all host cores; "
+                "throughput in shares/s does not depend on the sample size, so the ratio against the GPU arm stands",
     }
     print(json.dumps(line))
 
 
-def workload_config(log2_batch, log2_e2e):
-    cfg = {
+def workload_config(args):
+    """Identical in both arms (the reference arm processes a bounded sample of it per step, stated in its cpu_baseline.sample)."""
+    return {
         "workload": "HoneyBadgerMPC share-gen + batch reconstruction over ark_bls12_381::Fr, n=64, t=21 (BASELINE configs[2] shape)",
-        "n": N_PARTIES, "t": T_FAULTS, "degree": DEG, "secrets_per_rank_per_step": 1 << log2_batch,
+        "n": N_PARTIES, "t": T_FAULTS, "degree": DEG,
+        "secrets_per_step": f"2^{args.log2_batch} per rank" if args.scaling == "weak" else f"2^{args.log2_batch} in total, split over the ranks",
         "gen": "compute_shares coeffs[B][22] -> shares[B][64]", "recon": "batch_recover evals[64][B] -> coeffs[B][22] (S=64 senders, 43 examined)",
-        "l2": "inputs (>= 2.9 GB per kernel) are larger than the 126 MB L2; no explicit flush",
+        "l2": "inputs (>= 2.9 GB per kernel at 2^22 secrets) are larger than the 126 MB L2; no explicit flush",
+        "e2e_secrets_per_rank_per_step": 1 << args.log2_e2e_batch,
     }
-    if log2_e2e is not None:
-        cfg["e2e_secrets_per_rank_per_step"] = 1 << log2_e2e
-    return cfg
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -173,6 +202,234 @@ def random_fr_device(torch, shape, seed, device):
     return x
 
 
+def _np(x):
+    """device int64 limbs -> host uint64 limbs"""
+    return x.cpu().numpy().view(np.uint64)
+
+
+def timed(torch, stream, fn, reps=3):
+    """average device time of fn over `reps` back-to-back calls (CUDA events on the launching stream), after one warm-up call"""
+    fn()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record(stream)
+    for _ in range(reps):
+        fn()
+    d1.record(stream)
+    torch.cuda.synchronize()
+    return d0.elapsed_time(d1) / reps * 1e-3
+
+
+# ---- BASELINE configs[1]: n=16, t=5
+def leg_c2(torch, hb, ctx, stream, dev, cm, log2):
+    n, t, d, B = 16, 5, 5, 1 << log2
+    ids = np.arange(n)
+    coeffs = random_fr_device(torch, (B, d + 1), 0x5EED0002, dev)
+    shares = torch.empty((B, n, 4), dtype=torch.int64, device=dev)
+    tg = timed(torch, stream, lambda: ctx.compute_shares_batch(coeffs, n, out=shares))
+    ev = shares.permute(1, 0, 2).contiguous()
+    rec = torch.empty((B, d + 1, 4), dtype=torch.int64, device=dev)
+    path = torch.empty((B,), dtype=torch.int32, device=dev)
+    tr = timed(torch, stream, lambda: ctx.batch_recover(ids, ev, n, d, t, out=(rec, path, None)))
+    ok = ctx.synchronize() == 0 and bool(torch.equal(rec, coeffs)) and not bool(path.any())
+    out = {"workload": "n=16, t=5: compute_shares + batch_recover (all 16 senders), device-resident", "secrets": B, "gen_ms": 1e3 * tg, "recon_ms": 1e3 * tr,
+           "shares_per_s": 2 * B * n / (tg + tr), "roundtrip_ok": ok,
+           "hbm_gbs": {"gen": B * (d + 1 + n) * 32 / tg / 1e9, "recon": B * (n + d + 1) * 32 / tr / 1e9}}
+    if cm is not None:
+        Bs = 4096
+        cs = _np(coeffs[:Bs])
+        rc, want = cm.compute_shares(cs, n, threads=cm.max_threads())
+        evs = np.ascontiguousarray(want.transpose(1, 0, 2))
+        ref = cm.batch_recover_secret(ids, evs, n, d, t, threads=cm.max_threads())
+        pok = rc == 0 and np.array_equal(_np(shares[:Bs]), want) and np.array_equal(_np(rec[:Bs]), ref["coeffs"]) and np.array_equal(path[:Bs].cpu().numpy(), ref["path"])
+        out["parity_sample"] = {"items": Bs, "ok": bool(pok), "what": "GPU shares / coefficients / path of the first 4096 secrets == C oracle"}
+    return out
+
+
+# ---- BASELINE configs[2], the call a batch-reconstruction handler makes first: exactly d+t+1 = 43 senders have arrived
+def leg_c3_first_call(torch, hb, ctx, stream, dev, cm, coeffs, evals, rec, path, rank):
+    B = coeffs.shape[0]
+    rng = np.random.default_rng(0x5EED43)
+    arrival = rng.permutation(N_PARTIES)[:NEEDED]               # ids of the first 43 arrivals, in arrival order
+    ev43 = evals[torch.as_tensor(arrival, device=dev)].contiguous()
+    flags43 = torch.empty((B, 1), dtype=torch.int64, device=dev)
+    sec = torch.empty((B, 4), dtype=torch.int64, device=dev)
+
+    def checked(fn, what):
+        s = timed(torch, stream, fn)
+        assert ctx.synchronize() == 0 and what(), "first-call recovery differs from the original polynomials"
+        return s
+
+    t_co = checked(lambda: ctx.batch_recover(arrival, ev43, N_PARTIES, DEG, T_FAULTS, out=(rec, path, None)), lambda: torch.equal(rec, coeffs))
+    t_se = checked(lambda: ctx.batch_recover_secrets(arrival, ev43, N_PARTIES, DEG, T_FAULTS, out=(sec, path)), lambda: torch.equal(sec, coeffs[:, 0]))
+    t_fl = checked(lambda: ctx.batch_recover(arrival, ev43, N_PARTIES, DEG, T_FAULTS, out=(rec, path, flags43)), lambda: torch.equal(rec, coeffs) and not bool(flags43.any()))
+    # the dense kernel on its own (roofline_dense): a context that sends calls with flags straight to the dense check, as every
+    # chunk with a disagreeing share goes (HBMPC_NO_ER_FLAGS is a test knob read at context creation)
+    os.environ["HBMPC_NO_ER_FLAGS"] = "1"
+    ctx_dense = hb.Context(torch.cuda.current_device())
+    del os.environ["HBMPC_NO_ER_FLAGS"]
+    ctx_dense.set_stream(stream.cuda_stream)
+    ctx_dense.set_async(True)
+    t_dense = timed(torch, stream, lambda: ctx_dense.batch_recover(arrival, ev43, N_PARTIES, DEG, T_FAULTS, out=(rec, path, flags43)))
+    assert ctx_dense.synchronize() == 0 and torch.equal(rec, coeffs)
+    ctx_dense.close()
+    out = {"workload": "batch_recover / batch_recover_secrets with the first d+t+1 = 43 arrivals (random id subset, arrival order), 2^22 chunks per rank",
+           "chunks": B, "coeffs_ms": 1e3 * t_co, "secrets_ms": 1e3 * t_se, "coeffs_flags_ms": 1e3 * t_fl, "dense_flags_ms": 1e3 * t_dense,
+           "routes": "coeffs: erasure-weighted inverse NTT + triangular recovery; secrets: same transform, one product per chunk; flags: the transform over all supplied senders, dense check only for chunks it rejects; dense: matvec_kernel on every chunk"}
+    if cm is not None and rank == 0:
+        Bs = 4096
+        evs = _np(ev43[:, :Bs].contiguous())
+        ref = cm.batch_recover_secret(arrival, evs, N_PARTIES, DEG, T_FAULTS, threads=cm.max_threads())
+        pok = ref["rc"] == 0 and np.array_equal(_np(rec[:Bs]), ref["coeffs"]) and np.array_equal(_np(sec[:Bs]), ref["coeffs"][:, 0]) and not ref["path"].any()
+        out["parity_sample"] = {"items": Bs, "ok": bool(pok), "what": "coefficients and secrets of the first 4096 chunks == C oracle batch_recover_secret on the same 43 sender vectors"}
+    return out, t_dense
+
+
+# ---- BASELINE configs[3]: n=128, t=42 robust interpolation with injected errors
+def leg_c4(torch, hb, ctx, stream, dev, cm, log2):
+    n, t, d, B = 128, 42, 42, 1 << log2
+    ids = np.arange(n)
+    coeffs = random_fr_device(torch, (B, d + 1), 0x5EED0004, dev)
+    shares = torch.empty((B, n, 4), dtype=torch.int64, device=dev)
+    ctx.set_async(True)
+    ctx.compute_shares_batch(coeffs, n, out=shares)
+    g = torch.Generator(device=dev)
+    g.manual_seed(44)
+    needed = d + t + 1
+
+    def corrupt(kind):
+        if kind == "clean":
+            return shares.clone(), torch.zeros((B, n), dtype=torch.bool, device=dev)
+        if kind == "uniform":      # e ~ U{0..t} errors at uniform distinct positions
+            e = torch.randint(0, t + 1, (B,), device=dev, generator=g)
+            perm = torch.rand((B, n), device=dev, generator=g).argsort(dim=1)
+        else:                      # adversarial: exactly t errors, all at ids < d+t+1 (forces the reference's last OEC round)
+            e = torch.full((B,), t, device=dev)
+            perm = torch.rand((B, needed), device=dev, generator=g).argsort(dim=1)
+        mask = torch.zeros((B, n), dtype=torch.bool, device=dev)
+        sel = torch.arange(perm.shape[1], device=dev)[None, :] < e[:, None]
+        mask.scatter_(1, perm, sel)
+        bad = shares.clone()
+        bad[..., 0] = torch.where(mask, bad[..., 0] ^ 0x5A5A5, bad[..., 0])
+        return bad, mask
+
+    def expected_path(mask):
+        """OEC round the reference accepts in (robust_interpolate.rs:579-628): the first r whose prefix of d+t+1+r ids holds at most r
+        errors (r = 0: the optimistic check on the lowest d+t+1 ids passes)."""
+        cum = mask.to(torch.int32).cumsum(dim=1)
+        r = torch.arange(0, n - needed + 1, device=dev)
+        in_prefix = cum[:, needed - 1:]                       # errors among the first d+t+1+r ids, r = 0 .. n-needed
+        okr = in_prefix <= r[None, :]
+        return torch.where(okr.any(dim=1), okr.to(torch.int32).argmax(dim=1), torch.full((B,), -1, device=dev, dtype=torch.int64)).to(torch.int32)
+
+    co = torch.empty((B, d + 1, 4), dtype=torch.int64, device=dev)
+    sec = torch.empty((B, 4), dtype=torch.int64, device=dev)
+    path = torch.empty((B,), dtype=torch.int32, device=dev)
+    fl = torch.empty((B, 2), dtype=torch.int64, device=dev)
+    weights = (torch.ones(64, dtype=torch.int64, device=dev) << torch.arange(64, device=dev))
+    res = {}
+    sample = None
+    for kind in ("clean", "uniform", "adversarial"):
+        bad, mask = corrupt(kind)
+        ctx.set_async(False)   # synchronous calls know the failing count on the host: large failing sets take the staged decoder
+        l0 = ctx.launch_count
+        ctx.robust_interpolate_batch(ids, bad, n, d, t, out=(co, sec, path, fl))
+        launches = ctx.launch_count - l0
+        s = timed(torch, stream, lambda: ctx.robust_interpolate_batch(ids, bad, n, d, t, out=(co, sec, path, fl)), reps=2)
+        ctx.set_async(True)
+        want_flags = torch.stack([(mask[:, :64].to(torch.int64) * weights).sum(dim=1), (mask[:, 64:].to(torch.int64) * weights).sum(dim=1)], dim=1)
+        checks = {"coeffs_equal_original": bool(torch.equal(co, coeffs)), "flags_equal_injected_error_positions": bool(torch.equal(fl, want_flags)),
+                  "path_equals_first_oec_round_with_at_most_r_errors_in_prefix": bool(torch.equal(path, expected_path(mask)))}
+        res[kind] = {"ms": 1e3 * s, "codewords_per_s": B / s, "max_path": int(path.max()), "gpu_launches_per_call": int(launches),
+                     "analytic_check": {"items": B, "ok": all(checks.values()), **checks}}
+        if kind == "uniform":
+            sample = (_np(bad[:64]), _np(co[:64]), path[:64].cpu().numpy(), _np(fl[:64]))
+        del bad, mask
+    out = {"workload": "robust_interpolate_batch n=128, t=42, d=42: clean / e~U{0..42} errors at uniform positions / exactly 42 errors inside the examined prefix",
+           "codewords": B, **res}
+    if cm is not None and sample is not None:
+        ref = cm.robust_interpolate_batch(ids, sample[0], n, d, t, threads=cm.max_threads())
+        pok = ref["rc"] == 0 and np.array_equal(sample[1], ref["coeffs"]) and np.array_equal(sample[2], ref["path"]) and np.array_equal(sample[3], ref["flags"][:, :2])
+        out["parity_sample"] = {"items": 64, "ok": bool(pok), "what": "coefficients, OEC round and flags of the first 64 'uniform' codewords == C oracle (reference-faithful OEC + Gao, ~1 core-second per codeword)"}
+    return out
+
+
+# ---- BASELINE configs[4]: RanSha + DouSha + RanDouSha + Beaver triple generation, one party's field work for T triples
+def leg_c5(torch, hb, ctx, stream, dev, cm, log2, rank):
+    n, t = N_PARTIES, T_FAULTS
+    T = 1 << log2
+    ids = np.arange(n)
+    E = lambda *shape: torch.empty(tuple(shape) + (4,), dtype=torch.int64, device=dev)
+    I32 = lambda k: torch.empty((k,), dtype=torch.int32, device=dev)
+    cols_rs = -(-2 * T // (n - 2 * t))      # RanSha columns: n-2t outputs each, 2 random shares per triple
+    cols_ds = -(-T // (t + 1))              # DouSha / RanDouSha columns: t+1 outputs each
+    groups = -(-T // (2 * t + 1))           # triple groups of 2t+1 (one batch-recon chunk each)
+    seed = 0x5EED0500 + 16 * rank
+    # synthetic inputs (consistent sharings so that every check takes the honest path)
+    c_t = random_fr_device(torch, (cols_rs, t + 1), seed + 1, dev); sh_t = E(cols_rs, n)
+    c_d = random_fr_device(torch, (cols_ds, t + 1), seed + 2, dev); c_d2 = random_fr_device(torch, (cols_ds, 2 * t + 1), seed + 3, dev)
+    c_d2[:, 0] = c_d[:, 0]
+    sh_d, sh_d2 = E(cols_ds, n), E(cols_ds, n)
+    recv = random_fr_device(torch, (cols_rs, n), seed + 4, dev); mix = E(cols_rs, n)           # shares received from the n dealers
+    recv_d, mix_d, mix_d2 = random_fr_device(torch, (cols_ds, n), seed + 5, dev), E(cols_ds, n), E(cols_ds, n)
+    aS, bS, r2S, rtS = (random_fr_device(torch, (T,), seed + s, dev) for s in (6, 7, 8, 9))    # own shares of a, b, r_2t, r_t
+    prod, masked, cS = E(T), E(T), E(T)
+    grp = random_fr_device(torch, (groups, 2 * t + 1), seed + 10, dev)                          # opened values a*b - r per group
+    y_enc = E(n, groups)
+    y_all = E(groups, n)
+    ctx.compute_shares_batch(grp, n, out=y_all)                                                  # what the n parties would send (degree 2t)
+    y_sm = y_all.permute(1, 0, 2).contiguous()
+    sec1, p1 = E(groups), I32(groups)
+    co2, p2 = E(groups, 2 * t + 1), I32(groups)
+    ver_co, ver_sec, ver_p = E(cols_rs, t + 1), E(cols_rs), I32(cols_rs)
+    chk_co, chk_sec, chk_st, chk_co2, chk_sec2, chk_st2 = E(cols_ds, t + 1), E(cols_ds), I32(cols_ds), E(cols_ds, 2 * t + 1), E(cols_ds), I32(cols_ds)
+    phases = {
+        "ransha_deal (K1 d=t, 1 secret/column)": lambda: ctx.compute_shares_batch(c_t, n, out=sh_t),
+        "ransha_mix (K2 64x64 per column)": lambda: ctx.apply_vandermonde_batch(recv, n, out=mix),
+        "ransha_verify (robust recover of one opened row per column, all n shares)": lambda: ctx.robust_interpolate_batch(ids, sh_t, n, t, t, out=(ver_co, ver_sec, ver_p, None)),
+        "dousha_deal (K1 d=t and d=2t per column)": lambda: (ctx.compute_shares_batch(c_d, n, out=sh_d), ctx.compute_shares_batch(c_d2, n, out=sh_d2)),
+        "randousha_mix (2x K2 64x64 per column)": lambda: (ctx.apply_vandermonde_batch(recv_d, n, out=mix_d), ctx.apply_vandermonde_batch(sh_d2, n, out=mix_d2)),
+        "randousha_check (NonRobust recover deg t and 2t, all n shares)": lambda: (ctx.nonrobust_recover_batch(ids, sh_d, n, t, out=(chk_co, chk_sec, chk_st)),
+                                                                                 ctx.nonrobust_recover_batch(ids, sh_d2, n, 2 * t, out=(chk_co2, chk_sec2, chk_st2))),
+        "triple_mask (K5: a*b - r_2t per triple)": lambda: (ctx.elementwise(2, aS, bS, out=prod), ctx.elementwise(1, prod, r2S, out=masked)),
+        "triple_open_encode (K2 64x43 per group, recipient-major)": lambda: ctx.apply_vandermonde_batch(grp, n, recipient_major=True, out=y_enc),
+        "triple_open_round1 (batch_recover_secrets d=2t, 64 senders)": lambda: ctx.batch_recover_secrets(ids, y_sm, n, 2 * t, t, out=(sec1, p1)),
+        "triple_open_round2 (batch_recover d=2t, 64 senders)": lambda: ctx.batch_recover(ids, y_sm, n, 2 * t, t, out=(co2, p2, None)),
+        "triple_finish (K5: r_t + opened)": lambda: ctx.elementwise(0, rtS, masked, out=cS),
+    }
+    ctx.set_async(True)
+    res, total = {}, 0.0
+    for name, fn in phases.items():
+        s = timed(torch, stream, fn)
+        res[name] = round(1e3 * s, 4)
+        total += s
+    ok = ctx.synchronize() == 0 and bool(torch.equal(co2, grp)) and bool(torch.equal(sec1, grp[:, 0])) and bool(torch.equal(chk_sec, c_d[:, 0])) \
+        and bool(torch.equal(chk_sec2, c_d[:, 0])) and int(chk_st.min()) == t and int(chk_st2.min()) == 2 * t and bool(torch.equal(ver_sec, c_t[:, 0])) \
+        and bool(torch.equal(y_enc, y_sm))
+    out = {"workload": "one party's field work of RanSha + DouSha + RanDouSha + Beaver triple generation (n=64, t=21), device-resident, per rank",
+           "triples_per_rank": T, "ransha_columns": cols_rs, "dousha_columns": cols_ds, "groups": groups, "phase_ms": res, "total_ms": round(1e3 * total, 3),
+           "triples_per_s_per_gpu": T / total, "self_consistent": ok, "_total_s": total}
+    if cm is not None and rank == 0:
+        K, th = 256, cm.max_threads()
+        rc1, w_sh = cm.compute_shares(_np(c_t[:K]), n, threads=th)
+        rc2, w_mix = cm.apply_vandermonde(_np(recv[:K]), n, threads=th)
+        rc3, w_mix2 = cm.apply_vandermonde(_np(sh_d2[:K]), n, threads=th)
+        w_ver = cm.robust_interpolate_batch(ids, _np(sh_t[:K]), n, t, t, threads=th)
+        rc4, w_enc = cm.apply_vandermonde(_np(grp[:K]), n, recipient_major=True, threads=th)
+        w_r2 = cm.batch_recover_secret(ids, _np(y_sm[:, :K].contiguous()), n, 2 * t, t, threads=th)
+        Ke = 4096
+        w_prod = cm.elementwise(2, _np(aS[:Ke]), _np(bS[:Ke]), threads=th)
+        w_mask = cm.elementwise(1, w_prod, _np(r2S[:Ke]), threads=th)
+        w_c = cm.elementwise(0, _np(rtS[:Ke]), w_mask, threads=th)
+        nr = [cm.nonrobust_recover_secret(ids, _np(sh_d2[b]), n, 2 * t) for b in range(8)]
+        pok = (rc1 == rc2 == rc3 == rc4 == 0 and np.array_equal(_np(sh_t[:K]), w_sh) and np.array_equal(_np(mix[:K]), w_mix) and np.array_equal(_np(mix_d2[:K]), w_mix2)
+               and np.array_equal(_np(ver_co[:K]), w_ver["coeffs"]) and np.array_equal(_np(y_enc[:, :K].contiguous()), w_enc)
+               and np.array_equal(_np(co2[:K]), w_r2["coeffs"]) and np.array_equal(_np(sec1[:K]), w_r2["coeffs"][:, 0])
+               and np.array_equal(_np(masked[:Ke]), w_mask) and np.array_equal(_np(cS[:Ke]), w_c)
+               and all(r["rc"] == 0 and np.array_equal(_np(chk_co2[b]), r["coeffs"]) for b, r in enumerate(nr)))
+        out["parity_sample"] = {"items": K, "ok": bool(pok), "what": "first 256 columns / groups of every K1/K2/K3 phase, first 4096 triples of the K5 phases, 8 degree-2t checks == C oracle"}
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -189,13 +446,36 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     n_gpus = world
+    configs_on = not (args.no_configs or args.no_robust_leg)
 
     ctx = hb.Context(local)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     ctx.set_async(True)
     B = 1 << args.log2_batch
+    if args.scaling == "strong":
+        sh = importlib.import_module("mpc-protocols_b200.sharding")
+        lo_, hi_ = sh.shard_range(B, world, rank)
+        B = hi_ - lo_
     ids = np.arange(N_PARTIES)
+
+    def max_over_ranks(vals):
+        tt = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tt.tolist()
+
+    def sum_over_ranks(vals):
+        tt = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        return tt.tolist()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     # ---- synthetic inputs, resident in HBM before the timed region
     coeffs = random_fr_device(torch, (B, M), 0x5EED0003 + rank, dev)
@@ -206,18 +486,12 @@ def run_b200(args):
     path = torch.empty((B,), dtype=torch.int32, device=dev)
     assert ctx.synchronize() == 0
 
-    def step(ev):
+    def step(ev, c=coeffs, s=shares, e=evals, r=rec, p=path):
         ev[0].record(stream)
-        ctx.compute_shares_batch(coeffs, N_PARTIES, out=shares)
+        ctx.compute_shares_batch(c, N_PARTIES, out=s)
         ev[1].record(stream)
-        ctx.batch_recover(ids, evals, N_PARTIES, DEG, T_FAULTS, out=(rec, path, None))
+        ctx.batch_recover(ids, e, N_PARTIES, DEG, T_FAULTS, out=(r, p, None))
         ev[2].record(stream)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     mk = lambda: [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     for _ in range(max(args.warmup, 0)):
@@ -226,7 +500,7 @@ def run_b200(args):
     assert torch.equal(rec, coeffs) and not bool(path.any()), "reconstruction != original coefficients"
 
     imad_peak = ctx.measure_imad_peak(0)[0] * 1e9  # thread-level IMAD/s, measured in this run on this GPU
-    imad_wide_peak = ctx.measure_imad_peak(1)[0] * 1e9
+    imad_wide_peak = ctx.measure_imad_peak(1)[0] * 1e9  # IMAD.WIDE.U32(.X) SASS instructions/s (one per mad.lo/madc.hi pair of the carry chains)
 
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -242,54 +516,43 @@ def run_b200(args):
     t_rec = sum(ev[1].elapsed_time(ev[2]) for ev in events) * 1e-3
     t_tot = sum(ev[0].elapsed_time(ev[2]) for ev in events) * 1e-3
     assert torch.equal(rec, coeffs) and not bool(path.any())
-    tt = torch.tensor([t_tot, t_gen, t_rec], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_tot, t_gen, t_rec = tt.tolist()
+    t_tot, t_gen, t_rec = max_over_ranks([t_tot, t_gen, t_rec])
+    B_all = int(sum_over_ranks([float(B)])[0])
 
-    # ---- general path of K3 for comparison: only the first d+t+1 = 43 senders supplied (the call a batch-reconstruction
-    # handler makes on its first attempt).  Without flags: erasure-weighted inverse NTT + triangular recovery; with flags:
-    # the dense matvec_kernel (43 check/coefficient rows x 22 terms).
-    needed = DEG + T_FAULTS + 1
-    ev43, ids43 = evals[:needed], np.arange(needed)
-    flags43 = torch.empty((B, 1), dtype=torch.int64, device=dev)
+    # ---- CPU oracle (rank 0 only): the checker of every parity sample below and, at N = 1, the timed cpu_baseline
+    cm = load_oracle_native() if (rank == 0 and not args.no_cpu_baseline) else None
 
-    def timed3(fn):
-        fn()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d0.record(stream)
+    configs = {}
+    t_dense = None
+    if configs_on:
+        # the 43-sender first call (every rank measures; rank 0 reports and checks against the oracle)
+        fc, t_dense = leg_c3_first_call(torch, hb, ctx, stream, dev, cm, coeffs, evals, rec, path, rank)
+        fc_ms = max_over_ranks([fc["coeffs_ms"], fc["secrets_ms"], fc["coeffs_flags_ms"], fc["dense_flags_ms"]])
+        fc["coeffs_ms"], fc["secrets_ms"], fc["coeffs_flags_ms"], fc["dense_flags_ms"] = fc_ms
+        t_dense = fc_ms[3] * 1e-3
+        configs["c3_first_call"] = fc
+        # restore the headline outputs for the parity sample below
+        ctx.batch_recover(ids, evals, N_PARTIES, DEG, T_FAULTS, out=(rec, path, None))
+        assert ctx.synchronize() == 0
+
+    # ---- BASELINE configs[2] as stated: 2^22 secrets in total, sharded over the ranks (strong scaling), device-resident
+    if world > 1 and args.scaling == "weak" and configs_on:
+        Bs = (1 << args.log2_batch) // world
+        cs_, ss_, es_, rs_, ps_ = coeffs[:Bs], shares[:Bs], evals[:, :Bs].contiguous(), rec[:Bs], path[:Bs]
         for _ in range(3):
-            fn()
-        d1.record(stream)
-        assert ctx.synchronize() == 0 and torch.equal(rec, coeffs)
-        return d0.elapsed_time(d1) / 3 * 1e-3
-
-    t_gen43 = timed3(lambda: ctx.batch_recover(ids43, ev43, N_PARTIES, DEG, T_FAULTS, out=(rec, path, None)))
-    t_flags43 = timed3(lambda: ctx.batch_recover(ids43, ev43, N_PARTIES, DEG, T_FAULTS, out=(rec, path, flags43)))
-    # the dense kernel on its own (roofline_dense): a context that sends calls with flags straight to the dense check, as every
-    # chunk with a disagreeing share goes (HBMPC_NO_ER_FLAGS is a test knob read at context creation)
-    os.environ["HBMPC_NO_ER_FLAGS"] = "1"
-    ctx_dense = hb.Context(local)
-    del os.environ["HBMPC_NO_ER_FLAGS"]
-    ctx_dense.set_stream(stream.cuda_stream)
-    ctx_dense.set_async(True)
-
-    def timed3_dense():
-        fn = lambda: ctx_dense.batch_recover(ids43, ev43, N_PARTIES, DEG, T_FAULTS, out=(rec, path, flags43))
-        fn()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d0.record(stream)
-        for _ in range(3):
-            fn()
-        d1.record(stream)
-        assert ctx_dense.synchronize() == 0 and torch.equal(rec, coeffs)
-        return d0.elapsed_time(d1) / 3 * 1e-3
-
-    t_dense = timed3_dense()
-    ctx_dense.close()
+            step(mk(), cs_, ss_, es_, rs_, ps_)
+        barrier()
+        evs = [mk() for _ in range(10)]
+        for ev in evs:
+            step(ev, cs_, ss_, es_, rs_, ps_)
+        barrier()
+        ts = max_over_ranks([sum(ev[0].elapsed_time(ev[2]) for ev in evs) * 1e-3])[0]
+        assert ctx.synchronize() == 0 and torch.equal(rs_, cs_)
+        configs["c3_strong"] = {"workload": "configs[2] as stated: 2^%d secrets in TOTAL, contiguous ranges over the ranks, gen + recon per step" % args.log2_batch,
+                                "secrets_total": Bs * world, "secrets_per_rank": Bs, "ms_per_step": 1e3 * ts / 10, "shares_per_s": 10 * 2 * Bs * world * N_PARTIES / ts}
 
     # ---- end-to-end leg: same calls with HOST (pinned) buffers, copies inside the timed region
-    Be = 1 << args.log2_e2e_batch
+    Be = min(1 << args.log2_e2e_batch, B)
     h_coeffs = torch.empty((Be, M, 4), dtype=torch.int64).pin_memory()
     h_coeffs.copy_(coeffs[:Be].cpu())
     h_shares = torch.empty((Be, N_PARTIES, 4), dtype=torch.int64).pin_memory()
@@ -314,16 +577,15 @@ def run_b200(args):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     assert np.array_equal(np_r, np_c) and not np_p.any()
-    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    t_e2e = te.item()
-    h2d = Be * M * 32 + Be * needed * 32  # coefficients in; of the 64 sender vectors the library uploads only the 43 it examines
+    t_e2e = max_over_ranks([t_e2e])[0]
+    h2d = Be * M * 32 + Be * NEEDED * 32  # coefficients in; of the 64 sender vectors the library uploads only the 43 it examines
     d2h = Be * N_PARTIES * 32 + Be * M * 32 + Be * 4
+    ctx.set_async(True)
+    del h_coeffs, h_shares, h_evals, h_rec, h_path
 
     # ---- NCCL gather of the reconstructed secrets (the only collective; outside the hot path)
     gather_ms = None
-    if world > 1:
+    if world > 1 and args.scaling == "weak":
         sh = importlib.import_module("mpc-protocols_b200.sharding")
         lo, hi = sh.shard_range(world * B, world, rank)      # this rank's contiguous range of the global batch
         assert hi - lo == B
@@ -337,104 +599,97 @@ def run_b200(args):
         torch.cuda.synchronize()
         gather_ms = g0.elapsed_time(g1)
         assert torch.equal(allsec[lo:hi], coeffs[:, 0, :])
+        del allsec
 
-    # ---- secondary leg (rank 0, N=1 only, outside the timed region): robust interpolation with injected errors, BASELINE
-    # configs[3] shape (n=128, t=42) at 2^log2_robust codewords, e ~ U{0..42} errors at uniform positions in each codeword
-    robust = None
-    if rank == 0 and n_gpus == 1 and not args.no_robust_leg:
-        n4, t4 = 128, 42
-        B4 = 1 << args.log2_robust
-        ids4 = np.arange(n4)
-        c4 = random_fr_device(torch, (B4, t4 + 1), 0x5EED0004, dev)
-        s4 = torch.empty((B4, n4, 4), dtype=torch.int64, device=dev)
-        ctx.set_async(True)
-        ctx.compute_shares_batch(c4, n4, out=s4)
-        g = torch.Generator(device=dev)
-        g.manual_seed(44)
-        e4 = torch.randint(0, t4 + 1, (B4,), device=dev, generator=g)
-        perm = torch.rand((B4, n4), device=dev, generator=g).argsort(dim=1)
-        mask = torch.zeros((B4, n4), dtype=torch.bool, device=dev)
-        mask.scatter_(1, perm, torch.arange(n4, device=dev)[None, :] < e4[:, None])
-        s4[..., 0] = torch.where(mask, s4[..., 0] ^ 0x5A5A5, s4[..., 0])
-        o4 = (torch.empty((B4, t4 + 1, 4), dtype=torch.int64, device=dev), torch.empty((B4, 4), dtype=torch.int64, device=dev),
-              torch.empty((B4,), dtype=torch.int32, device=dev), torch.empty((B4, 2), dtype=torch.int64, device=dev))
-        ctx.set_async(False)   # synchronous calls: large failing sets take the staged decoder
-        l4 = ctx.launch_count
-        ctx.robust_interpolate_batch(ids4, s4, n4, t4, t4, out=o4)
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record(stream)
-        for _ in range(3):
-            ctx.robust_interpolate_batch(ids4, s4, n4, t4, t4, out=o4)
-        k1.record(stream)
-        torch.cuda.synchronize()
-        ms4 = k0.elapsed_time(k1) / 3
-        assert torch.equal(o4[0], c4), "robust interpolation did not return the original polynomials"
-        robust = {"workload": "robust_interpolate n=128 t=42, e ~ U{0..42} injected errors per codeword (BASELINE configs[3] shape)", "codewords": B4,
-                  "ms": ms4, "codewords_per_s": B4 / (ms4 * 1e-3), "decoded_with_errors": int((o4[2] != 0).sum()), "max_oec_round": int(o4[2].max()),
-                  "gpu_launches_per_call": int((ctx.launch_count - l4) // 4)}
-        del c4, s4, o4, mask, perm
-
-    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores
-    cpu = None
-    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
-        cm = load_oracle_native()
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores; its outputs are the parity
+    # sample of the headline (the GPU shares / coefficients of the same first 2^17 secrets must be identical)
+    cpu, parity = None, None
+    if cm is not None and n_gpus == 1:
         threads = cm.max_threads()
-        Bc = 1 << args.cpu_log2_batch
-        cc = coeffs[:Bc].cpu().numpy().view(np.uint64)
+        Bc = min(1 << args.cpu_log2_batch, B)
+        cc = _np(coeffs[:Bc])
         cpu_step(cm, cc[: 1 << 12], threads)
-        reps, tcpu = 0, 0.0
-        while reps < 2 or (tcpu < 4.0 and reps < 64):
-            tcpu += cpu_step(cm, cc, threads)
-            reps += 1
-        cpu = {"value": reps * 2 * Bc * N_PARTIES / tcpu, "unit": "shares/s", "cores": threads, "kind": "port",
-               "sample": f"{reps} x 2^{args.cpu_log2_batch} secrets of the same workload (FFT compute_shares + batch_recover_secret), C oracle port -march=native, {threads} threads, {tcpu:.1f} s"}
+        keep = {}
+        v_all, reps, tcpu = cpu_rate(cm, cc, threads, 4.0, keep)
+        v_one, _, _ = cpu_rate(cm, cc[: 1 << 13], 1, 1.0)
+        cpu = {"value": v_all, "unit": "shares/s", "cores": threads, "kind": "port", "value_1_thread": v_one,
+               "sample": f"{reps} x 2^{args.cpu_log2_batch} secrets of the same workload (FFT compute_shares + batch_recover_secret), C oracle port -march=native, {threads} threads, {tcpu:.1f} s; value_1_thread: the same on one core (the reference node is single-threaded)"}
+        pok = np.array_equal(_np(shares[:Bc]), keep["shares"]) and np.array_equal(_np(rec[:Bc]), keep["coeffs"]) and np.array_equal(path[:Bc].cpu().numpy(), keep["path"])
+        parity = {"items": Bc, "ok": bool(pok), "what": "GPU shares[B][64], coefficients and path of the first 2^%d secrets of the timed batch == the oracle outputs computed by the cpu_baseline leg" % args.cpu_log2_batch}
+    elif cm is not None:
+        Bc = 4096
+        rc, want = cm.compute_shares(_np(coeffs[:Bc]), N_PARTIES, threads=cm.max_threads())
+        parity = {"items": Bc, "ok": bool(rc == 0 and np.array_equal(_np(shares[:Bc]), want) and np.array_equal(_np(rec[:Bc]), _np(coeffs[:Bc]))),
+                  "what": "rank 0: GPU shares of the first 4096 secrets == C oracle, coefficients == inputs"}
+
+    # ---- the other BASELINE configs (outside the timed region).  c2 / c4: rank 0 at N = 1; c5: every rank at every N
+    if configs_on:
+        del shares, evals
+        torch.cuda.empty_cache()
+        if n_gpus == 1:
+            configs["c2"] = leg_c2(torch, hb, ctx, stream, dev, cm, args.log2_c2)
+            configs["c4"] = leg_c4(torch, hb, ctx, stream, dev, cm, args.log2_c4)
+            torch.cuda.empty_cache()
+        c5 = leg_c5(torch, hb, ctx, stream, dev, cm, args.log2_c5, rank)
+        tot5 = max_over_ranks([c5.pop("_total_s")])[0]
+        ok5 = min(max_over_ranks([0.0 if c5["self_consistent"] else 1.0])) == 0.0
+        c5.update({"ranks": world, "triples_total": world * c5["triples_per_rank"], "total_ms_max_over_ranks": 1e3 * tot5,
+                   "triples_per_s": world * c5["triples_per_rank"] / tot5, "self_consistent_all_ranks": ok5})
+        configs["c5"] = c5
 
     if rank == 0:
-        shares_per_step = 2 * B * N_PARTIES
-        value = n_gpus * args.steps * shares_per_step / t_tot
+        shares_per_step = 2 * B_all * N_PARTIES
+        value = args.steps * shares_per_step / t_tot
         gen_launch_s = t_gen / args.steps
         rec_launch_s = t_rec / args.steps
         hbm = measured_hbm()
-        rec_alg_imad = B * ALG_MODMUL_REC * IMAD_PER_MODMUL
-        gen_alg_imad = B * ALG_MODMUL_GEN * IMAD_PER_MODMUL
-        # executed IMAD.WIDE (32x32->64 multiply-add) counts per secret: one Montgomery product = 8 rows x 16 = 128 wide;
-        # 64-point radix-2 NTT: 129 non-trivial twiddle products (the inverse scales its 22 coefficients by 1/N with a shift, not a product); dense: 64 per term + 64 per reduction
-        NTT_MULS = 129
-        gen_exec_wide = B * NTT_MULS * 128
-        rec_exec_wide = B * (NTT_MULS * 128 + M * 8)   # the 1/N scaling of the 22 coefficients is 8 narrow multiplies + a shift each (fr_div_pow2)
-        dense_exec_wide = B * ((T_FAULTS + M) * M + (T_FAULTS + M)) * 64
+        ex = executed_counts()
         traffic = ncu_traffic()
-        def roof(kernel, alg_imad, exec_wide, secs, nbytes, note, tkey):
-            return {"kernel": kernel, "bound": "int32-imad", "achieved": alg_imad / secs / 1e12, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
-                    "frac": alg_imad / secs / imad_peak, "how": note,
-                    "executed_wide_tinst": exec_wide / secs / 1e12, "imad_wide_peak_tinst": imad_wide_peak / 1e12,
-                    "executed_frac_of_imad_wide_peak": exec_wide / secs / imad_wide_peak,
-                    "hbm_gbs": nbytes / secs / 1e9, "hbm_frac": nbytes / secs / 1e9 / hbm, "algorithmic_bytes": nbytes,
-                    "traffic": (traffic[tkey] * B / (1 << 20)) if tkey in traffic else None}
+
+        def roof(kernel_key, label, alg_modmul, secs, nbytes, tkey, units=B):
+            """frac = EXECUTED 32x32->64 multiply-adds (IMAD.WIDE SASS instructions, counted by ncu per item: profiles/r02_executed_counts.json)
+            per launch / CUDA-event launch time / the IMAD.WIDE rate measured in this run.  alg_speedup = dense reference-faithful count / executed."""
+            e = ex.get(kernel_key, {})
+            wide = e.get("imad_wide_thread_inst_per_item")
+            o = {"kernel": label, "bound": "int32 multiplier pipe (IMAD.WIDE.U32: 32x32->64 multiply-add)", "unit": "T IMAD.WIDE/s",
+                 "peak": imad_wide_peak / 1e12, "peak_how": "IMAD.WIDE.U32.X carry-chain probe measured in this run (hbmpc_measure_imad_peak variant 1)",
+                 "achieved": (wide * units / secs / 1e12) if wide else None, "frac": (wide * units / secs / imad_wide_peak) if wide else None,
+                 "executed_imad_wide_per_item": wide, "executed_source": e.get("source"), "launch_ms": 1e3 * secs, "items_per_launch": units,
+                 "alg_modmul_per_item": alg_modmul, "alg_imad_per_s_T": alg_modmul * IMAD_PER_MODMUL * units / secs / 1e12,
+                 "alg_frac_of_imad_peak": alg_modmul * IMAD_PER_MODMUL * units / secs / imad_peak, "imad_peak_T": imad_peak / 1e12,
+                 "alg_speedup": (alg_modmul * IMAD_PER_MODMUL / 2 / wide) if wide else None,
+                 "hbm_gbs": nbytes / secs / 1e9, "hbm_frac": nbytes / secs / 1e9 / hbm, "algorithmic_bytes": nbytes,
+                 "traffic": (traffic[tkey] * units / (1 << 20)) if tkey in traffic else None}
+            return o
+
         line = {
-            "metric": "Fr shares generated+reconstructed per second (n=64,t=21)", "value": value, "unit": "shares/s",
+            "metric": METRIC, "value": value, "unit": "shares/s",
             "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (Fr, 255-bit Montgomery)", "data": "synthetic",
-            "config": workload_config(args.log2_batch, args.log2_e2e_batch),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+            "config": workload_config(args),
             "breakdown": {"gen_ms": 1e3 * t_gen / args.steps, "recon_ms": 1e3 * t_rec / args.steps,
-                          "gen_shares_per_s": n_gpus * args.steps * B * N_PARTIES / t_gen, "recon_shares_per_s": n_gpus * args.steps * B * N_PARTIES / t_rec,
-                          "alg_modmul_per_s": n_gpus * args.steps * B * (ALG_MODMUL_GEN + ALG_MODMUL_REC) / t_tot, "gather_ms": gather_ms,
-                          "recon_43_senders_ms": 1e3 * t_gen43, "recon_43_senders_flags_ms": 1e3 * t_flags43, "recon_43_senders_dense_ms": 1e3 * t_dense, "robust_n128_t42": robust,
-                          "recon_note": "recon_ms: all 64 senders supplied -> inverse NTT + degree check (bit-identical; items that fail fall back to the dense check); recon_43_senders_ms: only d+t+1 senders supplied -> erasure-weighted inverse NTT + triangular recovery; recon_43_senders_flags_ms: same call with flags -> the erasure-weighted transform over all supplied senders, dense check only for chunks it rejects; recon_43_senders_dense_ms: the dense matvec_kernel on every chunk (HBMPC_NO_ER_FLAGS=1)"},
-            "roofline": roof("ntt64_cta_kernel<1> (K3 batch_recover launch, all 64 senders: inverse 64-point NTT + degree check per chunk)", rec_alg_imad, rec_exec_wide,
-                             rec_launch_s, B * (N_PARTIES * 32 + M * 32 + 5),
-                             "achieved = algorithmic IMAD (B * 1430 modmul * 256, SURVEY 8d dense count) / CUDA-event launch time; peak = mad.lo.u32 probe measured in this run; executed_* = IMAD.WIDE actually issued vs the IMAD.WIDE probe",
-                             "ntt_inv"),
-            "roofline_gen": roof("ntt64_cta_kernel<0> (K1 compute_shares launch: zero-padded 64-point NTT per secret)", gen_alg_imad, gen_exec_wide, gen_launch_s, B * BYTES_GEN,
-                                 "algorithmic IMAD = B * 1344 modmul * 256 (dense Horner count of SURVEY 8d)", "ntt_fwd"),
-            "roofline_dense": roof("matvec_kernel<4> (K3 dense check with flags, 43 senders: 43x22 check+coefficient matrix per chunk; the route of every chunk with a disagreeing share)", rec_alg_imad, dense_exec_wide, t_dense,
-                                   B * (BYTES_REC + 8), "same algorithmic count, dense path", "matvec"),
+                          "gen_shares_per_s": args.steps * B_all * N_PARTIES / t_gen, "recon_shares_per_s": args.steps * B_all * N_PARTIES / t_rec,
+                          "alg_modmul_per_s": args.steps * B_all * (ALG_MODMUL_GEN + ALG_MODMUL_REC) / t_tot, "gather_ms": gather_ms,
+                          "recon_note": "recon_ms: all 64 senders supplied -> inverse NTT + degree check (bit-identical; items that fail fall back to the dense check and the decoder); configs.c3_first_call: the 43-sender call"},
+            "roofline": roof("recon", "K3 batch_recover launch, all 64 senders: inverse 64-point NTT + degree check per chunk", ALG_MODMUL_REC, rec_launch_s,
+                             B * (N_PARTIES * 32 + M * 32 + 5), "ntt_inv"),
+            "roofline_gen": roof("gen", "K1 compute_shares launch: zero-padded 64-point NTT per secret", ALG_MODMUL_GEN, gen_launch_s, B * BYTES_GEN, "ntt_fwd"),
+            "parity_sample": parity,
+            "configs": configs,
             "cpu_baseline": cpu,
             "e2e": {"value": n_gpus * e2e_steps * 2 * Be * N_PARTIES / t_e2e, "unit": "shares/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps, "host_buffers": "pinned"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if t_dense is not None:
+            line["roofline_dense"] = roof("dense", "matvec_kernel (K3 dense check with flags, 43 senders: 43x22 check+coefficient matrix per chunk; the route of every chunk with a disagreeing share)",
+                                          ALG_MODMUL_REC, t_dense, B * (BYTES_REC + 8), "matvec")
+        if "c4" in configs and "k4" in ex:
+            # K4: the staged decoder's dominant kernel is bm_segment_kernel; executed multiply-adds of the WHOLE call per codeword
+            s4 = configs["c4"]["uniform"]["ms"] * 1e-3
+            line["roofline_k4"] = roof("k4", "robust_interpolate_batch n=128,t=42, e~U{0..42}: all kernels of the call (dominant: bm_segment_kernel)", 13400, s4,
+                                       configs["c4"]["codewords"] * (128 * 32 + 43 * 32 + 32 + 4 + 16), "k4", units=configs["c4"]["codewords"])
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -445,6 +700,15 @@ def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 2^20 from the committed ncu --set full capture (profiles/)."""
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_per_2p20.json")))
+    except Exception:
+        return {}
+
+
+def executed_counts():
+    """Executed IMAD.WIDE thread-instructions per item of each headline kernel, summed over the SASS lines of the committed ncu source
+    page (tools/ncu_exec_counts.py -> profiles/r02_executed_counts.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_executed_counts.json")))
     except Exception:
         return {}
 

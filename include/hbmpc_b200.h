@@ -136,6 +136,9 @@ int hbmpc_measure_imad_peak(hbmpc_ctx *ctx, int variant, double *giga_inst_per_s
 /* Latency probe behind the kernels' occupancy choices: `chains` (1, 2, 4, 8) independent serial IMAD.WIDE.U32.X carry chains per
  * thread at `warps_per_smsp` (1 .. 16) resident warps per SM sub-partition; returns 1e9 thread-level multiply-adds per second. */
 int hbmpc_measure_wide_chains(hbmpc_ctx *ctx, int chains, int warps_per_smsp, double *giga_inst_per_s);
+/* Throughput of the Montgomery product the transforms and the decoder are built on (fr.cuh: mont_mul / mont_mul2), register-only:
+ * ilp (1, 2, 4) independent product chains per thread at warps_per_smsp resident warps; returns 1e9 products per second. */
+int hbmpc_measure_mont_mul(hbmpc_ctx *ctx, int ilp, int warps_per_smsp, double *giga_products_per_s);
 
 #ifdef __cplusplus
 }

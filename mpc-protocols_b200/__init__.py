@@ -33,7 +33,7 @@ EXPORTS = [
     "hbmpc_ctx_launch_count", "hbmpc_last_error", "hbmpc_compute_shares_batch", "hbmpc_apply_vandermonde_batch",
     "hbmpc_apply_matrix_batch", "hbmpc_batch_recover", "hbmpc_batch_recover_secrets", "hbmpc_robust_interpolate_batch",
     "hbmpc_nonrobust_recover_batch", "hbmpc_elementwise", "hbmpc_unpack_share_records", "hbmpc_pack_share_records",
-    "hbmpc_measure_imad_peak", "hbmpc_measure_wide_chains",
+    "hbmpc_measure_imad_peak", "hbmpc_measure_wide_chains", "hbmpc_measure_mont_mul",
 ]
 
 
@@ -77,6 +77,7 @@ def load_library():
     lib.hbmpc_pack_share_records.argtypes = [vp, sz, vp, sz, sz, vp]
     lib.hbmpc_measure_imad_peak.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.hbmpc_measure_wide_chains.argtypes = [vp, ci, ci, C.POINTER(C.c_double)]
+    lib.hbmpc_measure_mont_mul.argtypes = [vp, ci, ci, C.POINTER(C.c_double)]
     _lib = lib
     return lib
 
@@ -277,6 +278,11 @@ class Context:
         self._check(self.lib.hbmpc_measure_imad_peak(self.h, variant, C.byref(g), C.byref(ms)))
         return g.value, ms.value
 
+
+    def measure_mont_mul(self, ilp: int, warps_per_smsp: int) -> float:
+        g = C.c_double()
+        self._check(self.lib.hbmpc_measure_mont_mul(self.h, ilp, warps_per_smsp, C.byref(g)))
+        return g.value
 
     def measure_wide_chains(self, chains: int, warps_per_smsp: int) -> float:
         g = C.c_double()

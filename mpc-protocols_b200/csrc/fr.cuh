@@ -550,6 +550,58 @@ HB_DEV void mont_mul(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&
     for (int i = 0; i < 8; ++i) d[i] = sres[i];
 }
 
+// Two independent products with their rows issued alternately: twice the independent carry chains in flight per thread (a warp
+// issues one IMAD.WIDE of a single chain every ~8 cycles; the multiplier pipe accepts one every ~4).  Bit-identical to two mont_mul.
+HB_DEV void mont_mul2(uint32_t (&d0)[8], const uint32_t (&a0)[8], const uint32_t (&b0)[8], uint32_t (&d1)[8], const uint32_t (&a1)[8],
+                      const uint32_t (&b1)[8]) {
+    unsigned long long E0[4], O0[4], E1[4], O1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        E0[j] = (unsigned long long)a0[2 * j] * b0[0];
+        O0[j] = (unsigned long long)a0[2 * j + 1] * b0[0];
+        E1[j] = (unsigned long long)a1[2 * j] * b1[0];
+        O1[j] = (unsigned long long)a1[2 * j + 1] * b1[0];
+    }
+    {
+        const uint32_t m0 = 0u - (uint32_t)E0[0], m1 = 0u - (uint32_t)E1[0];
+        uint32_t k0 = 0, k1 = 0, k2 = 0, k3 = 0;
+        chain4w(O0[0], O0[1], O0[2], O0[3], k0, HB_R1, HB_R3, HB_R5, HB_R7, m0);
+        chain4w(O1[0], O1[1], O1[2], O1[3], k2, HB_R1, HB_R3, HB_R5, HB_R7, m1);
+        chain4w(E0[0], E0[1], E0[2], E0[3], k1, HB_R0, HB_R2, HB_R4, HB_R6, m0);
+        chain4w(E1[0], E1[1], E1[2], E1[3], k3, HB_R0, HB_R2, HB_R4, HB_R6, m1);
+        O0[3] += (unsigned long long)k1 << 32;
+        O1[3] += (unsigned long long)k3 << 32;
+        (void)k0; (void)k2;
+    }
+    cios_row(E0[0], E0[1], E0[2], E0[3], O0[0], O0[1], O0[2], O0[3], a0, b0[1]);
+    cios_row(E1[0], E1[1], E1[2], E1[3], O1[0], O1[1], O1[2], O1[3], a1, b1[1]);
+    cios_row(O0[0], O0[1], O0[2], O0[3], E0[0], E0[1], E0[2], E0[3], a0, b0[2]);
+    cios_row(O1[0], O1[1], O1[2], O1[3], E1[0], E1[1], E1[2], E1[3], a1, b1[2]);
+    cios_row(E0[0], E0[1], E0[2], E0[3], O0[0], O0[1], O0[2], O0[3], a0, b0[3]);
+    cios_row(E1[0], E1[1], E1[2], E1[3], O1[0], O1[1], O1[2], O1[3], a1, b1[3]);
+    cios_row(O0[0], O0[1], O0[2], O0[3], E0[0], E0[1], E0[2], E0[3], a0, b0[4]);
+    cios_row(O1[0], O1[1], O1[2], O1[3], E1[0], E1[1], E1[2], E1[3], a1, b1[4]);
+    cios_row(E0[0], E0[1], E0[2], E0[3], O0[0], O0[1], O0[2], O0[3], a0, b0[5]);
+    cios_row(E1[0], E1[1], E1[2], E1[3], O1[0], O1[1], O1[2], O1[3], a1, b1[5]);
+    cios_row(O0[0], O0[1], O0[2], O0[3], E0[0], E0[1], E0[2], E0[3], a0, b0[6]);
+    cios_row(O1[0], O1[1], O1[2], O1[3], E1[0], E1[1], E1[2], E1[3], a1, b1[6]);
+    cios_row(E0[0], E0[1], E0[2], E0[3], O0[0], O0[1], O0[2], O0[3], a0, b0[7]);
+    cios_row(E1[0], E1[1], E1[2], E1[3], O1[0], O1[1], O1[2], O1[3], a1, b1[7]);
+    auto fin = [](uint32_t (&d)[8], const unsigned long long (&E)[4], const unsigned long long (&O)[4]) {
+        uint32_t x[8], y[8], sres[8];
+        x[0] = (uint32_t)(O[0] >> 32); x[1] = (uint32_t)O[1]; x[2] = (uint32_t)(O[1] >> 32); x[3] = (uint32_t)O[2];
+        x[4] = (uint32_t)(O[2] >> 32); x[5] = (uint32_t)O[3]; x[6] = (uint32_t)(O[3] >> 32); x[7] = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { y[2 * j] = (uint32_t)E[j]; y[2 * j + 1] = (uint32_t)(E[j] >> 32); }
+        add8(sres, x, y);
+        cond_sub_mod(sres);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = sres[i];
+    };
+    fin(d0, E0, O0);
+    fin(d1, E1, O1);
+}
+
 // R^2 mod r (to Montgomery form: mont_mul(x, R2)); 1 (from Montgomery form: mont_mul(x, 1))
 HB_DEV void r2_limbs(uint32_t (&r)[8]) {
     r[0] = 0xf3f29c6du; r[1] = 0xc999e990u; r[2] = 0x87925c23u; r[3] = 0x2b6cedcbu;

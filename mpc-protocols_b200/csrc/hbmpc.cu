@@ -181,6 +181,41 @@ __global__ void __launch_bounds__(128) wide_chain_probe_kernel(unsigned int *sin
     if (s == 0x12345ull) sink[0] = (unsigned int)s;
 }
 
+// Throughput probe of the Montgomery product itself: ILP independent register-resident product chains x <- x * w per thread.
+template <int ILP>
+__global__ void __launch_bounds__(128) mont_mul_probe_kernel(unsigned int *sink, unsigned int seed, int iters) {
+    uint32_t x[ILP][8], w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = (seed + 0x9e3779b9u * (i + 1)) >> (i == 7 ? 2 : 0);
+#pragma unroll
+    for (int c = 0; c < ILP; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[c][i] = (threadIdx.x * 2654435761u + 977u * i + c) >> (i == 7 ? 2 : 0);
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        if (ILP == 2) {
+            uint32_t y0[8], y1[8];
+            mont_mul2(y0, x[0], w, y1, x[ILP - 1], w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { x[0][i] = y0[i]; x[ILP - 1][i] = y1[i]; }
+        } else {
+#pragma unroll
+            for (int c = 0; c < ILP; ++c) {
+                uint32_t y[8];
+                mont_mul(y, x[c], w);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[c][i] = y[i];
+            }
+        }
+    }
+    uint32_t s2 = 0;
+#pragma unroll
+    for (int c = 0; c < ILP; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s2 ^= x[c][i];
+    if (s2 == 0x12345u) sink[0] = s2;
+}
+
 }  // namespace hb
 
 // ------------------------------------------------------------------------------------------------ context
@@ -775,7 +810,7 @@ static int launch_ntt16x_t(hbmpc_ctx *ctx, cudaStream_t st, const NttArgs &a) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ntt16x_kernel<LOGN, MODE>, NTT16X_WARPS * 32, smem));
         ctas = nb > 0 ? nb : 1;
     }
-    const int ipc = NTT16X_WARPS * (32 >> (LOGN - 4));
+    const int ipc = NTT16X_WARPS * (32 >> (LOGN - ntt16x_logs<LOGN>()));
     const long long ntiles = (a.B + ipc - 1) / ipc;
     const long long grid = std::min<long long>(ntiles, (long long)ctx->num_sms * ctas);
     ntt16x_kernel<LOGN, MODE><<<(unsigned)grid, NTT16X_WARPS * 32, smem, st>>>(a);
@@ -2124,8 +2159,43 @@ extern "C" int hbmpc_measure_wide_chains(hbmpc_ctx *ctx, int chains, int warps_p
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    const double total = 8.0 * 4 * chains * iters * (double)blocks * threads;   // IMAD.WIDE per thread: 8 per chain call
+    const double total = 4.0 * 4 * chains * iters * (double)blocks * threads;   // IMAD.WIDE.U32.X per thread: 4 per chain call (one per mad.lo/madc.hi pair)
     *giga_inst_per_s = total / (best * 1e-3) / 1e9;
+    return HBMPC_SUCCESS;
+}
+
+// Montgomery products per second (1e9) of a register-only loop: ilp = 1 (one serial chain of products per thread), 2 (two chains
+// through mont_mul2), 4 (four chains through mont_mul), at warps_per_smsp resident warps per sub-partition
+extern "C" int hbmpc_measure_mont_mul(hbmpc_ctx *ctx, int ilp, int warps_per_smsp, double *giga_products_per_s) {
+    if (!ctx || !giga_products_per_s || warps_per_smsp < 1 || warps_per_smsp > 16) return HBMPC_INVALID_INPUT;
+    cudaSetDevice(ctx->device);
+    void *sink = nullptr;
+    int rc = scratch_get(ctx, ctx->lanes[0], 8, 256, &sink);
+    if (rc) return rc;
+    const int iters = 1024, blocks = ctx->num_sms * warps_per_smsp, threads = 128;
+    cudaStream_t st = ctx->main_stream();
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0, st));
+        switch (ilp) {
+            case 1: mont_mul_probe_kernel<1><<<blocks, threads, 0, st>>>((unsigned int *)sink, 12345u + rep, iters); break;
+            case 2: mont_mul_probe_kernel<2><<<blocks, threads, 0, st>>>((unsigned int *)sink, 12345u + rep, iters); break;
+            case 4: mont_mul_probe_kernel<4><<<blocks, threads, 0, st>>>((unsigned int *)sink, 12345u + rep, iters); break;
+            default: cudaEventDestroy(e0); cudaEventDestroy(e1); return HBMPC_INVALID_INPUT;
+        }
+        ctx->launches++;
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *giga_products_per_s = (double)ilp * iters * (double)blocks * threads / (best * 1e-3) / 1e9;
     return HBMPC_SUCCESS;
 }
 

@@ -12,4 +12,8 @@ tab = {}
 for ch in (1, 2, 4, 8):
     tab[f"chains={ch}"] = {f"warps_per_smsp={w}": round(ctx.measure_wide_chains(ch, w), 1) for w in (1, 2, 3, 4, 6, 8, 12, 16)}
 out["wide_chain_latency_table_ginst_per_s"] = tab
+mm = {}
+for ilp in (1, 2, 4):
+    mm[f"ilp={ilp}"] = {f"warps_per_smsp={w}": round(ctx.measure_mont_mul(ilp, w), 2) for w in (1, 2, 4, 6, 8, 12, 16)}
+out["mont_mul_gproducts_per_s"] = mm
 print(json.dumps(out, indent=1))
