@@ -417,9 +417,9 @@ def leg_c5(torch, hb, ctx, stream, dev, cm, log2, rank):
         rc4, w_enc = cm.apply_vandermonde(_np(grp[:K]), n, recipient_major=True, threads=th)
         w_r2 = cm.batch_recover_secret(ids, _np(y_sm[:, :K].contiguous()), n, 2 * t, t, threads=th)
         Ke = 4096
-        w_prod = cm.elementwise(2, _np(aS[:Ke]), _np(bS[:Ke]), threads=th)
-        w_mask = cm.elementwise(1, w_prod, _np(r2S[:Ke]), threads=th)
-        w_c = cm.elementwise(0, _np(rtS[:Ke]), w_mask, threads=th)
+        _, w_prod = cm.elementwise(2, _np(aS[:Ke]), _np(bS[:Ke]), threads=th)
+        _, w_mask = cm.elementwise(1, w_prod, _np(r2S[:Ke]), threads=th)
+        _, w_c = cm.elementwise(0, _np(rtS[:Ke]), w_mask, threads=th)
         nr = [cm.nonrobust_recover_secret(ids, _np(sh_d2[b]), n, 2 * t) for b in range(8)]
         pok = (rc1 == rc2 == rc3 == rc4 == 0 and np.array_equal(_np(sh_t[:K]), w_sh) and np.array_equal(_np(mix[:K]), w_mix) and np.array_equal(_np(mix_d2[:K]), w_mix2)
                and np.array_equal(_np(ver_co[:K]), w_ver["coeffs"]) and np.array_equal(_np(y_enc[:, :K].contiguous()), w_enc)
@@ -427,6 +427,69 @@ def leg_c5(torch, hb, ctx, stream, dev, cm, log2, rank):
                and np.array_equal(_np(masked[:Ke]), w_mask) and np.array_equal(_np(cS[:Ke]), w_c)
                and all(r["rc"] == 0 and np.array_equal(_np(chk_co2[b]), r["coeffs"]) for b, r in enumerate(nr)))
         out["parity_sample"] = {"items": K, "ok": bool(pok), "what": "first 256 columns / groups of every K1/K2/K3 phase, first 4096 triples of the K5 phases, 8 degree-2t checks == C oracle"}
+    return out
+
+
+def leg_group(torch, hb, n_dev, log2_total, cm):
+    """One process, n_dev GPUs: member contexts of an hbmpc_group driven from this process."""
+    ids = np.arange(N_PARTIES)
+    total = 1 << log2_total
+    grp = hb.Group(list(range(n_dev)))
+    members = []
+    for g in range(n_dev):
+        lo, hi = grp.shard_range(total, g)
+        dv = torch.device("cuda", g)
+        with torch.cuda.device(dv):
+            c = hb.Context(g)
+            c.set_async(True)
+            co = random_fr_device(torch, (hi - lo, M), 0x5EED0600 + g, dv)
+            sh = torch.empty((hi - lo, N_PARTIES, 4), dtype=torch.int64, device=dv)
+            c.compute_shares_batch(co, N_PARTIES, out=sh)
+            torch.cuda.synchronize(dv)
+            assert c.synchronize() == 0
+            ev = sh.permute(1, 0, 2).contiguous()
+            rec = torch.empty((hi - lo, M, 4), dtype=torch.int64, device=dv)
+            pth = torch.empty((hi - lo,), dtype=torch.int32, device=dv)
+            torch.cuda.synchronize(dv)
+            members.append((c, co, sh, ev, rec, pth))
+
+    def step():
+        for c, co, sh, ev, rec, pth in members:     # enqueue-only calls: all devices run concurrently
+            c.compute_shares_batch(co, N_PARTIES, out=sh)
+            c.batch_recover(ids, ev, N_PARTIES, DEG, T_FAULTS, out=(rec, pth, None))
+        for c, *_ in members:
+            assert c.synchronize() == 0
+
+    for _ in range(3):
+        step()
+    reps = 10
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    dt = (time.perf_counter() - t0) / reps
+    ok = all(bool(torch.equal(rec, co)) for _, co, _, _, rec, _ in members)
+    out = {"workload": "ONE process, one member context per GPU: 2^%d secrets in total in contiguous ranges, gen + recon per step, device-resident, wall clock around enqueue-on-all + synchronize-all" % log2_total,
+           "devices": n_dev, "secrets_total": total, "ms_per_step": 1e3 * dt, "shares_per_s": 2 * total * N_PARTIES / dt, "roundtrip_ok": ok}
+    # host-buffer group calls (hbmpc_group_*: internal host threads, PCIe-bound) on 2^20 secrets in total
+    Bh = 1 << 20
+    hc = _np(members[0][1][: min(Bh, members[0][1].shape[0])])
+    Bh = hc.shape[0]
+    hs = np.zeros((Bh, N_PARTIES, 4), dtype=np.uint64)
+    grp.compute_shares_batch(hc, N_PARTIES, out=hs)
+    he = np.ascontiguousarray(hs.transpose(1, 0, 2))
+    t0 = time.perf_counter()
+    grp.compute_shares_batch(hc, N_PARTIES, out=hs)
+    rc, hr, hp, _ = grp.batch_recover(ids, he, N_PARTIES, DEG, T_FAULTS)
+    dth = time.perf_counter() - t0
+    out["host_buffer_group_calls"] = {"secrets": Bh, "ms": 1e3 * dth, "shares_per_s": 2 * Bh * N_PARTIES / dth, "ok": bool(rc == 0 and np.array_equal(hr, hc) and not hp.any()),
+                                      "note": "pageable numpy buffers, one call each of hbmpc_group_compute_shares_batch / hbmpc_group_batch_recover"}
+    if cm is not None:
+        Ks = 2048
+        rcs, want = cm.compute_shares(hc[:Ks], N_PARTIES, threads=cm.max_threads())
+        out["parity_sample"] = {"items": Ks, "ok": bool(rcs == 0 and np.array_equal(hs[:Ks], want)), "what": "group share generation of the first 2048 secrets == C oracle"}
+    for c, *_ in members:
+        c.close()
+    grp.close()
     return out
 
 
@@ -560,13 +623,15 @@ def run_b200(args):
     h_evals.copy_(evals[:, :Be].cpu())
     h_rec = torch.empty((Be, M, 4), dtype=torch.int64).pin_memory()
     h_path = torch.empty((Be,), dtype=torch.int32).pin_memory()
-    ctx.set_async(False)
+    # asynchronous mode: both calls only enqueue (on two different sets of internal streams) and hbmpc_ctx_synchronize completes them,
+    # so the download-bound share generation and the upload-bound recovery use both PCIe directions at the same time
+    ctx.set_async(True)
     np_c, np_s, np_e, np_r, np_p = (x.numpy().view(np.uint64) if x.dtype == torch.int64 else x.numpy() for x in (h_coeffs, h_shares, h_evals, h_rec, h_path))
 
     def e2e_step():
         ctx.compute_shares_batch(np_c, N_PARTIES, out=np_s)
-        rc, _, _, _ = ctx.batch_recover(ids, np_e, N_PARTIES, DEG, T_FAULTS, out=(np_r, np_p, None))
-        assert rc == 0
+        ctx.batch_recover(ids, np_e, N_PARTIES, DEG, T_FAULTS, out=(np_r, np_p, None))
+        assert ctx.synchronize() == 0
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_step()
@@ -578,10 +643,17 @@ def run_b200(args):
     t_e2e = time.perf_counter() - t0
     assert np.array_equal(np_r, np_c) and not np_p.any()
     t_e2e = max_over_ranks([t_e2e])[0]
-    h2d = Be * M * 32 + Be * NEEDED * 32  # coefficients in; of the 64 sender vectors the library uploads only the 43 it examines
+    h2d = Be * M * 32 + Be * N_PARTIES * 32  # coefficients and all 64 sender vectors in (asynchronous calls upload every supplied sender)
     d2h = Be * N_PARTIES * 32 + Be * M * 32 + Be * 4
     ctx.set_async(True)
     del h_coeffs, h_shares, h_evals, h_rec, h_path
+
+    # ---- the box's pinned-copy rates, every rank AT THE SAME TIME (the roofline of the e2e leg: with N ranks they share the host bridge)
+    pcie = pcie_probe(torch, dev, barrier)
+    pcie_bound_s = max(h2d, d2h) / (pcie["both_each_GBs"] * 1e9)   # both directions busy: the slower one bounds the step
+    pcie_all = max_over_ranks([1.0 / pcie["h2d_GBs"], 1.0 / pcie["d2h_GBs"], 1.0 / pcie["both_each_GBs"]])
+    pcie_min = {"h2d_GBs": 1.0 / pcie_all[0], "d2h_GBs": 1.0 / pcie_all[1], "both_each_GBs": 1.0 / pcie_all[2]}
+    pcie_bound_s = max_over_ranks([pcie_bound_s])[0]
 
     # ---- NCCL gather of the reconstructed secrets (the only collective; outside the hot path)
     gather_ms = None
@@ -637,6 +709,18 @@ def run_b200(args):
                    "triples_per_s": world * c5["triples_per_rank"] / tot5, "self_consistent_all_ranks": ok5})
         configs["c5"] = c5
 
+    # ---- single-process multi-GPU (rank 0 drives one member context per GPU of the node: what a one-process reference party would
+    # do): configs[2] as stated, 2^22 secrets in total in contiguous ranges over the devices, device-resident, enqueue on every member
+    # then wait for all; and the same through the group's host-buffer entry points
+    if world > 1 and configs_on:
+        barrier()
+        if rank == 0:
+            try:
+                configs["c3_group_single_process"] = leg_group(torch, hb, world, args.log2_batch, cm)
+            except Exception as exc:   # never lose the headline line to this leg
+                configs["c3_group_single_process"] = {"error": repr(exc)}
+        barrier()
+
     if rank == 0:
         shares_per_step = 2 * B_all * N_PARTIES
         value = args.steps * shares_per_step / t_tot
@@ -678,7 +762,11 @@ def run_b200(args):
             "configs": configs,
             "cpu_baseline": cpu,
             "e2e": {"value": n_gpus * e2e_steps * 2 * Be * N_PARTIES / t_e2e, "unit": "shares/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps, "host_buffers": "pinned"},
+                    "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps, "host_buffers": "pinned",
+                    "mode": "asynchronous host-buffer calls (enqueue on two lane sets, hbmpc_ctx_synchronize per step)",
+                    "pcie_gbs": {"h2d": h2d * e2e_steps / t_e2e / 1e9, "d2h": d2h * e2e_steps / t_e2e / 1e9},
+                    "pcie_probe_slowest_rank": pcie_min, "pcie_bound_ms": 1e3 * pcie_bound_s, "pcie_frac": pcie_bound_s / (t_e2e / e2e_steps),
+                    "pcie_note": "pcie_probe: pinned 256 MiB copies on every rank concurrently (H2D alone, D2H alone, both at once); pcie_bound = max(h2d, d2h bytes per step) / the bidirectional per-direction rate; pcie_frac = bound / measured step"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -694,6 +782,37 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def pcie_probe(torch, dev, barrier, nbytes=1 << 28, reps=4):
+    """Pinned-memory copy bandwidth seen by this rank while every other rank does the same: H2D, D2H, and both at once on two streams."""
+    h1 = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h2 = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d1 = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d2 = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(up, down, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s1.wait_event(e0)
+        s2.wait_event(e0)
+        for _ in range(n):
+            if up:
+                with torch.cuda.stream(s1):
+                    d1.copy_(h1, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s2):
+                    h2.copy_(d2, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(s1)
+        torch.cuda.current_stream().wait_stream(s2)
+        e1.record()
+        torch.cuda.synchronize()
+        return n * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    run(True, True, 1)
+    return {"h2d_GBs": run(True, False, reps), "d2h_GBs": run(False, True, reps), "both_each_GBs": run(True, True, reps)}
 
 
 def ncu_traffic():

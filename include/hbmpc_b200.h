@@ -128,6 +128,29 @@ int hbmpc_elementwise(hbmpc_ctx *ctx, int op, size_t count, const uint64_t *a, c
 int hbmpc_unpack_share_records(hbmpc_ctx *ctx, size_t count, const void *records, uint64_t *values, uint64_t *ids, uint64_t *degrees);
 int hbmpc_pack_share_records(hbmpc_ctx *ctx, size_t count, const uint64_t *values, size_t per_id, size_t degree, void *records);
 
+/* Single-process multi-GPU.  The reference party is one process that issues all sessions' work before awaiting
+ * (honeybadger/mod.rs:245-257,1362-1375); every call of this path is a map over independent secrets / chunks / codewords, so a group
+ * (one context per device, tables replicated) splits the batch into contiguous ranges [g*B/G, (g+1)*B/G), one internal host thread
+ * per device, with NO collective on the data path.  Group calls take HOST buffers (pinned for full PCIe speed) laid out exactly as in
+ * the single-context calls and return when every range is complete; return value = the first non-zero status in device order.
+ * hbmpc_group_ctx(i) / hbmpc_group_shard_range give the member contexts and ranges to callers that keep their batches resident on
+ * the devices themselves (member contexts are ordinary contexts: one caller per context at a time). */
+typedef struct hbmpc_group hbmpc_group;
+int hbmpc_group_create(const int *devices, size_t n_devices, hbmpc_group **out);
+void hbmpc_group_destroy(hbmpc_group *grp);
+size_t hbmpc_group_size(const hbmpc_group *grp);
+hbmpc_ctx *hbmpc_group_ctx(hbmpc_group *grp, size_t i);
+void hbmpc_group_shard_range(const hbmpc_group *grp, size_t B, size_t i, size_t *lo, size_t *hi);
+int hbmpc_group_compute_shares_batch(hbmpc_group *grp, size_t n, size_t d, size_t B, const uint64_t *coeffs, uint64_t *shares);
+int hbmpc_group_apply_vandermonde_batch(hbmpc_group *grp, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out,
+                                        int recipient_major);
+int hbmpc_group_batch_recover(hbmpc_group *grp, size_t n, size_t d, size_t t, size_t S, const size_t *sender_ids, size_t B,
+                              const uint64_t *evals, uint64_t *coeffs, int32_t *path, uint64_t *flags);
+int hbmpc_group_batch_recover_secrets(hbmpc_group *grp, size_t n, size_t d, size_t t, size_t S, const size_t *sender_ids, size_t B,
+                                      const uint64_t *evals, uint64_t *secrets, int32_t *path);
+int hbmpc_group_robust_interpolate_batch(hbmpc_group *grp, size_t n, size_t d, size_t t, size_t S, const size_t *ids, size_t B,
+                                         const uint64_t *shares, uint64_t *coeffs, uint64_t *secrets, int32_t *path, uint64_t *flags);
+
 /* Integer-pipe roofline probe: runs a register-only dependent-chain microkernel on every SM and returns the sustained
  * rate in 1e9 thread-level instructions per second.  variant: 0 = mad.lo.u32 (IMAD, the north star's "IMAD peak"),
  * 1 = IMAD.WIDE.U32(.X) carry chains (the 32x32->64 multiply-add the product kernels issue), 2 = DFMA (FP64 pipe). */

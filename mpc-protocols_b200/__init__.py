@@ -34,6 +34,9 @@ EXPORTS = [
     "hbmpc_apply_matrix_batch", "hbmpc_batch_recover", "hbmpc_batch_recover_secrets", "hbmpc_robust_interpolate_batch",
     "hbmpc_nonrobust_recover_batch", "hbmpc_elementwise", "hbmpc_unpack_share_records", "hbmpc_pack_share_records",
     "hbmpc_measure_imad_peak", "hbmpc_measure_wide_chains", "hbmpc_measure_mont_mul",
+    "hbmpc_group_create", "hbmpc_group_destroy", "hbmpc_group_size", "hbmpc_group_ctx", "hbmpc_group_shard_range",
+    "hbmpc_group_compute_shares_batch", "hbmpc_group_apply_vandermonde_batch", "hbmpc_group_batch_recover",
+    "hbmpc_group_batch_recover_secrets", "hbmpc_group_robust_interpolate_batch",
 ]
 
 
@@ -78,6 +81,20 @@ def load_library():
     lib.hbmpc_measure_imad_peak.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.hbmpc_measure_wide_chains.argtypes = [vp, ci, ci, C.POINTER(C.c_double)]
     lib.hbmpc_measure_mont_mul.argtypes = [vp, ci, ci, C.POINTER(C.c_double)]
+    lib.hbmpc_group_create.argtypes = [C.POINTER(ci), sz, C.POINTER(vp)]
+    lib.hbmpc_group_destroy.argtypes = [vp]
+    lib.hbmpc_group_destroy.restype = None
+    lib.hbmpc_group_size.argtypes = [vp]
+    lib.hbmpc_group_size.restype = sz
+    lib.hbmpc_group_ctx.argtypes = [vp, sz]
+    lib.hbmpc_group_ctx.restype = vp
+    lib.hbmpc_group_shard_range.argtypes = [vp, sz, sz, C.POINTER(sz), C.POINTER(sz)]
+    lib.hbmpc_group_shard_range.restype = None
+    lib.hbmpc_group_compute_shares_batch.argtypes = [vp, sz, sz, sz, vp, vp]
+    lib.hbmpc_group_apply_vandermonde_batch.argtypes = [vp, sz, sz, sz, vp, vp, ci]
+    lib.hbmpc_group_batch_recover.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp, vp]
+    lib.hbmpc_group_batch_recover_secrets.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp]
+    lib.hbmpc_group_robust_interpolate_batch.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -288,6 +305,96 @@ class Context:
         g = C.c_double()
         self._check(self.lib.hbmpc_measure_wide_chains(self.h, chains, warps_per_smsp, C.byref(g)))
         return g.value
+
+
+class Group:
+    """Single-process multi-GPU group (``hbmpc_group``): one context per device, every batch split into contiguous ranges over the
+    devices on internal host threads, no collective.  Calls take host (numpy) buffers."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.hbmpc_group_create(devs, len(devices), C.byref(h))
+        if rc != 0:
+            raise HbmpcError(rc, "hbmpc_group_create")
+        self.h = h
+        self.size = len(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hbmpc_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shard_range(self, B: int, i: int):
+        lo, hi = C.c_size_t(), C.c_size_t()
+        self.lib.hbmpc_group_shard_range(self.h, B, i, C.byref(lo), C.byref(hi))
+        return lo.value, hi.value
+
+    @staticmethod
+    def _host(x):
+        return np.ascontiguousarray(x, dtype=np.uint64)
+
+    def compute_shares_batch(self, coeffs, n: int, out=None):
+        c = self._host(coeffs)
+        B, m = c.shape[0], c.shape[1]
+        out = np.zeros((B, n, 4), dtype=np.uint64) if out is None else out
+        rc = self.lib.hbmpc_group_compute_shares_batch(self.h, n, m - 1, B, c.ctypes.data, out.ctypes.data)
+        if rc != 0:
+            raise HbmpcError(rc)
+        return out
+
+    def apply_vandermonde_batch(self, inp, n: int, recipient_major: bool = False, out=None):
+        x = self._host(inp)
+        B, cols = x.shape[0], x.shape[1]
+        out = np.zeros((n, B, 4) if recipient_major else (B, n, 4), dtype=np.uint64) if out is None else out
+        rc = self.lib.hbmpc_group_apply_vandermonde_batch(self.h, n, cols, B, x.ctypes.data, out.ctypes.data, int(recipient_major))
+        if rc != 0:
+            raise HbmpcError(rc)
+        return out
+
+    def batch_recover(self, sender_ids, evals, n: int, d: int, t: int, want_flags: bool = False, out=None):
+        e = self._host(evals)
+        S, B = e.shape[0], e.shape[1]
+        ids = np.ascontiguousarray(sender_ids, dtype=np.uint64)
+        if out is None:
+            coeffs, path = np.zeros((B, d + 1, 4), dtype=np.uint64), np.zeros((B,), dtype=np.int32)
+            flags = np.zeros((B, (S + 63) // 64), dtype=np.uint64) if want_flags else None
+        else:
+            coeffs, path, flags = out
+        rc = self.lib.hbmpc_group_batch_recover(self.h, n, d, t, S, ids.ctypes.data, B, e.ctypes.data, coeffs.ctypes.data, path.ctypes.data,
+                                                flags.ctypes.data if flags is not None else None)
+        if rc not in (0, DECODING_ERROR):
+            raise HbmpcError(rc)
+        return rc, coeffs, path, flags
+
+    def batch_recover_secrets(self, sender_ids, evals, n: int, d: int, t: int):
+        e = self._host(evals)
+        S, B = e.shape[0], e.shape[1]
+        ids = np.ascontiguousarray(sender_ids, dtype=np.uint64)
+        secrets, path = np.zeros((B, 4), dtype=np.uint64), np.zeros((B,), dtype=np.int32)
+        rc = self.lib.hbmpc_group_batch_recover_secrets(self.h, n, d, t, S, ids.ctypes.data, B, e.ctypes.data, secrets.ctypes.data, path.ctypes.data)
+        if rc not in (0, DECODING_ERROR):
+            raise HbmpcError(rc)
+        return rc, secrets, path
+
+    def robust_interpolate_batch(self, ids, shares, n: int, d: int, t: int, want_flags: bool = False):
+        s = self._host(shares)
+        B, S = s.shape[0], s.shape[1]
+        idv = np.ascontiguousarray(ids, dtype=np.uint64)
+        coeffs, secrets, path = np.zeros((B, d + 1, 4), dtype=np.uint64), np.zeros((B, 4), dtype=np.uint64), np.zeros((B,), dtype=np.int32)
+        flags = np.zeros((B, (S + 63) // 64), dtype=np.uint64) if want_flags else None
+        rc = self.lib.hbmpc_group_robust_interpolate_batch(self.h, n, d, t, S, idv.ctypes.data, B, s.ctypes.data, coeffs.ctypes.data, secrets.ctypes.data,
+                                                           path.ctypes.data, flags.ctypes.data if flags is not None else None)
+        if rc not in (0, DECODING_ERROR):
+            raise HbmpcError(rc)
+        return rc, coeffs, secrets, path, flags
 
 
 def to_limbs(values) -> np.ndarray:

@@ -9,7 +9,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <initializer_list>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hbmpc_b200.h"
@@ -225,12 +227,14 @@ struct DevBuf {
 };
 
 // A lane = a stream with its own scratch.  Lane 0 is the context's (user-visible) stream and serves calls whose buffers
-// are all device pointers; lanes 1..3 pipeline calls with host buffers chunk by chunk (H2D | kernels | D2H overlap).
+// are all device pointers; lanes 1..3 pipeline calls with host buffers chunk by chunk (H2D | kernels | D2H overlap).  In
+// asynchronous mode host-buffer calls only enqueue and alternate between lanes 1..3 and 4..6, so that two consecutive calls run
+// concurrently: a download-bound call (share generation) and an upload-bound one (recovery) then use both PCIe directions at once.
 struct Lane {
     cudaStream_t stream = nullptr;
     DevBuf scratch[12];
 };
-static const int NLANES = 4;
+static const int NLANES = 7, LANES_PER_SET = 3;
 
 struct RecoverTables {
     // optimistic matvec
@@ -316,7 +320,7 @@ struct hbmpc_ctx {
     bool no_er_flags = false;                       // HBMPC_NO_ER_FLAGS=1: calls with flags on a sender subset go straight to the dense check
     bool no_fastpath = false;                       // HBMPC_NO_FASTPATH=1: K3 never takes the all-shares-present inverse-NTT path
     bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
-    size_t chunk_bytes = 16u << 20;                 // HBMPC_CHUNK_MB: target bytes per pipelined host copy
+    size_t chunk_bytes = 64u << 20;                 // HBMPC_CHUNK_MB: target bytes per pipelined host copy (measured: 16 MB 75.3, 64 MB 71.7, 128 MB 69.5 ms per e2e step)
     // status words in mapped pinned host memory (device view d_status, host view h_status): kernels store 1 on the rare
     // error, the host reads them after a stream synchronize -- no copy, no memset on the call path
     unsigned int *d_status = nullptr;  // [0] non-canonical input seen, [2] some item failed to decode
@@ -329,7 +333,7 @@ struct hbmpc_ctx {
     std::map<TableKey, struct NonRobustTables> *nonrobust = nullptr;   // same for the a10 tables
     std::vector<void *> owned;                        // device allocations freed at destroy
     MapRing maps;                                     // per-call arrival-order index maps (order, col_map, chk_map, in_map)
-    unsigned int deferred_bad = 0, deferred_undec = 0;  // async mode: status of earlier enqueue-only calls, reported by hbmpc_ctx_synchronize
+    int lane_set = 0;                                   // async mode: lane set (0: lanes 1..3, 1: lanes 4..6) of the next host-buffer call
     cudaStream_t main_stream() const { return lanes[0].stream; }
 };
 
@@ -559,16 +563,6 @@ static int collect_status(hbmpc_ctx *ctx) {
     if (undec) return HBMPC_DECODING_ERROR;
     return HBMPC_SUCCESS;
 }
-// asynchronous mode: what the status words hold BEFORE a call with host buffers starts belongs to the enqueue-only calls issued
-// earlier; it is kept for hbmpc_ctx_synchronize instead of being reported by (and blamed on) the host-buffer call
-static int fold_deferred(hbmpc_ctx *ctx) {
-    unsigned int bad = 0, undec = 0;
-    int rc = read_status(ctx, bad, undec);
-    if (rc) return rc;
-    ctx->deferred_bad |= bad;
-    ctx->deferred_undec |= undec;
-    return 0;
-}
 // a call that failed half-way (CUDA error, allocation failure): nothing it left in the status words may surface in a later call
 static int abandon_call(hbmpc_ctx *ctx, int rc) {
     for (auto &ln : ctx->lanes)
@@ -584,12 +578,10 @@ static int abandon_call(hbmpc_ctx *ctx, int rc) {
 extern "C" int hbmpc_ctx_synchronize(hbmpc_ctx *ctx) {
     if (!ctx) return HBMPC_INVALID_INPUT;
     cudaSetDevice(ctx->device);
+    for (int i = 1; i < NLANES; ++i) CK(cudaStreamSynchronize(ctx->lanes[i].stream));   // enqueue-only host-buffer calls
     unsigned int bad = 0, undec = 0;
     int rc = read_status(ctx, bad, undec);
     if (rc) return rc;
-    bad |= ctx->deferred_bad;
-    undec |= ctx->deferred_undec;
-    ctx->deferred_bad = ctx->deferred_undec = 0;
     if (bad) return HBMPC_INVALID_INPUT;
     if (undec) return HBMPC_DECODING_ERROR;
     return HBMPC_SUCCESS;
@@ -607,9 +599,11 @@ struct BatchBuf {
     long long J = 0;
     size_t esz = 32;
     size_t B = 0;
+    size_t ld = 0;                           // record-major buffers: distance between records in items (B, or more when the call
+                                             // works on a column range of a wider array: group calls shard the batch axis)
     const std::vector<int> *rows = nullptr;  // record-major host buffers: copy only these records (ascending); others stay stale
 };
-static BatchBuf make_buf(const void *p, size_t B, long long J, bool record_major, size_t esz = 32) {
+static BatchBuf make_buf(const void *p, size_t B, long long J, bool record_major, size_t esz = 32, size_t ld = 0) {
     BatchBuf b;
     b.user = const_cast<void *>(p);
     b.present = p != nullptr;
@@ -618,6 +612,7 @@ static BatchBuf make_buf(const void *p, size_t B, long long J, bool record_major
     b.record_major = record_major;
     b.esz = esz;
     b.B = B;
+    b.ld = ld ? ld : B;
     return b;
 }
 // device view of the chunk [b0, b0+Bc)
@@ -629,7 +624,7 @@ static int chunk_prepare(hbmpc_ctx *ctx, Lane &ln, int slot, const BatchBuf &bb,
     if (!bb.present) return 0;
     if (!bb.host) {
         v.sb = bb.record_major ? 1 : bb.J;
-        v.sj = bb.record_major ? (long long)bb.B : 1;
+        v.sj = bb.record_major ? (long long)bb.ld : 1;
         v.dev = (char *)bb.user + (size_t)b0 * (size_t)v.sb * bb.esz;
         return 0;
     }
@@ -639,14 +634,14 @@ static int chunk_prepare(hbmpc_ctx *ctx, Lane &ln, int slot, const BatchBuf &bb,
         v.sb = 1;
         v.sj = (long long)Bc;
         if (copy_in && !bb.rows)
-            CK(cudaMemcpy2DAsync(v.dev, Bc * bb.esz, (char *)bb.user + b0 * bb.esz, bb.B * bb.esz, Bc * bb.esz, (size_t)bb.J, cudaMemcpyHostToDevice, ln.stream));
+            CK(cudaMemcpy2DAsync(v.dev, Bc * bb.esz, (char *)bb.user + b0 * bb.esz, bb.ld * bb.esz, Bc * bb.esz, (size_t)bb.J, cudaMemcpyHostToDevice, ln.stream));
         if (copy_in && bb.rows) {
             const std::vector<int> &r = *bb.rows;
             for (size_t i = 0; i < r.size();) {  // one 2D copy per run of consecutive records
                 size_t k = i + 1;
                 while (k < r.size() && r[k] == r[k - 1] + 1) ++k;
-                CK(cudaMemcpy2DAsync((char *)v.dev + (size_t)r[i] * Bc * bb.esz, Bc * bb.esz, (char *)bb.user + ((size_t)r[i] * bb.B + b0) * bb.esz,
-                                     bb.B * bb.esz, Bc * bb.esz, k - i, cudaMemcpyHostToDevice, ln.stream));
+                CK(cudaMemcpy2DAsync((char *)v.dev + (size_t)r[i] * Bc * bb.esz, Bc * bb.esz, (char *)bb.user + ((size_t)r[i] * bb.ld + b0) * bb.esz,
+                                     bb.ld * bb.esz, Bc * bb.esz, k - i, cudaMemcpyHostToDevice, ln.stream));
                 i = k;
             }
         }
@@ -661,7 +656,7 @@ static int chunk_prepare(hbmpc_ctx *ctx, Lane &ln, int slot, const BatchBuf &bb,
 static int chunk_commit(hbmpc_ctx *ctx, Lane &ln, const BatchBuf &bb, size_t b0, size_t Bc, const ChunkView &v) {
     if (!bb.present || !bb.host) return 0;
     if (bb.record_major)
-        CK(cudaMemcpy2DAsync((char *)bb.user + b0 * bb.esz, bb.B * bb.esz, v.dev, Bc * bb.esz, Bc * bb.esz, (size_t)bb.J, cudaMemcpyDeviceToHost, ln.stream));
+        CK(cudaMemcpy2DAsync((char *)bb.user + b0 * bb.esz, bb.ld * bb.esz, v.dev, Bc * bb.esz, Bc * bb.esz, (size_t)bb.J, cudaMemcpyDeviceToHost, ln.stream));
     else
         CK(cudaMemcpyAsync((char *)bb.user + b0 * (size_t)bb.J * bb.esz, v.dev, Bc * (size_t)bb.J * bb.esz, cudaMemcpyDeviceToHost, ln.stream));
     return 0;
@@ -671,7 +666,10 @@ static int chunk_commit(hbmpc_ctx *ctx, Lane &ln, const BatchBuf &bb, size_t b0,
 // chunk round-robin over lanes 1..3 so that host->device copies, kernels and device->host copies of neighbouring chunks
 // overlap.  Returns after the host buffers are complete (or, all-device in async mode, after enqueueing).
 static size_t pick_chunk(const hbmpc_ctx *ctx, size_t B, size_t max_item_bytes) {
-    size_t Bc = ctx->chunk_bytes / std::max<size_t>(max_item_bytes, 32);
+    // large chunks move at a higher PCIe rate, but a call should still be cut into enough pieces for its copies and kernels to overlap
+    const size_t item = std::max<size_t>(max_item_bytes, 32);
+    const size_t target = std::min<size_t>(ctx->chunk_bytes, std::max<size_t>((size_t)8 << 20, B * item / 12));
+    size_t Bc = target / item;
     Bc = std::max<size_t>(Bc & ~(size_t)255, 1024);
     if (Bc >= B || B <= 4096) Bc = B;
     return Bc;
@@ -683,21 +681,22 @@ static int run_batched(hbmpc_ctx *ctx, size_t B, bool any_host, size_t max_item_
         if (rc) return abandon_call(ctx, rc);
         return ctx->async ? HBMPC_SUCCESS : collect_status(ctx);
     }
-    if (ctx->async) {
-        int rc = fold_deferred(ctx);
-        if (rc) return rc;
-    }
+    // asynchronous mode: enqueue only (the caller's buffers must stay valid until hbmpc_ctx_synchronize, which also returns the
+    // status), on the lane set the previous host-buffer call did not use
+    const int base = 1 + (ctx->async ? LANES_PER_SET * ctx->lane_set : 0);
+    if (ctx->async) ctx->lane_set ^= 1;
     const size_t Bc = pick_chunk(ctx, B, max_item_bytes);
     CK(cudaEventRecord(ctx->ev_main, ctx->main_stream()));
-    for (int i = 1; i < NLANES; ++i) CK(cudaStreamWaitEvent(ctx->lanes[i].stream, ctx->ev_main, 0));
+    for (int i = 0; i < LANES_PER_SET; ++i) CK(cudaStreamWaitEvent(ctx->lanes[base + i].stream, ctx->ev_main, 0));
     int li = 0, rc = 0;
     for (size_t b0 = 0; b0 < B && !rc; b0 += Bc) {
-        Lane &ln = ctx->lanes[1 + li];
-        li = (li + 1) % (NLANES - 1);
+        Lane &ln = ctx->lanes[base + li];
+        li = (li + 1) % LANES_PER_SET;
         rc = body(ln, b0, std::min(Bc, B - b0));
     }
-    for (int i = 1; i < NLANES; ++i) {
-        cudaError_t e = cudaStreamSynchronize(ctx->lanes[i].stream);
+    if (ctx->async && !rc) return HBMPC_SUCCESS;
+    for (int i = 0; i < LANES_PER_SET; ++i) {
+        cudaError_t e = cudaStreamSynchronize(ctx->lanes[base + i].stream);
         if (e != cudaSuccess && !rc) {
             ctx->err = std::string("pipeline lane: ") + cudaGetErrorString(e);
             rc = HBMPC_CUDA_ERROR;
@@ -911,8 +910,8 @@ static int get_vandermonde(hbmpc_ctx *ctx, size_t n, size_t cols, uint4 **out) {
 // ------------------------------------------------------------------------------------------------ K1 / K2
 // out[b][r] = sum_c M[r][c] in[b][c]: M == nullptr selects the domain transform (NTT) with `n` outputs
 static int apply_map(hbmpc_ctx *ctx, const uint4 *M, const uint4 *tw, int logn, size_t rows, size_t cols, size_t B, const uint64_t *in,
-                     uint64_t *out, int recipient_major) {
-    BatchBuf bi = make_buf(in, B, (long long)cols, false), bo = make_buf(out, B, (long long)rows, recipient_major != 0);
+                     uint64_t *out, int recipient_major, size_t ld_out = 0) {
+    BatchBuf bi = make_buf(in, B, (long long)cols, false), bo = make_buf(out, B, (long long)rows, recipient_major != 0, 32, ld_out);
     auto body = [&](Lane &ln, size_t b0, size_t Bc) -> int {
         ChunkView vi, vo;
         int rc;
@@ -947,7 +946,7 @@ static int apply_map(hbmpc_ctx *ctx, const uint4 *M, const uint4 *tw, int logn, 
     return run_batched(ctx, B, bi.host || bo.host, std::max(rows, cols) * 32, body);
 }
 
-static int apply_domain(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out, int recipient_major) {
+static int apply_domain(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out, int recipient_major, size_t ld_out = 0) {
     const int N = domain_size(n);
     int logn = 0;
     while ((1 << logn) < N) ++logn;
@@ -955,12 +954,12 @@ static int apply_domain(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const u
         uint4 *V = nullptr;
         int rc = get_vandermonde(ctx, n, cols, &V);
         if (rc) return rc;
-        return apply_map(ctx, V, nullptr, 0, n, cols, B, in, out, recipient_major);
+        return apply_map(ctx, V, nullptr, 0, n, cols, B, in, out, recipient_major, ld_out);
     }
     uint4 *tw = nullptr;
     int rc = get_twiddles(ctx, N, &tw);
     if (rc) return rc;
-    return apply_map(ctx, nullptr, tw, logn, n, cols, B, in, out, recipient_major);
+    return apply_map(ctx, nullptr, tw, logn, n, cols, B, in, out, recipient_major, ld_out);
 }
 
 extern "C" int hbmpc_compute_shares_batch(hbmpc_ctx *ctx, size_t n, size_t d, size_t B, const uint64_t *coeffs, uint64_t *shares) {
@@ -1395,7 +1394,8 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
 // ------------------------------------------------------------------------------------------------ K3 / K4
 // shared implementation: element (item b, arrival j) of `in` is sender-major [S][B] (K3) or codeword-major [B][S] (K4)
 static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, const size_t *ids, size_t B, const uint64_t *in,
-                        bool sender_major, uint64_t *coeffs, bool secrets_only, uint64_t *secrets, int32_t *path, uint64_t *flags) {
+                        bool sender_major, uint64_t *coeffs, bool secrets_only, uint64_t *secrets, int32_t *path, uint64_t *flags,
+                        size_t ld_in = 0) {
     // validation order of robust_interpolate.rs:290-341 / :100-142
     if (n < 3 * t + 1) return HBMPC_INVALID_INPUT;
     if (S == 0 || !ids) return HBMPC_INVALID_INPUT;
@@ -1462,7 +1462,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
     const int fw = want_flags ? (int)((S + 63) / 64) : 0;
     const bool want_secrets = !secrets_only && secrets != nullptr;
 
-    BatchBuf bi = make_buf(in, B, (long long)S, sender_major);
+    BatchBuf bi = make_buf(in, B, (long long)S, sender_major, 32, sender_major ? ld_in : 0);
     BatchBuf bc = make_buf(secrets_only ? secrets : coeffs, B, T.mout, false);
     BatchBuf bp = make_buf(path, B, 1, false, 4);
     BatchBuf bf = make_buf(flags, B, fw > 0 ? fw : 1, false, 8);
@@ -1474,7 +1474,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
     // which some item fails are re-run afterwards with every sender vector uploaded (robust decoding needs them all).
     std::vector<int> lean_rows;
     BatchBuf bi_lean = bi;
-    const bool lean = bi.host && sender_major && !want_flags && S > needed;
+    const bool lean = bi.host && sender_major && !want_flags && S > needed && !ctx->async;   // (needs a host decision between its two phases)
     size_t chunk_full = 0;
     if (lean) {
         for (size_t i = 0; i < needed; ++i) lean_rows.push_back(order[i]);
@@ -2093,6 +2093,119 @@ extern "C" int hbmpc_pack_share_records(hbmpc_ctx *ctx, size_t count, const uint
     ctx->launches++;
     CK(cudaGetLastError());
     return ctx->async ? HBMPC_SUCCESS : collect_status(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------ single-process multi-GPU groups
+// The reference party is ONE process (honeybadger/mod.rs:245-257) that issues all sessions' work before awaiting (:1362-1375); its
+// batches are maps over independent secrets / chunks / codewords.  A group owns one context per device and splits every
+// batch into contiguous ranges [g*B/G, (g+1)*B/G), one host thread per device, constant tables replicated, NO collective: results
+// land in the caller's (host) buffers in batch order.  Sender-major / recipient-major arrays are sharded along their batch axis
+// through the leading dimension of the per-device calls.
+struct hbmpc_group {
+    std::vector<hbmpc_ctx *> ctx;
+};
+
+extern "C" int hbmpc_group_create(const int *devices, size_t n_devices, hbmpc_group **out) {
+    if (!out || !devices || n_devices == 0 || n_devices > 64) return HBMPC_INVALID_INPUT;
+    *out = nullptr;
+    hbmpc_group *g = new hbmpc_group();
+    for (size_t i = 0; i < n_devices; ++i) {
+        hbmpc_ctx *c = nullptr;
+        int rc = hbmpc_ctx_create(devices[i], &c);
+        if (rc != HBMPC_SUCCESS) {
+            for (hbmpc_ctx *p : g->ctx) hbmpc_ctx_destroy(p);
+            delete g;
+            return rc;
+        }
+        g->ctx.push_back(c);
+    }
+    *out = g;
+    return HBMPC_SUCCESS;
+}
+extern "C" void hbmpc_group_destroy(hbmpc_group *g) {
+    if (!g) return;
+    for (hbmpc_ctx *p : g->ctx) hbmpc_ctx_destroy(p);
+    delete g;
+}
+extern "C" size_t hbmpc_group_size(const hbmpc_group *g) { return g ? g->ctx.size() : 0; }
+extern "C" hbmpc_ctx *hbmpc_group_ctx(hbmpc_group *g, size_t i) { return (g && i < g->ctx.size()) ? g->ctx[i] : nullptr; }
+// contiguous range of member i: [lo, hi)
+extern "C" void hbmpc_group_shard_range(const hbmpc_group *g, size_t B, size_t i, size_t *lo, size_t *hi) {
+    const size_t G = g ? g->ctx.size() : 1;
+    if (lo) *lo = B * i / G;
+    if (hi) *hi = B * (i + 1) / G;
+}
+
+// runs fn(member, lo, hi) on one host thread per device; returns the first non-zero status in member order
+template <typename Fn>
+static int group_run(hbmpc_group *g, size_t B, Fn fn) {
+    const size_t G = g->ctx.size();
+    std::vector<int> rcs(G, 0);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < G; ++i) {
+        const size_t lo = B * i / G, hi = B * (i + 1) / G;
+        if (hi == lo) continue;
+        th.emplace_back([&, i, lo, hi]() {
+            cudaSetDevice(g->ctx[i]->device);
+            rcs[i] = fn(g->ctx[i], lo, hi);
+        });
+    }
+    for (auto &t : th) t.join();
+    for (size_t i = 0; i < G; ++i)
+        if (rcs[i]) return rcs[i];
+    return HBMPC_SUCCESS;
+}
+static bool group_host_only(std::initializer_list<const void *> ptrs) {
+    for (const void *p : ptrs)
+        if (p && is_device_ptr(p)) return false;
+    return true;
+}
+
+extern "C" int hbmpc_group_compute_shares_batch(hbmpc_group *g, size_t n, size_t d, size_t B, const uint64_t *coeffs, uint64_t *shares) {
+    if (!g) return HBMPC_INVALID_INPUT;
+    if (n <= d) return HBMPC_INVALID_INPUT;
+    if (!domain_size(n)) return HBMPC_NO_SUITABLE_DOMAIN;
+    if (B == 0) return HBMPC_SUCCESS;
+    if (!coeffs || !shares || !group_host_only({coeffs, shares})) return HBMPC_INVALID_INPUT;   // a group call takes host buffers
+    return group_run(g, B, [&](hbmpc_ctx *c, size_t lo, size_t hi) {
+        return hbmpc_compute_shares_batch(c, n, d, hi - lo, coeffs + lo * (d + 1) * 4, shares + lo * n * 4);
+    });
+}
+
+extern "C" int hbmpc_group_apply_vandermonde_batch(hbmpc_group *g, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out, int recipient_major) {
+    if (!g) return HBMPC_INVALID_INPUT;
+    if (cols == 0 || cols > 256) return HBMPC_INVALID_INPUT;
+    if (!domain_size(n)) return HBMPC_NO_SUITABLE_DOMAIN;
+    if (B == 0) return HBMPC_SUCCESS;
+    if (!in || !out || !group_host_only({in, out})) return HBMPC_INVALID_INPUT;
+    return group_run(g, B, [&](hbmpc_ctx *c, size_t lo, size_t hi) {
+        cudaSetDevice(c->device);
+        return apply_domain(c, n, cols, hi - lo, in + lo * cols * 4, recipient_major ? out + lo * 4 : out + lo * n * 4, recipient_major, recipient_major ? B : 0);
+    });
+}
+
+static int group_recover(hbmpc_group *g, size_t n, size_t d, size_t t, size_t S, const size_t *ids, size_t B, const uint64_t *in, bool sender_major,
+                         uint64_t *coeffs, bool secrets_only, uint64_t *secrets, int32_t *path, uint64_t *flags) {
+    if (!g) return HBMPC_INVALID_INPUT;
+    if (B == 0) return HBMPC_INVALID_INPUT;
+    if (!group_host_only({in, coeffs, secrets, path, flags})) return HBMPC_INVALID_INPUT;
+    const size_t m = d + 1, fw = (S + 63) / 64;
+    return group_run(g, B, [&](hbmpc_ctx *c, size_t lo, size_t hi) {
+        return recover_impl(c, n, d, t, S, ids, hi - lo, sender_major ? in + lo * 4 : in + lo * S * 4, sender_major, coeffs ? coeffs + lo * m * 4 : nullptr,
+                            secrets_only, secrets ? secrets + lo * 4 : nullptr, path ? path + lo : nullptr, flags ? flags + lo * fw : nullptr, sender_major ? B : 0);
+    });
+}
+extern "C" int hbmpc_group_batch_recover(hbmpc_group *g, size_t n, size_t d, size_t t, size_t S, const size_t *sender_ids, size_t B, const uint64_t *evals,
+                                         uint64_t *coeffs, int32_t *path, uint64_t *flags) {
+    return group_recover(g, n, d, t, S, sender_ids, B, evals, true, coeffs, false, nullptr, path, flags);
+}
+extern "C" int hbmpc_group_batch_recover_secrets(hbmpc_group *g, size_t n, size_t d, size_t t, size_t S, const size_t *sender_ids, size_t B,
+                                                 const uint64_t *evals, uint64_t *secrets, int32_t *path) {
+    return group_recover(g, n, d, t, S, sender_ids, B, evals, true, nullptr, true, secrets, path, nullptr);
+}
+extern "C" int hbmpc_group_robust_interpolate_batch(hbmpc_group *g, size_t n, size_t d, size_t t, size_t S, const size_t *ids, size_t B, const uint64_t *shares,
+                                                    uint64_t *coeffs, uint64_t *secrets, int32_t *path, uint64_t *flags) {
+    return group_recover(g, n, d, t, S, ids, B, shares, false, coeffs, false, secrets, path, flags);
 }
 
 extern "C" int hbmpc_measure_imad_peak(hbmpc_ctx *ctx, int variant, double *giga_inst_per_s, double *elapsed_ms) {
