@@ -430,6 +430,31 @@ def leg_c5(torch, hb, ctx, stream, dev, cm, log2, rank):
     return out
 
 
+def leg_sampler(torch, hb, ctx, stream, dev, cm):
+    """SURVEY 8f N4: the polynomials of 2^20 sharings (n=64, t=21) drawn on the device from a 32-byte seed (StdRng = ChaCha12 + Fp::rand
+    rejection sampling, bit-compatible with the reference's generator) instead of uploaded: 704 bytes per secret stay off PCIe."""
+    B, d = 1 << 20, DEG
+    seed = bytes(range(32))
+    coeffs = torch.empty((B, d + 1, 4), dtype=torch.int64, device=dev)
+    ctx.set_async(False)
+    ctx.sample_polynomials(seed, B, d, out=coeffs)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ctx.sample_polynomials(seed, B, d, out=coeffs)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 3
+    ctx.set_async(True)
+    out = {"workload": "hbmpc_sample_polynomials: 2^20 sharings of degree 21 (d+2 = 23 Fp::rand draws each, ~25.4 ChaCha12 candidates), device-resident output",
+           "sharings": B, "ms": 1e3 * dt, "field_draws_per_s": B * (d + 2) / dt, "upload_bytes_saved_per_secret": (d + 1) * 32}
+    if cm is not None:
+        from oracle import chacha_fr as cf
+        want = cf.sample_polynomials(seed, 64, d)
+        got = hb.from_limbs(_np(coeffs[:64]))
+        out["parity_sample"] = {"items": 64, "ok": bool(got == want), "what": "first 64 coefficient vectors == oracle/chacha_fr.py (ChaCha12 pinned by RFC 7539 / strombergson vectors; arkworks byte parity unpinned)"}
+    return out
+
+
 def leg_group(torch, hb, n_dev, log2_total, cm):
     """One process, n_dev GPUs: member contexts of an hbmpc_group driven from this process."""
     ids = np.arange(N_PARTIES)
@@ -702,6 +727,8 @@ def run_b200(args):
             configs["c2"] = leg_c2(torch, hb, ctx, stream, dev, cm, args.log2_c2)
             configs["c4"] = leg_c4(torch, hb, ctx, stream, dev, cm, args.log2_c4)
             torch.cuda.empty_cache()
+        if n_gpus == 1:
+            configs["n4_device_sampling"] = leg_sampler(torch, hb, ctx, stream, dev, cm)
         c5 = leg_c5(torch, hb, ctx, stream, dev, cm, args.log2_c5, rank)
         tot5 = max_over_ranks([c5.pop("_total_s")])[0]
         ok5 = min(max_over_ranks([0.0 if c5["self_consistent"] else 1.0])) == 0.0
@@ -714,12 +741,13 @@ def run_b200(args):
     # then wait for all; and the same through the group's host-buffer entry points
     if world > 1 and configs_on:
         barrier()
+        cpu_group = dist.new_group(backend="gloo")   # the other ranks must wait on the CPU: an NCCL barrier would spin on their GPUs
         if rank == 0:
             try:
                 configs["c3_group_single_process"] = leg_group(torch, hb, world, args.log2_batch, cm)
             except Exception as exc:   # never lose the headline line to this leg
                 configs["c3_group_single_process"] = {"error": repr(exc)}
-        barrier()
+        dist.barrier(group=cpu_group)
 
     if rank == 0:
         shares_per_step = 2 * B_all * N_PARTIES

@@ -128,6 +128,20 @@ int hbmpc_elementwise(hbmpc_ctx *ctx, int op, size_t count, const uint64_t *a, c
 int hbmpc_unpack_share_records(hbmpc_ctx *ctx, size_t count, const void *records, uint64_t *values, uint64_t *ids, uint64_t *degrees);
 int hbmpc_pack_share_records(hbmpc_ctx *ctx, size_t count, const uint64_t *values, size_t per_id, size_t degree, void *records);
 
+/* N4.  The randomness of a sharing as the reference draws it, on the device.  The reference samples the polynomial inside
+ * compute_shares (robust_interpolate.rs:68-69: DensePolynomial::rand(d, rng) with coefficient 0 overwritten by the secret; callers draw
+ * the secret with F::rand first: share_gen.rs:250, double_share_generation.rs:167) from rand 0.8 `StdRng` (ChaCha12, 64-bit block
+ * counter from 0, stream 0) with ark-ff 0.5 `Fp::rand` (four next_u64 limbs, top bit cleared, redrawn while >= r, accepted limbs = the
+ * Montgomery representation).  seed32 = the 32-byte StdRng::from_seed seed.
+ *   hbmpc_sample_fr_batch:     out[count] = the first `count` elements `F::rand(&mut rng)` returns (canonical limbs).
+ *   hbmpc_sample_polynomials:  coeffs[B][d+1] of B consecutive sharings drawn from ONE generator.  secrets == NULL: every sharing draws
+ *       its secret and then d+1 coefficients of which the first is dropped (d+2 draws: the RanSha / DouSha dealers);  secrets != NULL
+ *       (secrets[B], host or device): d+1 draws per sharing, the first dropped, coeffs[b][0] = secrets[b] (the C ABI path,
+ *       ffi/c_bindings/share/mod.rs:418-425).  Feed the result to hbmpc_compute_shares_batch: a dealer uploads a seed, not 32*(d+1)
+ *       bytes per secret.  out / coeffs may be host or device pointers; at most ~3.8e9 draws per call. */
+int hbmpc_sample_fr_batch(hbmpc_ctx *ctx, const uint8_t *seed32, size_t count, uint64_t *out);
+int hbmpc_sample_polynomials(hbmpc_ctx *ctx, const uint8_t *seed32, size_t B, size_t d, const uint64_t *secrets, uint64_t *coeffs);
+
 /* Single-process multi-GPU.  The reference party is one process that issues all sessions' work before awaiting
  * (honeybadger/mod.rs:245-257,1362-1375); every call of this path is a map over independent secrets / chunks / codewords, so a group
  * (one context per device, tables replicated) splits the batch into contiguous ranges [g*B/G, (g+1)*B/G), one internal host thread

@@ -34,6 +34,7 @@ EXPORTS = [
     "hbmpc_apply_matrix_batch", "hbmpc_batch_recover", "hbmpc_batch_recover_secrets", "hbmpc_robust_interpolate_batch",
     "hbmpc_nonrobust_recover_batch", "hbmpc_elementwise", "hbmpc_unpack_share_records", "hbmpc_pack_share_records",
     "hbmpc_measure_imad_peak", "hbmpc_measure_wide_chains", "hbmpc_measure_mont_mul",
+    "hbmpc_sample_fr_batch", "hbmpc_sample_polynomials",
     "hbmpc_group_create", "hbmpc_group_destroy", "hbmpc_group_size", "hbmpc_group_ctx", "hbmpc_group_shard_range",
     "hbmpc_group_compute_shares_batch", "hbmpc_group_apply_vandermonde_batch", "hbmpc_group_batch_recover",
     "hbmpc_group_batch_recover_secrets", "hbmpc_group_robust_interpolate_batch",
@@ -81,6 +82,8 @@ def load_library():
     lib.hbmpc_measure_imad_peak.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.hbmpc_measure_wide_chains.argtypes = [vp, ci, ci, C.POINTER(C.c_double)]
     lib.hbmpc_measure_mont_mul.argtypes = [vp, ci, ci, C.POINTER(C.c_double)]
+    lib.hbmpc_sample_fr_batch.argtypes = [vp, vp, sz, vp]
+    lib.hbmpc_sample_polynomials.argtypes = [vp, vp, sz, sz, vp, vp]
     lib.hbmpc_group_create.argtypes = [C.POINTER(ci), sz, C.POINTER(vp)]
     lib.hbmpc_group_destroy.argtypes = [vp]
     lib.hbmpc_group_destroy.restype = None
@@ -295,6 +298,24 @@ class Context:
         self._check(self.lib.hbmpc_measure_imad_peak(self.h, variant, C.byref(g), C.byref(ms)))
         return g.value, ms.value
 
+
+    # -- N4: device-side sampling (StdRng = ChaCha12 + ark-ff Fp::rand)
+    def sample_fr_batch(self, seed: bytes, count: int, out=None):
+        assert len(seed) == 32
+        sd = np.frombuffer(seed, dtype=np.uint8).copy()
+        out = np.zeros((count, 4), dtype=np.uint64) if out is None else out
+        self._check(self.lib.hbmpc_sample_fr_batch(self.h, sd.ctypes.data, count, _ptr(out)))
+        return out
+
+    def sample_polynomials(self, seed: bytes, B: int, d: int, secrets=None, out=None):
+        assert len(seed) == 32
+        sd = np.frombuffer(seed, dtype=np.uint8).copy()
+        out = np.zeros((B, d + 1, 4), dtype=np.uint64) if out is None else out
+        sec = None
+        if secrets is not None:
+            sec = secrets if _is_torch(secrets) else np.ascontiguousarray(secrets, dtype=np.uint64)
+        self._check(self.lib.hbmpc_sample_polynomials(self.h, sd.ctypes.data, B, d, _ptr(sec) if sec is not None else None, _ptr(out)))
+        return out
 
     def measure_mont_mul(self, ilp: int, warps_per_smsp: int) -> float:
         g = C.c_double()

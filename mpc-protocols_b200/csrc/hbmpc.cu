@@ -20,6 +20,7 @@
 #include "ntt.cuh"
 #include "ntt16x.cuh"
 #include "robust.cuh"
+#include "sampler.cuh"
 #include "tables.hpp"
 
 using namespace hb;
@@ -668,7 +669,7 @@ static int chunk_commit(hbmpc_ctx *ctx, Lane &ln, const BatchBuf &bb, size_t b0,
 static size_t pick_chunk(const hbmpc_ctx *ctx, size_t B, size_t max_item_bytes) {
     // large chunks move at a higher PCIe rate, but a call should still be cut into enough pieces for its copies and kernels to overlap
     const size_t item = std::max<size_t>(max_item_bytes, 32);
-    const size_t target = std::min<size_t>(ctx->chunk_bytes, std::max<size_t>((size_t)8 << 20, B * item / 12));
+    const size_t target = std::min<size_t>(ctx->chunk_bytes, std::max<size_t>((size_t)16 << 20, B * item / 12));
     size_t Bc = target / item;
     Bc = std::max<size_t>(Bc & ~(size_t)255, 1024);
     if (Bc >= B || B <= 4096) Bc = B;
@@ -2093,6 +2094,70 @@ extern "C" int hbmpc_pack_share_records(hbmpc_ctx *ctx, size_t count, const uint
     ctx->launches++;
     CK(cudaGetLastError());
     return ctx->async ? HBMPC_SUCCESS : collect_status(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------ N4: device-side sampling
+// accepted elements 0 .. want-1 of the Fp::rand stream of StdRng::from_seed(seed), laid out by `mode` (sampler.cuh); out: device or host
+static int sample_stream(hbmpc_ctx *ctx, const uint8_t *seed, unsigned long long want, int mode, int per, size_t out_elems, uint64_t *out,
+                         const uint64_t *secrets, size_t B) {
+    if (!ctx || !seed || !out) return HBMPC_INVALID_INPUT;
+    if (want == 0) return HBMPC_SUCCESS;
+    cudaSetDevice(ctx->device);
+    Lane &ln = ctx->lanes[0];
+    cudaStream_t st = ln.stream;
+    const bool host_out = !is_device_ptr(out);
+    void *dout = out;
+    int rc;
+    if (host_out && (rc = scratch_get(ctx, ln, 1, out_elems * 32, &dout))) return rc;
+    SampleArgs a{};
+    for (int i = 0; i < 8; ++i) a.key[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) | ((uint32_t)seed[4 * i + 3] << 24);
+    a.out = (uint4 *)dout;
+    a.want = want;
+    a.mode = mode;
+    a.per = per;
+    // acceptance probability r / 2^255 = 0.9057: examine want / 0.9 candidates (+ slack); more only if that was not enough
+    unsigned long long ncand = (unsigned long long)((double)want / 0.9) + 8192;
+    for (;;) {
+        if (ncand >= (1ull << 32)) return HBMPC_INVALID_INPUT;
+        const unsigned int nblk = (unsigned int)((ncand + SAMPLE_THREADS - 1) / SAMPLE_THREADS);
+        void *cnt = nullptr;
+        if ((rc = scratch_get(ctx, ln, 0, (size_t)nblk * 4 + 64, &cnt))) return rc;
+        a.ncand = ncand;
+        a.counts = (unsigned int *)cnt + 16;
+        a.total = (unsigned long long *)cnt;
+        sample_count_kernel<<<nblk, SAMPLE_THREADS, 0, st>>>(a);
+        sample_scan_kernel<<<1, 1024, 0, st>>>(a.counts, nblk, a.total);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+        unsigned long long total = 0;
+        CK(cudaMemcpyAsync(&total, a.total, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (total >= want) {
+            sample_emit_kernel<<<nblk, SAMPLE_THREADS, 0, st>>>(a);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            break;
+        }
+        ncand *= 2;
+    }
+    if (mode == 2 && secrets) {   // coefficient 0 of every sharing = the caller's secret
+        const bool host_sec = !is_device_ptr(secrets);
+        if (host_sec) CK(cudaMemcpy2DAsync(dout, (size_t)(per + 1) * 32, secrets, 32, 32, B, cudaMemcpyHostToDevice, st));
+        else CK(cudaMemcpy2DAsync(dout, (size_t)(per + 1) * 32, secrets, 32, 32, B, cudaMemcpyDeviceToDevice, st));
+    }
+    if (host_out) CK(cudaMemcpyAsync(out, dout, out_elems * 32, cudaMemcpyDeviceToHost, st));
+    if (host_out || !ctx->async) CK(cudaStreamSynchronize(st));
+    return HBMPC_SUCCESS;
+}
+
+extern "C" int hbmpc_sample_fr_batch(hbmpc_ctx *ctx, const uint8_t *seed32, size_t count, uint64_t *out) {
+    return sample_stream(ctx, seed32, count, 0, 0, count, out, nullptr, 0);
+}
+extern "C" int hbmpc_sample_polynomials(hbmpc_ctx *ctx, const uint8_t *seed32, size_t B, size_t d, const uint64_t *secrets, uint64_t *coeffs) {
+    if (B == 0) return HBMPC_SUCCESS;
+    if (d > 255) return HBMPC_INVALID_INPUT;
+    if (secrets) return sample_stream(ctx, seed32, (unsigned long long)B * (d + 1), 2, (int)d, B * (d + 1), coeffs, secrets, B);
+    return sample_stream(ctx, seed32, (unsigned long long)B * (d + 2), 1, (int)d, B * (d + 1), coeffs, nullptr, B);
 }
 
 // ------------------------------------------------------------------------------------------------ single-process multi-GPU groups
