@@ -179,7 +179,9 @@ class BatchReconNode {
         switch (msg.msg_type) {
             case BatchReconMsgType::Eval: {
                 const U256 val = detail::deser_f(msg.payload.data(), msg.payload.size());
-                BatchReconStore &store = get_or_create_store(msg.session_id);
+                BatchReconStore *sp = live_store(msg.session_id);
+                if (!sp) return;   // terminated session: late / duplicate message, dropped (batch_recon.rs:519-530)
+                BatchReconStore &store = *sp;
                 if (!seen(store.evals_received, sender_id)) store.evals_received.push_back(Share{val, sender_id, degree});
                 if (store.evals_received.size() >= needed && !store.y_j) {
                     U256 value;
@@ -197,7 +199,9 @@ class BatchReconNode {
             }
             case BatchReconMsgType::Reveal: {
                 const U256 y = detail::deser_f(msg.payload.data(), msg.payload.size());
-                BatchReconStore &store = get_or_create_store(msg.session_id);
+                BatchReconStore *sp = live_store(msg.session_id);
+                if (!sp) return;
+                BatchReconStore &store = *sp;
                 if (!seen(store.reveals_received, sender_id)) store.reveals_received.push_back(Share{y, sender_id, degree});
                 if (store.reveals_received.size() >= needed && !store.secrets) {
                     std::vector<U256> poly;
@@ -215,7 +219,9 @@ class BatchReconNode {
             case BatchReconMsgType::EvalBatch: {
                 std::vector<U256> values = detail::deser_bounded_vec(msg.payload, msg.payload.size());
                 if (values.empty()) throw BatchReconError(BatchReconError::InvalidInput, "empty EvalBatch payload");
-                BatchReconStore &store = get_or_create_store(msg.session_id);
+                BatchReconStore *sp = live_store(msg.session_id);
+                if (!sp) return;
+                BatchReconStore &store = *sp;
                 if (!store.batch_evals_received.empty() && store.batch_evals_received[0].second.size() != values.size())
                     throw BatchReconError(BatchReconError::InvalidInput, "inconsistent EvalBatch width");
                 if (!seen(store.batch_evals_received, sender_id)) store.batch_evals_received.emplace_back(sender_id, std::move(values));
@@ -231,7 +237,9 @@ class BatchReconNode {
             case BatchReconMsgType::RevealBatch: {
                 std::vector<U256> values = detail::deser_bounded_vec(msg.payload, msg.payload.size());
                 if (values.empty()) throw BatchReconError(BatchReconError::InvalidInput, "empty RevealBatch payload");
-                BatchReconStore &store = get_or_create_store(msg.session_id);
+                BatchReconStore *sp = live_store(msg.session_id);
+                if (!sp) return;
+                BatchReconStore &store = *sp;
                 if (!store.batch_reveals_received.empty() && store.batch_reveals_received[0].second.size() != values.size())
                     throw BatchReconError(BatchReconError::InvalidInput, "inconsistent RevealBatch width");
                 if (!seen(store.batch_reveals_received, sender_id)) store.batch_reveals_received.emplace_back(sender_id, std::move(values));
@@ -260,6 +268,12 @@ class BatchReconNode {
     void clear_entire_store() { store_.clear(); }
     size_t store_len() const { return store_.size(); }
     BatchReconStore &get_or_create_store(SessionId session_id) { return store_[session_id]; }
+    // get_or_create_store as the handler uses it (batch_recon.rs:491-530): Ok(None) -- here nullptr -- once the session's secrets are
+    // set, so that a late or duplicate message of a finished session is dropped instead of being validated and stored again
+    BatchReconStore *live_store(SessionId session_id) {
+        BatchReconStore &st = store_[session_id];
+        return st.secrets ? nullptr : &st;
+    }
 
    private:
     Context &ctx_;

@@ -161,6 +161,15 @@ static void test_batch_reconstruction_many(Context &ctx, bool byzantine) {
         REQUIRE(got.size() == secrets.size());
         for (size_t k = 0; k < secrets.size(); ++k) REQUIRE(got[k] == secrets[k]);
     }
+    {   // late / duplicate messages of a TERMINATED session are dropped (batch_recon.rs:519-530), whatever they carry: no error, no state
+        const size_t who = n - 1, before = nodes[who].store_len();
+        const std::vector<uint8_t> secrets_before = nodes[who].get_store(sid);
+        BatchReconMsg late1{sid, 2, BatchReconMsgType::RevealBatch, detail::ser_vec({fr_from_u64(1)})};   // wrong width: would be InvalidInput on a live session
+        BatchReconMsg late2{sid, 3, BatchReconMsgType::EvalBatch, detail::ser_vec({fr_from_u64(9), fr_from_u64(9)})};
+        nodes[who].process(late1, nets[who]);
+        nodes[who].process(late2, nets[who]);
+        REQUIRE(nodes[who].store_len() == before && nodes[who].get_store(sid) == secrets_before && nodes[who].output.size() == 1);
+    }
     // reference-shaped input validation
     try { nodes[n - 1].init_batch_reconstruct_many({all_shares[n - 1][0]}, sid, nets[n - 1]); REQUIRE(false); } catch (const BatchReconError &e) { REQUIRE(e.kind == BatchReconError::InvalidInput); }
     {

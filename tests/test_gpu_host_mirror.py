@@ -208,3 +208,26 @@ def test_group_calls_from_c(tmp_path):
         res = subprocess.run([str(exe), members], capture_output=True, text=True, timeout=600)
         assert res.returncode == 0, res.stdout + res.stderr
         assert "identical to the single-context results" in res.stdout
+
+
+def _compile_cpp(tmp_path, name):
+    exe = tmp_path / name
+    lib_dir = os.path.join(ROOT, "mpc-protocols_b200")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "host", name + ".cpp"),
+           "-L", lib_dir, "-lhbmpc_b200", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def test_triple_mul_mirror_compiles_and_links(tmp_path):
+    _compile_cpp(tmp_path, "triple_mul_test")
+
+
+@pytest.mark.gpu
+def test_triple_generation_and_multiplication_over_fake_network(tmp_path):
+    """BASELINE configs[0]: 4 parties, t = 1, Beaver triples from TripleGenNode, 10*10 = 100 and 20*20 = 400 through Multiply
+    (mpc/tests/node_test.rs:584-764), five multiplications with a remainder value and a Byzantine party, and n = 16, t = 5."""
+    exe = _compile_cpp(tmp_path, "triple_mul_test")
+    res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "all triple generation / multiplication tests passed" in res.stdout
