@@ -3,7 +3,7 @@
 // The reference draws the polynomial INSIDE compute_shares (robust_interpolate.rs:68-69: DensePolynomial::rand(degree, rng), coefficient
 // 0 overwritten by the secret; share_gen.rs:250 draws the secret with F::rand first) from rand 0.8's StdRng.  Neither generator nor
 // sampler is in the reference tree (rand_chacha 0.3, ark-ff 0.5: crates.io dependencies); their published algorithms are restated here
-// and in oracle/chacha_fr.py:
+// (the CPU restatement that the tests check this file against is tests-side: chacha_fr.py):
 //   StdRng = ChaCha12: key = 32-byte seed, 64-bit block counter (state words 12-13) from 0, stream id 0; next_u64 = two consecutive
 //   output words, low word first.   Fp::rand = four next_u64 limbs, top bit of the last limb cleared, redrawn while >= r; the accepted
 //   limbs are the Montgomery representation, so the value is limbs * 2^-256 mod r (one Montgomery product with 1).

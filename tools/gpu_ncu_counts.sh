@@ -1,17 +1,30 @@
 #!/bin/bash
 # Executed-instruction evidence for bench.py's roofline (profiles/r02_executed_counts.json): ncu source counters (per SASS line
-# executed counts) of the headline transforms, of the dense kernel and of one K4 call, exported as source-page csv.
+# executed counts) of the headline transforms, of the dense kernel and of one K4 call.  The source pages are reduced ON THE BOX to
+# small per-kernel JSON summaries (tools/ncu_exec_counts.py): gpurun returns at most 64 MiB.
 # usage: bash tools/gpu_ncu_counts.sh <tag>
 TAG=${1:-rXX}
 mkdir -p gpurun_out
 SEC="--section SourceCounters --section LaunchStats --section SpeedOfLight --section WarpStateStats --section ComputeWorkloadAnalysis --section MemoryWorkloadAnalysis"
+# headline transforms: one K1 and one K3 launch at 2^20 items (ncu --set full: also the dram traffic of profiles/ncu_traffic_per_2p20.json)
+python tools/ncu_ntt.py > gpurun_out/ncu_plain_ntt_$TAG.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"ntt" -s 2 -c 2 -o /tmp/ntt_$TAG python tools/ncu_ntt.py > gpurun_out/ncu_ntt_$TAG.log 2>&1
+ncu -i /tmp/ntt_$TAG.ncu-rep --page raw --csv > gpurun_out/raw_ntt_$TAG.csv 2>/dev/null
+ncu -i /tmp/ntt_$TAG.ncu-rep --page source --csv > /tmp/src_ntt_$TAG.csv 2>/dev/null
+python tools/ncu_exec_counts.py /tmp/src_ntt_$TAG.csv --items 1048576 --json gpurun_out/exec_ntt_$TAG.json > gpurun_out/exec_ntt_$TAG.txt
+# dense kernel (43 senders, flags): one launch at 2^20 chunks
 python tools/ncu_ntt.py --what dense --reps 2 > gpurun_out/ncu_plain_dense_$TAG.log 2>&1 && \
-ncu $SEC --clock-control none --import-source on -k regex:"matvec" -c 2 -o /tmp/dense_$TAG python tools/ncu_ntt.py --what dense --reps 2 > gpurun_out/ncu_dense_$TAG.log 2>&1
-ncu -i /tmp/dense_$TAG.ncu-rep --page source --csv > gpurun_out/src_dense_$TAG.csv 2>/dev/null
+ncu --set full --clock-control none --import-source on -k regex:"matvec" -s 1 -c 1 -o /tmp/dense_$TAG python tools/ncu_ntt.py --what dense --reps 2 > gpurun_out/ncu_dense_$TAG.log 2>&1
 ncu -i /tmp/dense_$TAG.ncu-rep --page raw --csv > gpurun_out/raw_dense_$TAG.csv 2>/dev/null
+ncu -i /tmp/dense_$TAG.ncu-rep --page source --csv > /tmp/src_dense_$TAG.csv 2>/dev/null
+python tools/ncu_exec_counts.py /tmp/src_dense_$TAG.csv --items 1048576 --json gpurun_out/exec_dense_$TAG.json > gpurun_out/exec_dense_$TAG.txt
+# K4: every kernel of ONE robust_interpolate_batch call (n=128, t=42, 2^17 codewords, e~U{0..42}); the call is bracketed by
+# cudaProfilerStart/Stop in tools/ncu_ntt.py
 python tools/ncu_ntt.py --what k4 --log2 17 --reps 2 > gpurun_out/ncu_plain_k4_$TAG.log 2>&1 && \
-ncu $SEC --clock-control none --import-source on -c 2000 -o /tmp/k4_$TAG python tools/ncu_ntt.py --what k4 --log2 17 --reps 2 > gpurun_out/ncu_k4_$TAG.log 2>&1
-ncu -i /tmp/k4_$TAG.ncu-rep --page source --csv > gpurun_out/src_k4_$TAG.csv 2>/dev/null
-ncu -i /tmp/k4_$TAG.ncu-rep --page raw --csv > gpurun_out/raw_k4_$TAG.csv 2>/dev/null
+ncu $SEC --clock-control none --import-source on --profile-from-start off -o /tmp/k4_$TAG python tools/ncu_ntt.py --what k4 --log2 17 --reps 2 > gpurun_out/ncu_k4_$TAG.log 2>&1
+ncu -i /tmp/k4_$TAG.ncu-rep --page raw --csv > /tmp/raw_k4_$TAG.csv 2>/dev/null
+python tools/ncu_summary.py /tmp/raw_k4_$TAG.csv gpurun_out/raw_k4_summary_$TAG.json > /dev/null 2>&1
+ncu -i /tmp/k4_$TAG.ncu-rep --page source --csv > /tmp/src_k4_$TAG.csv 2>/dev/null
+python tools/ncu_exec_counts.py /tmp/src_k4_$TAG.csv --items 131072 --aggregate --json gpurun_out/exec_k4_$TAG.json > gpurun_out/exec_k4_$TAG.txt
 cat gpurun_out/ncu_plain_k4_$TAG.log
-ls -la gpurun_out/*$TAG*; du -sh gpurun_out
+ls -la gpurun_out/*$TAG* /tmp/*.csv; du -sh gpurun_out

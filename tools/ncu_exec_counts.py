@@ -22,6 +22,11 @@ def parse(path):
             continue
         if cur is not None and hdr is not None and len(row) >= len(hdr) - 1:
             cur["rows"].append(dict(zip(hdr, row)))
+    # `ncu --page source --csv` prints every launch twice (one section per view); keep one of each identical pair
+    def sig(k):
+        return (k["name"], len(k["rows"]), sum(int(r["Instructions Executed"] or 0) for r in k["rows"]))
+    if len(kernels) % 2 == 0 and all(sig(kernels[i]) == sig(kernels[i + 1]) for i in range(0, len(kernels), 2)):
+        kernels = kernels[::2]
     return kernels
 
 def summarise(k, items=None, top=12):
@@ -54,18 +59,55 @@ def summarise(k, items=None, top=12):
         out["thread_inst_per_item"] = sum(v["thread_inst"] for v in cls.values()) / items
     return out
 
+def aggregate(res, items):
+    """per kernel name: launches and summed class counts; first entry: the grand total of the whole capture"""
+    by = collections.OrderedDict()
+    for r in res:
+        name = re.sub(r"\(.*", "", r["kernel"])
+        e = by.setdefault(name, {"kernel": name, "launches": 0, "warp_inst_total": 0, "classes": collections.defaultdict(lambda: collections.Counter()),
+                                 "fma_pipe_warp_cycles": 0, "alu_pipe_warp_cycles": 0, "stall_samples_total": 0, "stall_kinds": collections.Counter(), "top_stall_instructions": []})
+        e["launches"] += 1
+        for k in ("warp_inst_total", "fma_pipe_warp_cycles", "alu_pipe_warp_cycles", "stall_samples_total"):
+            e[k] += r[k]
+        for c, v in r["classes"].items():
+            e["classes"][c].update(v)
+        e["stall_kinds"].update(r["stall_kinds"])
+    out = []
+    tot = {"kernel": "TOTAL (all kernels of the captured call)", "launches": 0, "warp_inst_total": 0, "classes": collections.defaultdict(lambda: collections.Counter()),
+           "fma_pipe_warp_cycles": 0, "alu_pipe_warp_cycles": 0, "stall_samples_total": 0, "stall_kinds": collections.Counter(), "top_stall_instructions": []}
+    for e in by.values():
+        for k in ("launches", "warp_inst_total", "fma_pipe_warp_cycles", "alu_pipe_warp_cycles", "stall_samples_total"):
+            tot[k] += e[k]
+        for c, v in e["classes"].items():
+            tot["classes"][c].update(v)
+        tot["stall_kinds"].update(e["stall_kinds"])
+    for e in [tot] + sorted(by.values(), key=lambda e: -e["fma_pipe_warp_cycles"]):
+        e["classes"] = {c: dict(v) for c, v in e["classes"].items()}
+        e["stall_kinds"] = dict(e["stall_kinds"].most_common(8))
+        for c in ("imad_wide", "imad_other", "alu", "fp"):
+            e["classes"].setdefault(c, {"warp_inst": 0, "thread_inst": 0, "stall_samples": 0})
+        if items:
+            e["items"] = items
+            e["imad_wide_thread_inst_per_item"] = e["classes"]["imad_wide"]["thread_inst"] / items
+            e["thread_inst_per_item"] = sum(v["thread_inst"] for v in e["classes"].values()) / items
+        out.append(e)
+    return out
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("csv")
     ap.add_argument("--items", type=int)
     ap.add_argument("--json")
     ap.add_argument("--top", type=int, default=12)
+    ap.add_argument("--aggregate", action="store_true", help="sum all launches per kernel name and add a grand total (a multi-kernel call, e.g. K4)")
     a = ap.parse_args()
     res = [summarise(k, a.items, a.top) for k in parse(a.csv)]
+    if a.aggregate:
+        res = aggregate(res, a.items)
     if a.json:
         json.dump(res, open(a.json, "w"), indent=1)
     for r in res:
-        print("==", r["kernel"], "warp inst", r["warp_inst_total"], "| WIDE/item", r.get("imad_wide_thread_inst_per_item"), "| inst/item", r.get("thread_inst_per_item"))
+        print("==", r["kernel"], ("x%d" % r["launches"]) if "launches" in r else "", "warp inst", r["warp_inst_total"], "| WIDE/item", r.get("imad_wide_thread_inst_per_item"), "| inst/item", r.get("thread_inst_per_item"))
         for c, v in sorted(r["classes"].items(), key=lambda kv: -kv[1]["warp_inst"]):
             print(f"   {c:11s} warp_inst {v['warp_inst']:>12d} ({100*v['warp_inst']/max(r['warp_inst_total'],1):5.1f} %)  stall samples {v['stall_samples']:>8d} ({100*v['stall_samples']/max(r['stall_samples_total'],1):5.1f} %)")
         print("   fma pipe warp-cycles", r["fma_pipe_warp_cycles"], " alu pipe warp-cycles", r["alu_pipe_warp_cycles"], " stalls:", r["stall_kinds"])
