@@ -335,6 +335,10 @@ struct hbmpc_ctx {
     std::vector<void *> owned;                        // device allocations freed at destroy
     MapRing maps;                                     // per-call arrival-order index maps (order, col_map, chk_map, in_map)
     int lane_set = 0;                                   // async mode: lane set (0: lanes 1..3, 1: lanes 4..6) of the next host-buffer call
+    // dynamic tile queues of ntt16x_kernel: one self-resetting pair of counters per stream (kernels of one stream run in order)
+    unsigned long long *work_pool = nullptr;            // [WORK_SLOTS][4]
+    std::vector<cudaStream_t> work_streams;
+    bool static_tiles = false;                          // HBMPC_STATIC_TILES=1: static round-robin tiles (measurement knob)
     cudaStream_t main_stream() const { return lanes[0].stream; }
 };
 
@@ -454,6 +458,8 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
         if (sm) ctx->staged_min = (size_t)atoll(sm);
         const char *sg = getenv("HBMPC_STAGED_SEG");
         if (sg && atoi(sg) > 0) ctx->staged_seg = atoi(sg);
+        const char *stl = getenv("HBMPC_STATIC_TILES");
+        ctx->static_tiles = stl && stl[0] == '1';
         const char *cm = getenv("HBMPC_CHUNK_MB");
         if (cm && atoi(cm) > 0) ctx->chunk_bytes = (size_t)atoi(cm) << 20;
     }
@@ -800,8 +806,31 @@ static int launch_ntt64_cta(hbmpc_ctx *ctx, cudaStream_t st, const NttArgs &a) {
     CK(cudaGetLastError());
     return 0;
 }
+constexpr int WORK_SLOTS = 64;
+// the tile-queue words of stream `st` (nullptr when the pool is exhausted: the kernel then walks its tiles statically)
+static unsigned long long *work_slot(hbmpc_ctx *ctx, cudaStream_t st) {
+    if (ctx->static_tiles) return nullptr;
+    if (!ctx->work_pool) {
+        void *p = nullptr;
+        if (cudaMalloc(&p, WORK_SLOTS * 4 * sizeof(unsigned long long)) != cudaSuccess || cudaMemset(p, 0, WORK_SLOTS * 4 * sizeof(unsigned long long)) != cudaSuccess) {
+            cudaGetLastError();
+            if (p) cudaFree(p);
+            ctx->static_tiles = true;
+            return nullptr;
+        }
+        ctx->work_pool = (unsigned long long *)p;
+        ctx->owned.push_back(p);
+    }
+    for (size_t i = 0; i < ctx->work_streams.size(); ++i)
+        if (ctx->work_streams[i] == st) return ctx->work_pool + 4 * i;
+    if (ctx->work_streams.size() >= (size_t)WORK_SLOTS) return nullptr;
+    ctx->work_streams.push_back(st);
+    return ctx->work_pool + 4 * (ctx->work_streams.size() - 1);
+}
 template <int LOGN, int MODE>
-static int launch_ntt16x_t(hbmpc_ctx *ctx, cudaStream_t st, const NttArgs &a) {
+static int launch_ntt16x_t(hbmpc_ctx *ctx, cudaStream_t st, const NttArgs &a0) {
+    NttArgs a = a0;
+    a.work = work_slot(ctx, st);
     const size_t smem = ntt16x_smem_bytes<LOGN, MODE>();
     int &ctas = ctx->ntt16x_ctas[MODE][LOGN];
     if (ctas == 0) {

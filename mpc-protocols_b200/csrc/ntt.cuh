@@ -55,6 +55,10 @@ struct NttArgs {
     // in[b] at the q-th set bit of rootmask[b]), scaled by N^{-1}, SUBTRACTED from out[item_list[b]][k], k < mout
     int out_group32;       // MODE 2: output slot b, element pos at out[(((b>>5)*out_sb + pos)*2 + half)*32 + (b&31)] (groups of 32
                            // slots interleaved at 16-byte granularity: one thread per slot reads it coalesced)
+    // ntt16x_kernel: dynamic tile queue (nullptr: static round-robin).  work[0] = tiles handed out beyond the first one of every
+    // warp, work[1] = warps that have finished; the last warp to finish zeroes both, so the words are ready for the next launch
+    // on the same stream.
+    unsigned long long *work;
 };
 
 // SKIP_ONE: test for the trivial twiddle (only where the index is warp-uniform -- pass 0 -- so the test folds away or

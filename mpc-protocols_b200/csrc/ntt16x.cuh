@@ -197,7 +197,15 @@ __global__ void __launch_bounds__(NTT16X_WARPS * 32, ntt16x_minb<LOGN>()) ntt16x
 
     const long long ntiles = (a.B + IPW - 1) / IPW;
     unsigned bad = 0;
-    for (long long tile = (long long)blockIdx.x * NTT16X_WARPS + warp; tile < ntiles; tile += (long long)gridDim.x * NTT16X_WARPS) {
+    // Tiles are handed out dynamically: the warp scheduler favours some warps of a sub-partition over others (measured: with a
+    // static round-robin the favoured warps run out of tiles at ~60 % of the kernel's duration and the sub-partition finishes with
+    // 3-4 of its 6 warps, 4.6 on average), so every warp fetches its next tile from a global counter while it works on the
+    // current one (one 64-bit atomic per tile, its latency hidden behind the transform).
+    const long long nwarps = (long long)gridDim.x * NTT16X_WARPS;
+    long long tile = (long long)blockIdx.x * NTT16X_WARPS + warp;
+    while (tile < ntiles) {
+        unsigned long long nxt = 0;
+        if (a.work && lane == 0) nxt = atomicAdd(a.work, 1ull);
         const long long b = tile * IPW + item;
         const int active = b < a.B ? 1 : 0;
         // ---- inputs: lane j takes k = L*i + cj to row bitrev(i) of its own column (asynchronous copies, no registers); rows that
@@ -287,6 +295,13 @@ __global__ void __launch_bounds__(NTT16X_WARPS * 32, ntt16x_minb<LOGN>()) ntt16x
         bad |= rcs & 1u;
         if (MODE != 0 && (rcs & 2u) && active) a.fail[b] = 1;
         __syncwarp();   // the rows are reloaded by other lanes' columns in the next tile
+        tile = a.work ? nwarps + (long long)__shfl_sync(0xffffffffu, nxt, 0) : tile + nwarps;
+    }
+    if (a.work && lane == 0) {   // the last warp to leave resets the queue for the next launch on this stream
+        if (atomicAdd(a.work + 1, 1ull) == (unsigned long long)(nwarps - 1)) {
+            a.work[0] = 0ull;
+            a.work[1] = 0ull;
+        }
     }
     if (bad) *(volatile unsigned int *)a.err = 1u;
 }
