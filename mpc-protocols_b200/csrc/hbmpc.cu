@@ -30,6 +30,7 @@ namespace hb {
 
 // K5: element-wise share algebra on canonical values.  HBM-bound (96 B per element).
 __global__ void __launch_bounds__(256) elementwise_kernel(int op, long long count, const uint4 *a, const uint4 *b, uint4 *out, unsigned int *err) {
+    fma_ballast(count < 0, err);
     unsigned bad = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
         uint32_t x[8], y[8], z[8];
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(128) wide_chain_probe_kernel(unsigned int *sin
 // Throughput probe of the Montgomery product itself: ILP independent register-resident product chains x <- x * w per thread.
 template <int ILP>
 __global__ void __launch_bounds__(128) mont_mul_probe_kernel(unsigned int *sink, unsigned int seed, int iters) {
+    fma_ballast(iters < 0, sink);
     uint32_t x[ILP][8], w[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] = (seed + 0x9e3779b9u * (i + 1)) >> (i == 7 ? 2 : 0);

@@ -59,6 +59,7 @@ __device__ __forceinline__ void stg_stream(uint4 *p, const uint4 &v) {
 
 template <int TBT>
 __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
+    fma_ballast(a.B < 0, a.err);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = blockDim.x >> 5;
     const int C = a.C;

@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
     constexpr int PADN = N + N / 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4 *sTw = reinterpret_cast<uint4 *>(smem_raw);            // [N/2][2]
+    fma_ballast(a.B < 0, a.err);
     uint4 *sD = sTw + (N > 1 ? N : 2);                           // [IPC][2][PADN]   (NP > 1 only)
     uint4 *sIn = sD + (NP > 1 ? (size_t)IPC * 2 * PADN : 0);     // [E][2][BLOCK] per-thread input staging (prefetch)
     for (int i = threadIdx.x; i < N; i += blockDim.x) sTw[i] = a.tw[i];  // N/2 entries * 2 halves
@@ -376,6 +377,7 @@ template <int MODE>
 __global__ void __launch_bounds__(HB_NTT64_IPC * 16, 768 / (HB_NTT64_IPC * 16)) ntt64_cta_kernel(const NttArgs a) {
     constexpr int LOGN = 6, N = 64, E = 4, IPC = HB_NTT64_IPC, PADN = N + N / 8, ISTR = 2 * PADN + 1, BLOCK = IPC * 16;
     constexpr int LI = IPC == 16 ? 4 : 3;  // log2(IPC)
+    fma_ballast(a.B < 0, a.err);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4 *sTw = reinterpret_cast<uint4 *>(smem_raw);   // [N/2][2]
     uint4 *sD = sTw + N;                                 // [IPC][ISTR]

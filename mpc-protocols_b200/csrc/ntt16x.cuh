@@ -169,6 +169,7 @@ template <int LOGN, int MODE>
 __global__ void __launch_bounds__(NTT16X_WARPS * 32, ntt16x_minb<LOGN>()) ntt16x_kernel(const NttArgs a) {
     static_assert(LOGN >= 4 && LOGN <= 7, "N = 16 .. 128");
     static_assert(MODE >= 0 && MODE <= 2, "forward, inverse + degree check, weighted inverse");
+    fma_ballast(a.B < 0, a.err);
     constexpr int LOGS = ntt16x_logs<LOGN>(), S = 1 << LOGS;
     constexpr int N = 1 << LOGN, LL = LOGN - LOGS, L = 1 << LL, IPW = 32 / L;
     static_assert(L <= S && L <= 32, "every lane of an item owns at least one row in P1");

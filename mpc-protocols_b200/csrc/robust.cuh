@@ -528,6 +528,7 @@ __device__ __forceinline__ void robust_store_item(const RobustArgs &a, long long
 #define HB_ROBUST_MINB 8
 #endif
 __global__ void __launch_bounds__(128, HB_ROBUST_MINB) robust_kernel(const RobustArgs a) {
+    fma_ballast(a.rmax < 0, a.fail_any);
     size_t cnt = a.fail_scan ? (size_t)a.B : (size_t)*a.count;
     if (!a.fail_scan && a.list_max && cnt > (size_t)a.list_first + a.list_max) cnt = (size_t)a.list_first + a.list_max;
     const size_t T = (size_t)gridDim.x * blockDim.x;
@@ -684,6 +685,7 @@ struct GView {
 #define HB_BM_MINB 5
 #endif
 __global__ void __launch_bounds__(128, HB_BM_MINB) bm_segment_kernel(const StagedArgs a) {
+    fma_ballast(a.syn_ld < 0, a.rootmask);
     const unsigned int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= a.W) return;
     const GView lam(a.lamG[0], pos, a.tp), bp(a.bpG[0], pos, a.tp), syn(a.synG[0], pos, a.syn_ld), bd(a.bdisP[0], pos, 1);
@@ -838,6 +840,7 @@ __global__ void sort_scatter_kernel(const unsigned char *key, unsigned int W, un
 // Omega = S*Lambda mod z^L and the Lambda' coefficients l*Lambda_l, read by position, written per slot (item-major, zero
 // padded) for the Chien / Forney transforms together with the slot's final state and sort key
 __global__ void __launch_bounds__(128, 4) omega_kernel(const StagedArgs a) {
+    fma_ballast(a.syn_ld < 0, a.rootmask);
     const unsigned int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= a.W) return;
     const unsigned int slot = a.originP[0][pos];
@@ -905,6 +908,7 @@ __device__ __forceinline__ int staged_roots(const StagedArgs &s, unsigned int sl
 // 6a. per slot (sorted order idx): prefix products of the Forney denominators Lambda'(x_q^-1) into `om`, their product into
 // runs[idx] (1 for slots whose fast attempt has failed, so that the batched inversion is not poisoned), verdict into okf[idx]
 __global__ void __launch_bounds__(128, 4) staged_prefix_kernel(const RobustArgs a, const StagedArgs s) {
+    fma_ballast(s.syn_ld < 0, s.rootmask);
     const unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= s.W) return;
     const unsigned int slot = s.perm ? s.perm[idx] : idx;
@@ -941,6 +945,7 @@ __global__ void __launch_bounds__(128, 4) staged_prefix_kernel(const RobustArgs 
 // 6b. runs[idx] <- runs[idx]^-1, HB_INV_BATCH consecutive values per thread with one Fermat inversion (Montgomery's trick)
 #define HB_INV_BATCH 8
 __global__ void __launch_bounds__(128) staged_invert_kernel(const StagedArgs s) {
+    fma_ballast(s.syn_ld < 0, s.rootmask);
     const unsigned int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * HB_INV_BATCH;
     if (i0 >= s.W) return;
     const int cnt = (int)min((unsigned int)HB_INV_BATCH, s.W - i0);
@@ -972,6 +977,7 @@ __global__ void __launch_bounds__(128) staged_invert_kernel(const StagedArgs s) 
 
 // 6c. error values, path rule, outputs
 __global__ void __launch_bounds__(128, 4) staged_finish_kernel(const RobustArgs a, const StagedArgs s) {
+    fma_ballast(s.syn_ld < 0, s.rootmask);
     const unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= s.W) return;
     const unsigned int slot = s.perm ? s.perm[idx] : idx;
