@@ -653,12 +653,41 @@ def run_b200(args):
     ctx.set_async(True)
     np_c, np_s, np_e, np_r, np_p = (x.numpy().view(np.uint64) if x.dtype == torch.int64 else x.numpy() for x in (h_coeffs, h_shares, h_evals, h_rec, h_path))
 
-    def e2e_step():
+    def e2e_step_coeffs():
         ctx.compute_shares_batch(np_c, N_PARTIES, out=np_s)
         ctx.batch_recover(ids, np_e, N_PARTIES, DEG, T_FAULTS, out=(np_r, np_p, None))
         assert ctx.synchronize() == 0
 
     e2e_steps = max(2, min(args.steps, 5))
+    e2e_step_coeffs()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step_coeffs()
+    torch.cuda.synchronize()
+    t_e2e_c = time.perf_counter() - t0
+    assert np.array_equal(np_r, np_c) and not np_p.any()
+    t_e2e_c = max_over_ranks([t_e2e_c])[0]
+    h2d_c = Be * M * 32 + Be * N_PARTIES * 32  # coefficients and all 64 sender vectors in (asynchronous calls upload every supplied sender)
+    d2h = Be * N_PARTIES * 32 + Be * M * 32 + Be * 4
+
+    # the headline e2e step: share generation with the reference's own argument meaning -- compute_shares(secret, n, degree, rng): the
+    # polynomial is drawn inside the call (robust_interpolate.rs:68-69), here on the device from a StdRng seed, so the dealer uploads 32 B
+    # per secret instead of 704 -- followed by the same batch_recover call on the 64 sender vectors of those sharings
+    seed = bytes((17 * i + rank + 1) & 0xFF for i in range(32))
+    h_sec = torch.empty((Be, 4), dtype=torch.int64).pin_memory()
+    h_sec.copy_(coeffs[:Be, 0].cpu())
+    np_sec = h_sec.numpy().view(np.uint64)
+    ctx.set_async(False)
+    ctx.share_secrets_batch(seed, np_sec, N_PARTIES, DEG, out=np_s, coeffs_out=np_c)   # np_c: the polynomials the generator drew
+    np_e[...] = np_s.transpose(1, 0, 2)
+    ctx.set_async(True)
+
+    def e2e_step():
+        ctx.share_secrets_batch(seed, np_sec, N_PARTIES, DEG, out=np_s)
+        ctx.batch_recover(ids, np_e, N_PARTIES, DEG, T_FAULTS, out=(np_r, np_p, None))
+        assert ctx.synchronize() == 0
+
     e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -666,12 +695,12 @@ def run_b200(args):
         e2e_step()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
-    assert np.array_equal(np_r, np_c) and not np_p.any()
+    assert np.array_equal(np_r, np_c) and np.array_equal(np_r[:, 0], np_sec) and not np_p.any()
+    assert np.array_equal(np_e, np_s.transpose(1, 0, 2)), "seeded share generation is not reproducible"
     t_e2e = max_over_ranks([t_e2e])[0]
-    h2d = Be * M * 32 + Be * N_PARTIES * 32  # coefficients and all 64 sender vectors in (asynchronous calls upload every supplied sender)
-    d2h = Be * N_PARTIES * 32 + Be * M * 32 + Be * 4
+    h2d = Be * 32 + 32 + Be * N_PARTIES * 32
     ctx.set_async(True)
-    del h_coeffs, h_shares, h_evals, h_rec, h_path
+    del h_coeffs, h_shares, h_evals, h_rec, h_path, h_sec
 
     # ---- the box's pinned-copy rates, every rank AT THE SAME TIME (the roofline of the e2e leg: with N ranks they share the host bridge)
     pcie = pcie_probe(torch, dev, barrier)
@@ -791,7 +820,9 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "e2e": {"value": n_gpus * e2e_steps * 2 * Be * N_PARTIES / t_e2e, "unit": "shares/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e / e2e_steps, "host_buffers": "pinned",
-                    "mode": "asynchronous host-buffer calls (enqueue on two lane sets, hbmpc_ctx_synchronize per step)",
+                    "mode": "hbmpc_share_secrets_batch (secrets + StdRng seed in, polynomials drawn on the device, shares out) + hbmpc_batch_recover (64 sender vectors in, coefficients out); asynchronous host-buffer calls (enqueue on two lane sets, hbmpc_ctx_synchronize per step)",
+                    "coeffs_uploaded": {"value": n_gpus * e2e_steps * 2 * Be * N_PARTIES / t_e2e_c, "ms_per_step": 1e3 * t_e2e_c / e2e_steps, "h2d_bytes_per_step": h2d_c,
+                                        "what": "same step with hbmpc_compute_shares_batch on host coefficients (704 B per secret uploaded): the round-1 e2e shape"},
                     "pcie_gbs": {"h2d": h2d * e2e_steps / t_e2e / 1e9, "d2h": d2h * e2e_steps / t_e2e / 1e9},
                     "pcie_probe_slowest_rank": pcie_min, "pcie_bound_ms": 1e3 * pcie_bound_s, "pcie_frac": pcie_bound_s / (t_e2e / e2e_steps),
                     "pcie_note": "pcie_probe: pinned 256 MiB copies on every rank concurrently (H2D alone, D2H alone, both at once); pcie_bound = max(h2d, d2h bytes per step) / the bidirectional per-direction rate; pcie_frac = bound / measured step"},

@@ -18,7 +18,8 @@
  *     context moved onto that stream with hbmpc_ctx_set_stream) before the call -- the library does not synchronize with
  *     streams it does not own;
  *   - outputs are CALLER-allocated (the reference leaks Vecs to C and frees them through free_* helpers);
- *   - no hidden RNG: share generation takes the polynomial coefficients, so results are reproducible;
+ *   - no hidden RNG: share generation takes the polynomial coefficients, or a 32-byte StdRng seed from which the device draws them
+ *     exactly as the reference's generator would (hbmpc_share_secrets_batch), so results are reproducible;
  *   - there is no CPU fallback: every call fails with HBMPC_NO_DEVICE if no CUDA device is usable.
  * A context is thread-compatible: one caller at a time per context; use one context per GPU / per thread.
  */
@@ -141,6 +142,14 @@ int hbmpc_pack_share_records(hbmpc_ctx *ctx, size_t count, const uint64_t *value
  *       bytes per secret.  out / coeffs may be host or device pointers; at most ~3.8e9 draws per call. */
 int hbmpc_sample_fr_batch(hbmpc_ctx *ctx, const uint8_t *seed32, size_t count, uint64_t *out);
 int hbmpc_sample_polynomials(hbmpc_ctx *ctx, const uint8_t *seed32, size_t B, size_t d, const uint64_t *secrets, uint64_t *coeffs);
+/* K1 with the reference's own argument meaning -- RobustShare::compute_shares(secret, n, degree, None, rng)
+ * (robust_interpolate.rs:52-82; C ABI: robust_share_compute_shares, ffi/c_bindings/share/mod.rs:410-445) for B secrets: the
+ * polynomials are drawn on the device as B consecutive calls on ONE StdRng::from_seed(seed32) would draw them
+ * (== hbmpc_sample_polynomials with secrets, then hbmpc_compute_shares_batch), so a dealer moves 32 bytes per secret to the device
+ * instead of 32*(d+1).  secrets[B] -> shares[B][n]; coeffs_out[B][d+1] (may be NULL) receives the polynomials.  Host or device
+ * pointers; same errors as hbmpc_compute_shares_batch. */
+int hbmpc_share_secrets_batch(hbmpc_ctx *ctx, const uint8_t *seed32, size_t n, size_t d, size_t B, const uint64_t *secrets,
+                              uint64_t *shares, uint64_t *coeffs_out);
 
 /* Single-process multi-GPU.  The reference party is one process that issues all sessions' work before awaiting
  * (honeybadger/mod.rs:245-257,1362-1375); every call of this path is a map over independent secrets / chunks / codewords, so a group

@@ -34,7 +34,7 @@ EXPORTS = [
     "hbmpc_apply_matrix_batch", "hbmpc_batch_recover", "hbmpc_batch_recover_secrets", "hbmpc_robust_interpolate_batch",
     "hbmpc_nonrobust_recover_batch", "hbmpc_elementwise", "hbmpc_unpack_share_records", "hbmpc_pack_share_records",
     "hbmpc_measure_imad_peak", "hbmpc_measure_wide_chains", "hbmpc_measure_mont_mul",
-    "hbmpc_sample_fr_batch", "hbmpc_sample_polynomials",
+    "hbmpc_sample_fr_batch", "hbmpc_sample_polynomials", "hbmpc_share_secrets_batch",
     "hbmpc_group_create", "hbmpc_group_destroy", "hbmpc_group_size", "hbmpc_group_ctx", "hbmpc_group_shard_range",
     "hbmpc_group_compute_shares_batch", "hbmpc_group_apply_vandermonde_batch", "hbmpc_group_batch_recover",
     "hbmpc_group_batch_recover_secrets", "hbmpc_group_robust_interpolate_batch",
@@ -84,6 +84,7 @@ def load_library():
     lib.hbmpc_measure_mont_mul.argtypes = [vp, ci, ci, C.POINTER(C.c_double)]
     lib.hbmpc_sample_fr_batch.argtypes = [vp, vp, sz, vp]
     lib.hbmpc_sample_polynomials.argtypes = [vp, vp, sz, sz, vp, vp]
+    lib.hbmpc_share_secrets_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
     lib.hbmpc_group_create.argtypes = [C.POINTER(ci), sz, C.POINTER(vp)]
     lib.hbmpc_group_destroy.argtypes = [vp]
     lib.hbmpc_group_destroy.restype = None
@@ -315,6 +316,17 @@ class Context:
         if secrets is not None:
             sec = secrets if _is_torch(secrets) else np.ascontiguousarray(secrets, dtype=np.uint64)
         self._check(self.lib.hbmpc_sample_polynomials(self.h, sd.ctypes.data, B, d, _ptr(sec) if sec is not None else None, _ptr(out)))
+        return out
+
+    def share_secrets_batch(self, seed: bytes, secrets, n: int, d: int, out=None, coeffs_out=None):
+        """secrets[B][4] -> shares[B][n][4], polynomials drawn on the device from StdRng::from_seed(seed)
+        (RobustShare::compute_shares(secret, n, degree, None, rng), robust_interpolate.rs:52-82, for B secrets on one generator)"""
+        assert len(seed) == 32
+        sd = np.frombuffer(seed, dtype=np.uint8).copy()
+        s = _Buf(secrets)
+        B = s.shape[0]
+        out = s.like((B, n, 4)) if out is None else out
+        self._check(self.lib.hbmpc_share_secrets_batch(self.h, sd.ctypes.data, n, d, B, s.ptr, _ptr(out), _ptr(coeffs_out) if coeffs_out is not None else None))
         return out
 
     def measure_mont_mul(self, ilp: int, warps_per_smsp: int) -> float:

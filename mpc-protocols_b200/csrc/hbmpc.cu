@@ -235,7 +235,7 @@ struct DevBuf {
 // concurrently: a download-bound call (share generation) and an upload-bound one (recovery) then use both PCIe directions at once.
 struct Lane {
     cudaStream_t stream = nullptr;
-    DevBuf scratch[12];
+    DevBuf scratch[14];
 };
 static const int NLANES = 7, LANES_PER_SET = 3;
 
@@ -2189,6 +2189,33 @@ extern "C" int hbmpc_sample_polynomials(hbmpc_ctx *ctx, const uint8_t *seed32, s
     if (d > 255) return HBMPC_INVALID_INPUT;
     if (secrets) return sample_stream(ctx, seed32, (unsigned long long)B * (d + 1), 2, (int)d, B * (d + 1), coeffs, secrets, B);
     return sample_stream(ctx, seed32, (unsigned long long)B * (d + 2), 1, (int)d, B * (d + 1), coeffs, nullptr, B);
+}
+
+// K1 with the reference's own argument meaning: RobustShare::compute_shares(secret, n, degree, None, rng) (robust_interpolate.rs:52-82)
+// for B secrets whose polynomials are drawn on the device from StdRng::from_seed(seed32) exactly as B consecutive calls on one
+// generator would draw them (d+1 draws per sharing, the first overwritten by the secret).  A dealer uploads 32 bytes per secret.
+extern "C" int hbmpc_share_secrets_batch(hbmpc_ctx *ctx, const uint8_t *seed32, size_t n, size_t d, size_t B, const uint64_t *secrets,
+                                         uint64_t *shares, uint64_t *coeffs_out) {
+    if (!ctx || !seed32) return HBMPC_INVALID_INPUT;
+    if (n <= d) return HBMPC_INVALID_INPUT;                 // robust_interpolate.rs:59-64
+    if (!domain_size(n)) return HBMPC_NO_SUITABLE_DOMAIN;   // :65-66
+    if (B == 0) return HBMPC_SUCCESS;
+    if (!secrets || !shares || d > 255) return HBMPC_INVALID_INPUT;
+    cudaSetDevice(ctx->device);
+    if (ctx->async)   // the coefficient scratch of an earlier call may still be read by its pipelined chunks
+        for (int i = 1; i < NLANES; ++i) CK(cudaStreamSynchronize(ctx->lanes[i].stream));
+    void *dc = nullptr;
+    const bool own = !(coeffs_out && is_device_ptr(coeffs_out));
+    int rc;
+    if (own) {
+        if ((rc = scratch_get(ctx, ctx->lanes[0], 12, B * (d + 1) * 32, &dc))) return rc;
+    } else dc = coeffs_out;
+    if ((rc = sample_stream(ctx, seed32, (unsigned long long)B * (d + 1), 2, (int)d, B * (d + 1), (uint64_t *)dc, secrets, B))) return rc;
+    if (own && coeffs_out) {
+        CK(cudaMemcpyAsync(coeffs_out, dc, B * (d + 1) * 32, cudaMemcpyDeviceToHost, ctx->main_stream()));
+        CK(cudaStreamSynchronize(ctx->main_stream()));
+    }
+    return apply_domain(ctx, n, d + 1, B, (const uint64_t *)dc, shares, 0);
 }
 
 // ------------------------------------------------------------------------------------------------ single-process multi-GPU groups

@@ -82,3 +82,28 @@ def test_device_sampler_large_and_device_resident(hb, ctx, orc):
     shares = ctx.compute_shares_batch(coeffs, n)          # non-canonical values would raise InvalidInput
     rc, want = orc.compute_shares(tail, n)
     assert rc == 0 and np.array_equal(shares[-2:].cpu().numpy().view(np.uint64), want)
+
+
+@pytest.mark.gpu
+def test_share_secrets_batch_is_compute_shares_on_a_seeded_generator(hb, ctx, orc):
+    """hbmpc_share_secrets_batch(seed, secrets) == the oracle's compute_shares on the polynomials B consecutive
+    RobustShare::compute_shares(secret, n, d, None, rng) calls would draw from StdRng::from_seed(seed) (robust_interpolate.rs:68-69):
+    host buffers (pipelined chunks), device buffers, with and without the polynomials returned."""
+    import torch
+
+    seed = bytes((11 * i + 5) & 0xFF for i in range(32))
+    for n, d, B in ((4, 1, 3), (16, 5, 700), (64, 21, 5000), (64, 42, 300), (128, 42, 200)):
+        sec = [(123456789 * (b + 1)) % hb.R_MOD for b in range(B)]
+        polys = cf.sample_polynomials(seed, B, d, secrets=sec)
+        rc, want = orc.compute_shares(hb.to_limbs(polys), n)
+        assert rc == 0
+        cout = np.zeros((B, d + 1, 4), dtype=np.uint64)
+        got = ctx.share_secrets_batch(seed, hb.to_limbs(sec), n, d, coeffs_out=cout)
+        assert np.array_equal(got, want) and hb.from_limbs(cout) == polys
+        dsec = torch.from_numpy(hb.to_limbs(sec).view(np.int64)).cuda()
+        dgot = ctx.share_secrets_batch(seed, dsec, n, d)
+        assert ctx.synchronize() == 0
+        assert np.array_equal(dgot.cpu().numpy().view(np.uint64), want)
+    with pytest.raises(hb.HbmpcError) as e:
+        ctx.share_secrets_batch(seed, hb.to_limbs([1, 2]), 4, 4)
+    assert e.value.code == hb.INVALID_INPUT
