@@ -773,8 +773,11 @@ static int launch_matvec(hbmpc_ctx *ctx, Lane &ln, MatvecArgs a, int flag_words)
     return 0;
 }
 
+static unsigned long long *work_slot(hbmpc_ctx *ctx, cudaStream_t st);
 template <int LOGN, int MODE>
-static int launch_ntt_t(hbmpc_ctx *ctx, cudaStream_t st, const NttArgs &a) {
+static int launch_ntt_t(hbmpc_ctx *ctx, cudaStream_t st, const NttArgs &a0) {
+    NttArgs a = a0;
+    a.work = work_slot(ctx, st);
     const size_t smem = ntt_smem_bytes<LOGN>();
     int &ctas = ctx->ntt_ctas[MODE][LOGN];
     if (ctas == 0) {

@@ -221,7 +221,13 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
 
     const int tid_i = threadIdx.x % TPI, item_l = threadIdx.x / TPI;
     uint4 *myD = sD + (size_t)item_l * 2 * PADN;
-    const long long ntiles = (a.B + IPC - 1) / IPC;
+    // A tile is the IPW items of ONE warp (the warps of a CTA only share the twiddle table): warps fetch their tiles from a global
+    // queue (a.work, see ntt16x.cuh: the scheduler's priorities make statically assigned warps finish at very different times), one
+    // tile ahead of the prefetch, i.e. two ahead of the transform; a.work == nullptr: static round-robin.
+    constexpr int IPW = 32 / TPI, WPC = HB_NTT_BLOCK / 32;
+    const int lane = threadIdx.x & 31, item_w = lane / TPI;
+    const long long ntiles = (a.B + IPW - 1) / IPW;
+    const long long nwarps = (long long)gridDim.x * WPC;
     unsigned bad = 0;
 
     // Which record feeds each of this thread's E positions is the same for every tile: position pos holds the input with
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
     // overwrite those slots cannot be issued before the reads have completed
     const unsigned int never = (unsigned int)a.n + 0x7fff0000u;
     auto prefetch = [&](long long t, unsigned int gate) {
-        const long long bb = t * IPC + item_l;
+        const long long bb = t * IPW + item_w;
         if (t < ntiles && bb < a.B && gate != never) {
             const long long src = (MODE == 2 && a.item_list) ? (long long)a.item_list[bb] : bb;
 #pragma unroll
@@ -252,10 +258,19 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
         }
         cp_async_commit();
     };
-    prefetch(blockIdx.x, 0u);
+    long long tile = (long long)blockIdx.x * WPC + (threadIdx.x >> 5);
+    long long next = tile + nwarps;
+    if (a.work) {
+        unsigned long long q = 0;
+        if (lane == 0) q = atomicAdd(a.work, 1ull);
+        next = nwarps + (long long)__shfl_sync(0xffffffffu, q, 0);
+    }
+    prefetch(tile, 0u);
 
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long b = tile * IPC + item_l;
+    while (tile < ntiles) {
+        unsigned long long q2 = 0;
+        if (a.work && lane == 0) q2 = atomicAdd(a.work, 1ull);   // the tile after `next`; consumed at the end of this iteration
+        const long long b = tile * IPW + item_w;
         const bool active = b < a.B;
         uint32_t x[E][8];
         // ---- pass 0: inputs from the prefetch staging (thread-private slots: no barrier), stages with half = 1, 2, 4
@@ -293,7 +308,7 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
         }
         if ((MODE == 1 || MODE == 2) && a.path && active && tid_i == 0) a.path[b] = 0;
         // the staged values are in registers (and were examined by geq_mod): the slots can take the next tile's inputs
-        prefetch(tile + gridDim.x, bad | dep);
+        prefetch(next, bad | dep);
         ntt_stages<G, E, true>(x, sTw, 0, 1, LOGN - 1);
         if constexpr (NP == 1) {
 #pragma unroll
@@ -350,6 +365,14 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
             __syncwarp();  // the tile's buffer is reused by the next tile's pass 0 writes
         }
         }  // NP > 1
+        tile = next;
+        next = a.work ? nwarps + (long long)__shfl_sync(0xffffffffu, q2, 0) : next + nwarps;
+    }
+    if (a.work && lane == 0) {   // the last warp to leave resets the queue for the next launch on this stream
+        if (atomicAdd(a.work + 1, 1ull) == (unsigned long long)(nwarps - 1)) {
+            a.work[0] = 0ull;
+            a.work[1] = 0ull;
+        }
     }
     if (bad) *(volatile unsigned int *)a.err = 1u;  // mapped host memory: plain store, every writer stores 1
 }
