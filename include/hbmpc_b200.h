@@ -129,6 +129,18 @@ int hbmpc_elementwise(hbmpc_ctx *ctx, int op, size_t count, const uint64_t *a, c
 int hbmpc_unpack_share_records(hbmpc_ctx *ctx, size_t count, const void *records, uint64_t *values, uint64_t *ids, uint64_t *degrees);
 int hbmpc_pack_share_records(hbmpc_ctx *ctx, size_t count, const uint64_t *values, size_t per_id, size_t degree, void *records);
 
+/* N1 (message payloads).  The per-sender vectors of batch reconstruction arrive, and the per-recipient vectors leave, as SEPARATE
+ * message payloads (`Vec<F>::serialize_compressed`: u64 length + 32-byte LE canonical values; batch_recon.rs:174-175, 339, 419;
+ * common/utils.rs:3-21).  These variants take one HOST pointer per sender / recipient -- `payload + 8`, 8-byte aligned -- and move the
+ * bytes straight between the message buffers and the device: no host-side gather into a contiguous [S][B] array, no scatter out of
+ * [n][B], (de)serialisation and transposition are the copy pattern of the call.  Same results, errors and chunked pipeline as
+ * hbmpc_batch_recover / hbmpc_batch_recover_secrets / hbmpc_apply_vandermonde_batch(recipient_major = 1). */
+int hbmpc_batch_recover_msgs(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, const size_t *sender_ids, size_t B,
+                             const uint64_t *const *sender_evals, uint64_t *coeffs, int32_t *path, uint64_t *flags);
+int hbmpc_batch_recover_secrets_msgs(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, const size_t *sender_ids, size_t B,
+                                     const uint64_t *const *sender_evals, uint64_t *secrets, int32_t *path);
+int hbmpc_apply_vandermonde_msgs(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *const *recipient_out);
+
 /* N4.  The randomness of a sharing as the reference draws it, on the device.  The reference samples the polynomial inside
  * compute_shares (robust_interpolate.rs:68-69: DensePolynomial::rand(d, rng) with coefficient 0 overwritten by the secret; callers draw
  * the secret with F::rand first: share_gen.rs:250, double_share_generation.rs:167) from rand 0.8 `StdRng` (ChaCha12, 64-bit block

@@ -156,7 +156,7 @@ class BatchReconNode {
         if (shares.empty() || shares.size() % width != 0)
             throw BatchReconError(BatchReconError::InvalidInput, "batched shares must be a non-empty multiple of degree + 1");
         const size_t chunks = shares.size() / width;
-        std::vector<U256> in(shares.size()), out(n * chunks);
+        std::vector<U256> in(shares.size());
         for (size_t c = 0; c < chunks; ++c)
             for (size_t k = 0; k < width; ++k) {
                 const Share &s = shares[c * width + k], &s0 = shares[c * width];
@@ -164,13 +164,19 @@ class BatchReconNode {
                 if (s.id != s0.id) throw BatchReconError(BatchReconError::ShareErr, "IdMismatch", HBMPC_ID_MISMATCH);
                 in[c * width + k] = s.share;
             }
-        const int rc = hbmpc_apply_vandermonde_batch(ctx_.get(), n, width, chunks, in[0].data(), out[0].data(), 1);
-        if (rc != HBMPC_SUCCESS) throw BatchReconError(BatchReconError::ShareErr, "apply_vandermonde", rc);
+        // the device writes recipient j's vector straight into the payload of the message for j (ark-serialize Vec<F>: u64 length, then
+        // the values): the transposition of batch_recon.rs:158-165 and the serialisation of :174-175 are the copy pattern of the call
+        std::vector<BatchReconMsg> msgs(n, BatchReconMsg{session_id, id, BatchReconMsgType::EvalBatch, {}});
+        std::vector<uint64_t *> out_ptrs(n);
+        const uint64_t len = chunks;
         for (size_t j = 0; j < n; ++j) {
-            std::vector<U256> values(out.begin() + j * chunks, out.begin() + (j + 1) * chunks);
-            BatchReconMsg m{session_id, id, BatchReconMsgType::EvalBatch, detail::ser_vec(values)};
-            net.send(j, m.encode());
+            msgs[j].payload.resize(8 + 32 * chunks);
+            std::memcpy(msgs[j].payload.data(), &len, 8);
+            out_ptrs[j] = reinterpret_cast<uint64_t *>(msgs[j].payload.data() + 8);
         }
+        const int rc = hbmpc_apply_vandermonde_msgs(ctx_.get(), n, width, chunks, in[0].data(), out_ptrs.data());
+        if (rc != HBMPC_SUCCESS) throw BatchReconError(BatchReconError::ShareErr, "apply_vandermonde", rc);
+        for (size_t j = 0; j < n; ++j) net.send(j, msgs[j].encode());
     }
 
     // batch_recon.rs:191-481
@@ -294,16 +300,16 @@ class BatchReconNode {
     std::vector<U256> decode(const std::vector<std::pair<size_t, std::vector<U256>>> &received, bool secrets_only) {
         const size_t S = received.size(), B = received[0].second.size();
         std::vector<size_t> ids(S);
-        std::vector<U256> evals(S * B);
+        std::vector<const uint64_t *> ptrs(S);   // one array per sender, where its message left it: no gather into [S][B]
         for (size_t i = 0; i < S; ++i) {
             if (received[i].second.size() != B) throw BatchReconError(BatchReconError::InterpolateError, "Inconsistent batch widths", HBMPC_INVALID_INPUT);
             ids[i] = received[i].first;
-            std::memcpy(evals[i * B].data(), received[i].second[0].data(), 32 * B);
+            ptrs[i] = received[i].second[0].data();
         }
         std::vector<int32_t> path(B);
         std::vector<U256> out(secrets_only ? B : B * (degree + 1));
-        const int rc = secrets_only ? hbmpc_batch_recover_secrets(ctx_.get(), n, degree, t, S, ids.data(), B, evals[0].data(), out[0].data(), path.data())
-                                    : hbmpc_batch_recover(ctx_.get(), n, degree, t, S, ids.data(), B, evals[0].data(), out[0].data(), path.data(), nullptr);
+        const int rc = secrets_only ? hbmpc_batch_recover_secrets_msgs(ctx_.get(), n, degree, t, S, ids.data(), B, ptrs.data(), out[0].data(), path.data())
+                                    : hbmpc_batch_recover_msgs(ctx_.get(), n, degree, t, S, ids.data(), B, ptrs.data(), out[0].data(), path.data(), nullptr);
         if (rc != HBMPC_SUCCESS) throw BatchReconError(BatchReconError::InterpolateError, "batch_recover_secret", rc);
         return out;
     }

@@ -35,6 +35,7 @@ EXPORTS = [
     "hbmpc_nonrobust_recover_batch", "hbmpc_elementwise", "hbmpc_unpack_share_records", "hbmpc_pack_share_records",
     "hbmpc_measure_imad_peak", "hbmpc_measure_wide_chains", "hbmpc_measure_mont_mul",
     "hbmpc_sample_fr_batch", "hbmpc_sample_polynomials", "hbmpc_share_secrets_batch",
+    "hbmpc_batch_recover_msgs", "hbmpc_batch_recover_secrets_msgs", "hbmpc_apply_vandermonde_msgs",
     "hbmpc_group_create", "hbmpc_group_destroy", "hbmpc_group_size", "hbmpc_group_ctx", "hbmpc_group_shard_range",
     "hbmpc_group_compute_shares_batch", "hbmpc_group_apply_vandermonde_batch", "hbmpc_group_batch_recover",
     "hbmpc_group_batch_recover_secrets", "hbmpc_group_robust_interpolate_batch",
@@ -85,6 +86,9 @@ def load_library():
     lib.hbmpc_sample_fr_batch.argtypes = [vp, vp, sz, vp]
     lib.hbmpc_sample_polynomials.argtypes = [vp, vp, sz, sz, vp, vp]
     lib.hbmpc_share_secrets_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
+    lib.hbmpc_batch_recover_msgs.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp, vp]
+    lib.hbmpc_batch_recover_secrets_msgs.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp]
+    lib.hbmpc_apply_vandermonde_msgs.argtypes = [vp, sz, sz, sz, vp, vp]
     lib.hbmpc_group_create.argtypes = [C.POINTER(ci), sz, C.POINTER(vp)]
     lib.hbmpc_group_destroy.argtypes = [vp]
     lib.hbmpc_group_destroy.restype = None
@@ -255,6 +259,38 @@ class Context:
                                                      _ptr(path), _ptr(flags) if flags is not None else None)
         self._check(rc, ok=(0, DECODING_ERROR))
         return rc, coeffs, secrets, path, flags
+
+    # -- N1: one host array per sender / recipient (message payloads)
+    @staticmethod
+    def _ptr_array(arrays):
+        arr = (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+        return arr
+
+    def batch_recover_msgs(self, sender_ids, sender_evals, n: int, d: int, t: int, want_flags: bool = False, secrets_only: bool = False):
+        """sender_evals: list of S host arrays (uint64 views of B x 32-byte values, e.g. payload[8:]) in arrival order"""
+        S, B = len(sender_evals), sender_evals[0].size // 4
+        ids = np.ascontiguousarray(sender_ids, dtype=np.uint64)
+        pa = self._ptr_array(sender_evals)
+        path = np.zeros(B, dtype=np.int32)
+        if secrets_only:
+            secrets = np.zeros((B, 4), dtype=np.uint64)
+            rc = self.lib.hbmpc_batch_recover_secrets_msgs(self.h, n, d, t, S, ids.ctypes.data, B, pa, secrets.ctypes.data, path.ctypes.data)
+            self._check(rc, ok=(0, DECODING_ERROR))
+            return rc, secrets, path
+        coeffs = np.zeros((B, d + 1, 4), dtype=np.uint64)
+        flags = np.zeros((B, (S + 63) // 64), dtype=np.uint64) if want_flags else None
+        rc = self.lib.hbmpc_batch_recover_msgs(self.h, n, d, t, S, ids.ctypes.data, B, pa, coeffs.ctypes.data, path.ctypes.data,
+                                               flags.ctypes.data if flags is not None else None)
+        self._check(rc, ok=(0, DECODING_ERROR))
+        return rc, coeffs, path, flags
+
+    def apply_vandermonde_msgs(self, inp, n: int, recipient_out):
+        """inp[B][cols][4] -> recipient_out[j] (list of n host arrays of B x 4 uint64) = the vector for recipient j"""
+        x = _Buf(inp)
+        B, cols = x.shape[0], x.shape[1]
+        pa = self._ptr_array(recipient_out)
+        self._check(self.lib.hbmpc_apply_vandermonde_msgs(self.h, n, cols, B, x.ptr, pa))
+        return recipient_out
 
     # -- a10
     def nonrobust_recover_batch(self, ids, shares, n: int, deg: int, sender_major: bool = False, out=None):

@@ -611,6 +611,8 @@ struct BatchBuf {
     size_t ld = 0;                           // record-major buffers: distance between records in items (B, or more when the call
                                              // works on a column range of a wider array: group calls shard the batch axis)
     const std::vector<int> *rows = nullptr;  // record-major host buffers: copy only these records (ascending); others stay stale
+    void *const *ptrs = nullptr;             // record-major host buffers given as J separate arrays of B items (one message payload per
+                                             // sender / recipient): record j lives at ptrs[j]; `user` is unused
 };
 static BatchBuf make_buf(const void *p, size_t B, long long J, bool record_major, size_t esz = 32, size_t ld = 0) {
     BatchBuf b;
@@ -623,6 +625,26 @@ static BatchBuf make_buf(const void *p, size_t B, long long J, bool record_major
     b.B = B;
     b.ld = ld ? ld : B;
     return b;
+}
+// J host arrays of B items each (nullptr entries or device pointers are rejected by the callers)
+static BatchBuf make_buf_ptrs(void *const *ptrs, size_t B, long long J, size_t esz = 32) {
+    BatchBuf b;
+    b.user = nullptr;
+    b.present = ptrs != nullptr;
+    b.host = true;
+    b.J = J;
+    b.record_major = true;
+    b.esz = esz;
+    b.B = B;
+    b.ld = B;
+    b.ptrs = ptrs;
+    return b;
+}
+static bool host_ptr_array_ok(const void *const *ptrs, size_t J) {
+    if (!ptrs) return false;
+    for (size_t j = 0; j < J; ++j)
+        if (!ptrs[j] || is_device_ptr(ptrs[j])) return false;
+    return true;
 }
 // device view of the chunk [b0, b0+Bc)
 struct ChunkView {
@@ -639,7 +661,19 @@ static int chunk_prepare(hbmpc_ctx *ctx, Lane &ln, int slot, const BatchBuf &bb,
     }
     int rc = scratch_get(ctx, ln, slot, Bc * (size_t)bb.J * bb.esz, &v.dev);
     if (rc) return rc;
-    if (bb.record_major) {
+    if (bb.record_major && bb.ptrs) {   // one message payload per record: copied straight from where the messages lie
+        v.sb = 1;
+        v.sj = (long long)Bc;
+        if (copy_in) {
+            if (!bb.rows) {
+                for (long long j = 0; j < bb.J; ++j)
+                    CK(cudaMemcpyAsync((char *)v.dev + (size_t)j * Bc * bb.esz, (const char *)bb.ptrs[j] + b0 * bb.esz, Bc * bb.esz, cudaMemcpyHostToDevice, ln.stream));
+            } else {
+                for (int j : *bb.rows)
+                    CK(cudaMemcpyAsync((char *)v.dev + (size_t)j * Bc * bb.esz, (const char *)bb.ptrs[j] + b0 * bb.esz, Bc * bb.esz, cudaMemcpyHostToDevice, ln.stream));
+            }
+        }
+    } else if (bb.record_major) {
         v.sb = 1;
         v.sj = (long long)Bc;
         if (copy_in && !bb.rows)
@@ -664,7 +698,10 @@ static int chunk_prepare(hbmpc_ctx *ctx, Lane &ln, int slot, const BatchBuf &bb,
 }
 static int chunk_commit(hbmpc_ctx *ctx, Lane &ln, const BatchBuf &bb, size_t b0, size_t Bc, const ChunkView &v) {
     if (!bb.present || !bb.host) return 0;
-    if (bb.record_major)
+    if (bb.record_major && bb.ptrs) {
+        for (long long j = 0; j < bb.J; ++j)
+            CK(cudaMemcpyAsync((char *)bb.ptrs[j] + b0 * bb.esz, (const char *)v.dev + (size_t)j * Bc * bb.esz, Bc * bb.esz, cudaMemcpyDeviceToHost, ln.stream));
+    } else if (bb.record_major)
         CK(cudaMemcpy2DAsync((char *)bb.user + b0 * bb.esz, bb.ld * bb.esz, v.dev, Bc * bb.esz, Bc * bb.esz, (size_t)bb.J, cudaMemcpyDeviceToHost, ln.stream));
     else
         CK(cudaMemcpyAsync((char *)bb.user + b0 * (size_t)bb.J * bb.esz, v.dev, Bc * (size_t)bb.J * bb.esz, cudaMemcpyDeviceToHost, ln.stream));
@@ -945,8 +982,9 @@ static int get_vandermonde(hbmpc_ctx *ctx, size_t n, size_t cols, uint4 **out) {
 // ------------------------------------------------------------------------------------------------ K1 / K2
 // out[b][r] = sum_c M[r][c] in[b][c]: M == nullptr selects the domain transform (NTT) with `n` outputs
 static int apply_map(hbmpc_ctx *ctx, const uint4 *M, const uint4 *tw, int logn, size_t rows, size_t cols, size_t B, const uint64_t *in,
-                     uint64_t *out, int recipient_major, size_t ld_out = 0) {
-    BatchBuf bi = make_buf(in, B, (long long)cols, false), bo = make_buf(out, B, (long long)rows, recipient_major != 0, 32, ld_out);
+                     uint64_t *out, int recipient_major, size_t ld_out = 0, void *const *out_ptrs = nullptr) {
+    BatchBuf bi = make_buf(in, B, (long long)cols, false);
+    BatchBuf bo = out_ptrs ? make_buf_ptrs(out_ptrs, B, (long long)rows) : make_buf(out, B, (long long)rows, recipient_major != 0, 32, ld_out);
     auto body = [&](Lane &ln, size_t b0, size_t Bc) -> int {
         ChunkView vi, vo;
         int rc;
@@ -981,7 +1019,8 @@ static int apply_map(hbmpc_ctx *ctx, const uint4 *M, const uint4 *tw, int logn, 
     return run_batched(ctx, B, bi.host || bo.host, std::max(rows, cols) * 32, body);
 }
 
-static int apply_domain(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out, int recipient_major, size_t ld_out = 0) {
+static int apply_domain(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out, int recipient_major, size_t ld_out = 0,
+                        void *const *out_ptrs = nullptr) {
     const int N = domain_size(n);
     int logn = 0;
     while ((1 << logn) < N) ++logn;
@@ -989,12 +1028,12 @@ static int apply_domain(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const u
         uint4 *V = nullptr;
         int rc = get_vandermonde(ctx, n, cols, &V);
         if (rc) return rc;
-        return apply_map(ctx, V, nullptr, 0, n, cols, B, in, out, recipient_major, ld_out);
+        return apply_map(ctx, V, nullptr, 0, n, cols, B, in, out, recipient_major, ld_out, out_ptrs);
     }
     uint4 *tw = nullptr;
     int rc = get_twiddles(ctx, N, &tw);
     if (rc) return rc;
-    return apply_map(ctx, nullptr, tw, logn, n, cols, B, in, out, recipient_major, ld_out);
+    return apply_map(ctx, nullptr, tw, logn, n, cols, B, in, out, recipient_major, ld_out, out_ptrs);
 }
 
 extern "C" int hbmpc_compute_shares_batch(hbmpc_ctx *ctx, size_t n, size_t d, size_t B, const uint64_t *coeffs, uint64_t *shares) {
@@ -1430,7 +1469,7 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
 // shared implementation: element (item b, arrival j) of `in` is sender-major [S][B] (K3) or codeword-major [B][S] (K4)
 static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, const size_t *ids, size_t B, const uint64_t *in,
                         bool sender_major, uint64_t *coeffs, bool secrets_only, uint64_t *secrets, int32_t *path, uint64_t *flags,
-                        size_t ld_in = 0) {
+                        size_t ld_in = 0, void *const *in_ptrs = nullptr) {
     // validation order of robust_interpolate.rs:290-341 / :100-142
     if (n < 3 * t + 1) return HBMPC_INVALID_INPUT;
     if (S == 0 || !ids) return HBMPC_INVALID_INPUT;
@@ -1448,7 +1487,8 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
     const size_t needed = d + t + 1, m = d + 1;
     if (S < needed) return HBMPC_INVALID_INPUT;
     if (!domain_size(n)) return HBMPC_NO_SUITABLE_DOMAIN;
-    if (!in || !path || (!coeffs && !secrets_only) || (secrets_only && !secrets)) return HBMPC_INVALID_INPUT;
+    if ((!in && !in_ptrs) || !path || (!coeffs && !secrets_only) || (secrets_only && !secrets)) return HBMPC_INVALID_INPUT;
+    if (in_ptrs && (!sender_major || !host_ptr_array_ok((const void *const *)in_ptrs, S))) return HBMPC_INVALID_INPUT;
     cudaSetDevice(ctx->device);
 
     const bool want_flags = flags != nullptr;
@@ -1497,7 +1537,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
     const int fw = want_flags ? (int)((S + 63) / 64) : 0;
     const bool want_secrets = !secrets_only && secrets != nullptr;
 
-    BatchBuf bi = make_buf(in, B, (long long)S, sender_major, 32, sender_major ? ld_in : 0);
+    BatchBuf bi = in_ptrs ? make_buf_ptrs(in_ptrs, B, (long long)S) : make_buf(in, B, (long long)S, sender_major, 32, sender_major ? ld_in : 0);
     BatchBuf bc = make_buf(secrets_only ? secrets : coeffs, B, T.mout, false);
     BatchBuf bp = make_buf(path, B, 1, false, 4);
     BatchBuf bf = make_buf(flags, B, fw > 0 ? fw : 1, false, 8);
@@ -1906,6 +1946,29 @@ extern "C" int hbmpc_robust_interpolate_batch(hbmpc_ctx *ctx, size_t n, size_t d
                                               const uint64_t *shares, uint64_t *coeffs, uint64_t *secrets, int32_t *path, uint64_t *flags) {
     if (!ctx) return HBMPC_INVALID_INPUT;
     return recover_impl(ctx, n, d, t, S, ids, B, shares, false, coeffs, false, secrets, path, flags);
+}
+
+// N1: the per-sender / per-recipient vectors as they lie in the message payloads (one host array per sender or recipient, e.g.
+// payload + 8 of an ark-serialize Vec<F>): no host-side gather into one contiguous [S][B] array, no scatter out of [n][B]
+// (batch_recon.rs:174-175, 339, 419; common/utils.rs:3-21).
+extern "C" int hbmpc_batch_recover_msgs(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, const size_t *sender_ids, size_t B,
+                                        const uint64_t *const *sender_evals, uint64_t *coeffs, int32_t *path, uint64_t *flags) {
+    if (!ctx || !sender_evals) return HBMPC_INVALID_INPUT;
+    return recover_impl(ctx, n, d, t, S, sender_ids, B, nullptr, true, coeffs, false, nullptr, path, flags, 0, (void *const *)sender_evals);
+}
+extern "C" int hbmpc_batch_recover_secrets_msgs(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, const size_t *sender_ids, size_t B,
+                                                const uint64_t *const *sender_evals, uint64_t *secrets, int32_t *path) {
+    if (!ctx || !sender_evals) return HBMPC_INVALID_INPUT;
+    return recover_impl(ctx, n, d, t, S, sender_ids, B, nullptr, true, nullptr, true, secrets, path, nullptr, 0, (void *const *)sender_evals);
+}
+extern "C" int hbmpc_apply_vandermonde_msgs(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *const *recipient_out) {
+    if (!ctx) return HBMPC_INVALID_INPUT;
+    if (cols == 0 || cols > 256) return HBMPC_INVALID_INPUT;
+    if (!domain_size(n)) return HBMPC_NO_SUITABLE_DOMAIN;
+    if (B == 0) return HBMPC_SUCCESS;
+    if (!in || !host_ptr_array_ok((const void *const *)recipient_out, n)) return HBMPC_INVALID_INPUT;
+    cudaSetDevice(ctx->device);
+    return apply_domain(ctx, n, cols, B, in, nullptr, 1, 0, (void *const *)recipient_out);
 }
 
 // ------------------------------------------------------------------------------------------------ a10: NonRobustShare::recover_secret, batched
