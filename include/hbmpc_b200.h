@@ -163,6 +163,25 @@ int hbmpc_sample_polynomials(hbmpc_ctx *ctx, const uint8_t *seed32, size_t B, si
 int hbmpc_share_secrets_batch(hbmpc_ctx *ctx, const uint8_t *seed32, size_t n, size_t d, size_t B, const uint64_t *secrets,
                               uint64_t *shares, uint64_t *coeffs_out);
 
+/* N4 (tail).  The same path over the reference's second field, GoldilocksField = Fp64, p = 2^64 - 2^32 + 1, generator 7
+ * (common/math/goldilocks.rs:4-13; the RandBit / PRandInt pipeline instantiates the generic sharing code with it).  An element is its
+ * canonical value in ONE uint64_t (< p, else HBMPC_INVALID_INPUT); shapes, evaluation domain (GeneralEvaluationDomain::new(n):
+ * w_N = 7^((p-1)/N)), id conventions, validation and error codes as in the Fr entry points of the same name.  hbmpc_gl_batch_recover is
+ * batch_recover_secret's optimistic path (interpolate the lowest d+1 ids, check the next t: robust_interpolate.rs:343-428): a chunk
+ * that fails the check gets path[b] = -HBMPC_DECODING_ERROR and zeroed outputs, and the call returns HBMPC_DECODING_ERROR -- the
+ * error-correcting decoder is not instantiated for this field (hand those chunks to the reference's CPU decoder).  coeffs or secrets
+ * (not both) may be NULL.  Matrices are limited to rows*cols <= 25600 (n = 64 .. 128 shapes fit).  8-byte elements make these calls
+ * HBM / PCIe bound. */
+int hbmpc_gl_compute_shares_batch(hbmpc_ctx *ctx, size_t n, size_t d, size_t B, const uint64_t *coeffs, uint64_t *shares);
+int hbmpc_gl_apply_vandermonde_batch(hbmpc_ctx *ctx, size_t n, size_t cols, size_t B, const uint64_t *in, uint64_t *out, int recipient_major);
+int hbmpc_gl_batch_recover(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, const size_t *sender_ids, size_t B, const uint64_t *evals,
+                           uint64_t *coeffs, uint64_t *secrets, int32_t *path);
+int hbmpc_gl_nonrobust_recover_batch(hbmpc_ctx *ctx, size_t n, size_t deg, size_t S, const size_t *ids, size_t B, const uint64_t *shares,
+                                     int sender_major, uint64_t *coeffs, uint64_t *secrets, int32_t *status);
+int hbmpc_gl_elementwise(hbmpc_ctx *ctx, int op, size_t count, const uint64_t *a, const uint64_t *b, uint64_t *out);
+/* device ordinal of a context */
+int hbmpc_ctx_device(const hbmpc_ctx *ctx);
+
 /* Single-process multi-GPU.  The reference party is one process that issues all sessions' work before awaiting
  * (honeybadger/mod.rs:245-257,1362-1375); every call of this path is a map over independent secrets / chunks / codewords, so a group
  * (one context per device, tables replicated) splits the batch into contiguous ranges [g*B/G, (g+1)*B/G), one internal host thread

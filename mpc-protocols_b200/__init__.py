@@ -36,6 +36,8 @@ EXPORTS = [
     "hbmpc_measure_imad_peak", "hbmpc_measure_wide_chains", "hbmpc_measure_mont_mul",
     "hbmpc_sample_fr_batch", "hbmpc_sample_polynomials", "hbmpc_share_secrets_batch",
     "hbmpc_batch_recover_msgs", "hbmpc_batch_recover_secrets_msgs", "hbmpc_apply_vandermonde_msgs",
+    "hbmpc_gl_compute_shares_batch", "hbmpc_gl_apply_vandermonde_batch", "hbmpc_gl_batch_recover", "hbmpc_gl_nonrobust_recover_batch",
+    "hbmpc_gl_elementwise", "hbmpc_ctx_device",
     "hbmpc_group_create", "hbmpc_group_destroy", "hbmpc_group_size", "hbmpc_group_ctx", "hbmpc_group_shard_range",
     "hbmpc_group_compute_shares_batch", "hbmpc_group_apply_vandermonde_batch", "hbmpc_group_batch_recover",
     "hbmpc_group_batch_recover_secrets", "hbmpc_group_robust_interpolate_batch",
@@ -89,6 +91,12 @@ def load_library():
     lib.hbmpc_batch_recover_msgs.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp, vp]
     lib.hbmpc_batch_recover_secrets_msgs.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp]
     lib.hbmpc_apply_vandermonde_msgs.argtypes = [vp, sz, sz, sz, vp, vp]
+    lib.hbmpc_gl_compute_shares_batch.argtypes = [vp, sz, sz, sz, vp, vp]
+    lib.hbmpc_gl_apply_vandermonde_batch.argtypes = [vp, sz, sz, sz, vp, vp, ci]
+    lib.hbmpc_gl_batch_recover.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp, vp]
+    lib.hbmpc_gl_nonrobust_recover_batch.argtypes = [vp, sz, sz, sz, vp, sz, vp, ci, vp, vp, vp]
+    lib.hbmpc_gl_elementwise.argtypes = [vp, ci, sz, vp, vp, vp]
+    lib.hbmpc_ctx_device.argtypes = [vp]
     lib.hbmpc_group_create.argtypes = [C.POINTER(ci), sz, C.POINTER(vp)]
     lib.hbmpc_group_destroy.argtypes = [vp]
     lib.hbmpc_group_destroy.restype = None
@@ -363,6 +371,45 @@ class Context:
         B = s.shape[0]
         out = s.like((B, n, 4)) if out is None else out
         self._check(self.lib.hbmpc_share_secrets_batch(self.h, sd.ctypes.data, n, d, B, s.ptr, _ptr(out), _ptr(coeffs_out) if coeffs_out is not None else None))
+        return out
+
+    # -- N4 tail: Goldilocks (Fp64, p = 2^64 - 2^32 + 1); elements are single canonical uint64 values, host numpy arrays
+    def gl_compute_shares_batch(self, coeffs, n: int):
+        c = np.ascontiguousarray(coeffs, dtype=np.uint64)
+        B, m = c.shape
+        out = np.zeros((B, n), dtype=np.uint64)
+        self._check(self.lib.hbmpc_gl_compute_shares_batch(self.h, n, m - 1, B, c.ctypes.data, out.ctypes.data))
+        return out
+
+    def gl_apply_vandermonde_batch(self, inp, n: int, recipient_major: bool = False):
+        x = np.ascontiguousarray(inp, dtype=np.uint64)
+        B, cols = x.shape
+        out = np.zeros((n, B) if recipient_major else (B, n), dtype=np.uint64)
+        self._check(self.lib.hbmpc_gl_apply_vandermonde_batch(self.h, n, cols, B, x.ctypes.data, out.ctypes.data, int(recipient_major)))
+        return out
+
+    def gl_batch_recover(self, sender_ids, evals, n: int, d: int, t: int):
+        e = np.ascontiguousarray(evals, dtype=np.uint64)
+        S, B = e.shape
+        ids = np.ascontiguousarray(sender_ids, dtype=np.uint64)
+        coeffs, secrets, path = np.zeros((B, d + 1), dtype=np.uint64), np.zeros(B, dtype=np.uint64), np.zeros(B, dtype=np.int32)
+        rc = self.lib.hbmpc_gl_batch_recover(self.h, n, d, t, S, ids.ctypes.data, B, e.ctypes.data, coeffs.ctypes.data, secrets.ctypes.data, path.ctypes.data)
+        self._check(rc, ok=(0, DECODING_ERROR))
+        return rc, coeffs, secrets, path
+
+    def gl_nonrobust_recover_batch(self, ids, shares, n: int, deg: int, sender_major: bool = False):
+        s = np.ascontiguousarray(shares, dtype=np.uint64)
+        S, B = (s.shape[0], s.shape[1]) if sender_major else (s.shape[1], s.shape[0])
+        idv = np.ascontiguousarray(ids, dtype=np.uint64)
+        coeffs, secrets, status = np.zeros((B, deg + 1), dtype=np.uint64), np.zeros(B, dtype=np.uint64), np.zeros(B, dtype=np.int32)
+        self._check(self.lib.hbmpc_gl_nonrobust_recover_batch(self.h, n, deg, len(idv), idv.ctypes.data, B, s.ctypes.data, int(sender_major),
+                                                               coeffs.ctypes.data, secrets.ctypes.data, status.ctypes.data))
+        return coeffs, secrets, status
+
+    def gl_elementwise(self, op: int, a, b):
+        x, y = np.ascontiguousarray(a, dtype=np.uint64), np.ascontiguousarray(b, dtype=np.uint64)
+        out = np.zeros_like(x)
+        self._check(self.lib.hbmpc_gl_elementwise(self.h, op, x.size, x.ctypes.data, y.ctypes.data, out.ctypes.data))
         return out
 
     def measure_mont_mul(self, ilp: int, warps_per_smsp: int) -> float:

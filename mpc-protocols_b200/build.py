@@ -11,7 +11,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhbmpc_b200.so")
-SOURCES = ["hbmpc.cu", "compat_share.cu"]
+SOURCES = ["hbmpc.cu", "compat_share.cu", "goldilocks.cu"]
 HEADERS = ["fr.cuh", "matvec.cuh", "ntt.cuh", "ntt16x.cuh", "sampler.cuh", "robust.cuh", "tables.hpp", "host_fr.hpp", os.path.join("..", "..", "include", "hbmpc_b200.h"), os.path.join("..", "..", "include", "hbmpc_compat_share.h")]
 
 NVCC_FLAGS = [

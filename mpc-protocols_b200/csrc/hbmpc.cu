@@ -498,9 +498,12 @@ static void note_destroy_error(const char *what) {
     if (e != cudaSuccess && getenv("HBMPC_DEBUG")) fprintf(stderr, "hbmpc_ctx_destroy: %s: %s\n", what, cudaGetErrorString(e));
 }
 
+extern "C" void hbmpc_gl_release(const hbmpc_ctx *ctx);   // goldilocks.cu
+extern "C" int hbmpc_ctx_device(const hbmpc_ctx *ctx) { return ctx ? ctx->device : -1; }
 extern "C" void hbmpc_ctx_destroy(hbmpc_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    hbmpc_gl_release(ctx);
     for (auto &ln : ctx->lanes)
         if (ln.stream) cudaStreamSynchronize(ln.stream);
     note_destroy_error("sync");
