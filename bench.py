@@ -455,6 +455,54 @@ def leg_sampler(torch, hb, ctx, stream, dev, cm):
     return out
 
 
+def leg_goldilocks(torch, hb, ctx, dev, cm):
+    """share generation + optimistic batch recovery over GoldilocksField (Fp64), n=64, t=21, 2^20 secrets, device-resident
+    (hbmpc_gl_* take device pointers; 8-byte elements)."""
+    B, n, d, t = 1 << 20, N_PARTIES, DEG, T_FAULTS
+    P = 0xFFFFFFFF00000001
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x601D)
+    coeffs = torch.randint(0, 1 << 62, (B, d + 1), dtype=torch.int64, device=dev, generator=g)   # < p
+    shares = torch.empty((B, n), dtype=torch.int64, device=dev)
+    rec = torch.empty((B, d + 1), dtype=torch.int64, device=dev)
+    path = torch.empty((B,), dtype=torch.int32, device=dev)
+    ids = np.arange(n, dtype=np.uint64)
+    lib, h = ctx.lib, ctx.h
+    torch.cuda.synchronize()
+
+    def gen():
+        assert lib.hbmpc_gl_compute_shares_batch(h, n, d, B, coeffs.data_ptr(), shares.data_ptr()) == 0
+
+    gen()
+    evals = shares.t().contiguous()
+    torch.cuda.synchronize()
+
+    def recon():
+        assert lib.hbmpc_gl_batch_recover(h, n, d, t, n, ids.ctypes.data, B, evals.data_ptr(), rec.data_ptr(), None, path.data_ptr()) == 0
+
+    recon()
+
+    def wall(fn, reps=3):
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps   # the calls are synchronous
+
+    tg, tr = wall(gen), wall(recon)
+    ok = bool(torch.equal(rec, coeffs)) and not bool(path.any())
+    out = {"workload": "GoldilocksField (p = 2^64 - 2^32 + 1): hbmpc_gl_compute_shares_batch + hbmpc_gl_batch_recover, n=64, t=21, 2^20 secrets, device-resident",
+           "secrets": B, "gen_ms": 1e3 * tg, "recon_ms": 1e3 * tr, "shares_per_s": 2 * B * n / (tg + tr), "roundtrip_ok": ok,
+           "hbm_gbs": {"gen": B * (d + 1 + n) * 8 / tg / 1e9, "recon": B * (d + t + 1 + d + 1) * 8 / tr / 1e9}}
+    if cm is not None:
+        from oracle import goldilocks as glo
+        k = 64
+        cs = coeffs[:k].cpu().numpy().astype(np.uint64)
+        sh = shares[:k].cpu().numpy().astype(np.uint64)
+        out["parity_sample"] = {"items": k, "ok": bool(all([int(v) for v in sh[b]] == glo.compute_shares([int(v) for v in cs[b]], n) for b in range(k))),
+                                "what": "shares of the first 64 secrets == oracle/goldilocks.py"}
+    return out
+
+
 def leg_group(torch, hb, n_dev, log2_total, cm):
     """One process, n_dev GPUs: member contexts of an hbmpc_group driven from this process."""
     ids = np.arange(N_PARTIES)
@@ -758,6 +806,7 @@ def run_b200(args):
             torch.cuda.empty_cache()
         if n_gpus == 1:
             configs["n4_device_sampling"] = leg_sampler(torch, hb, ctx, stream, dev, cm)
+            configs["n4_goldilocks"] = leg_goldilocks(torch, hb, ctx, dev, cm)
         c5 = leg_c5(torch, hb, ctx, stream, dev, cm, args.log2_c5, rank)
         tot5 = max_over_ranks([c5.pop("_total_s")])[0]
         ok5 = min(max_over_ranks([0.0 if c5["self_consistent"] else 1.0])) == 0.0

@@ -151,8 +151,29 @@ def _ptr(x):
     return x.data_ptr() if _is_torch(x) else x.ctypes.data
 
 
+def _check_out(x, shape, itemsize=8, name="out"):
+    """A caller-supplied output must be contiguous and hold exactly `shape` elements of `itemsize` bytes: the library writes through
+    the raw pointer (a wrong shape or a strided view would be written past its end)."""
+    want = int(np.prod(shape)) * itemsize
+    if _is_torch(x):
+        if not x.is_contiguous():
+            raise ValueError(f"{name}: torch tensor must be contiguous")
+        have = x.numel() * x.element_size()
+    else:
+        if not isinstance(x, np.ndarray) or not x.flags["C_CONTIGUOUS"] or not x.flags["WRITEABLE"]:
+            raise ValueError(f"{name}: numpy array must be C-contiguous and writeable")
+        have = x.nbytes
+    if have != want:
+        raise ValueError(f"{name}: {have} bytes supplied, {want} needed for shape {tuple(shape)}")
+    return x
+
+
 class Context:
-    """One context per GPU (``hbmpc_ctx``): stream, cached constant tables, scratch."""
+    """One context per GPU (``hbmpc_ctx``): stream, cached constant tables, scratch.
+
+    Torch CUDA tensors are processed on the CONTEXT's stream (created non-blocking: it is not ordered against torch's current
+    stream).  Either call ``set_stream(torch.cuda.current_stream().cuda_stream)`` once -- what bench.py and tools/ do -- or
+    ``use_torch_stream()`` before calls whose inputs were produced on torch's current stream."""
 
     def __init__(self, device: int = 0):
         self.lib = load_library()
@@ -178,6 +199,12 @@ class Context:
     def set_stream(self, cuda_stream: int):
         self.lib.hbmpc_ctx_set_stream(self.h, C.c_void_p(cuda_stream))
 
+    def use_torch_stream(self):
+        """Move the context onto torch's current stream (so tensors produced by torch ops are ordered before the library's kernels)."""
+        import torch
+
+        self.set_stream(torch.cuda.current_stream().cuda_stream)
+
     def set_async(self, flag: bool):
         self.lib.hbmpc_ctx_set_async(self.h, int(flag))
 
@@ -201,7 +228,7 @@ class Context:
         """coeffs[B][d+1][4] -> shares[B][n][4]   (RobustShare::compute_shares, robust_interpolate.rs:52-82)"""
         c = _Buf(coeffs)
         B, m = c.shape[0], c.shape[1]
-        out = c.like((B, n, 4)) if out is None else out
+        out = c.like((B, n, 4)) if out is None else _check_out(out, (B, n, 4))
         self._check(self.lib.hbmpc_compute_shares_batch(self.h, n, m - 1, B, c.ptr, _ptr(out)))
         return out
 
@@ -210,7 +237,7 @@ class Context:
         """in[B][cols][4] -> out[B][n][4] (or [n][B][4])   (apply_vandermonde, common/share/mod.rs:50-76)"""
         x = _Buf(inp)
         B, cols = x.shape[0], x.shape[1]
-        out = x.like((n, B, 4) if recipient_major else (B, n, 4)) if out is None else out
+        out = x.like((n, B, 4) if recipient_major else (B, n, 4)) if out is None else _check_out(out, (n, B, 4))
         self._check(self.lib.hbmpc_apply_vandermonde_batch(self.h, n, cols, B, x.ptr, _ptr(out), int(recipient_major)))
         return out
 
@@ -219,7 +246,7 @@ class Context:
         rows, cols = M.shape[0], M.shape[1]
         x = _Buf(inp)
         B = x.shape[0]
-        out = x.like((rows, B, 4) if recipient_major else (B, rows, 4)) if out is None else out
+        out = x.like((rows, B, 4) if recipient_major else (B, rows, 4)) if out is None else _check_out(out, (rows, B, 4))
         self._check(self.lib.hbmpc_apply_matrix_batch(self.h, rows, cols, M.ctypes.data, B, x.ptr, _ptr(out), int(recipient_major)))
         return out
 
@@ -230,11 +257,17 @@ class Context:
         e = _Buf(evals)
         S, B = e.shape[0], e.shape[1]
         ids = np.ascontiguousarray(sender_ids, dtype=np.uint64)
+        if len(ids) != S:
+            raise ValueError(f"{len(ids)} sender ids for {S} sender vectors")
         if out is None:
             coeffs, path = e.like((B, d + 1, 4)), e.like((B,), "i32")
             flags = e.like((B, (S + 63) // 64), "u64") if want_flags else None
         else:
             coeffs, path, flags = out
+            _check_out(coeffs, (B, d + 1, 4), name="coeffs")
+            _check_out(path, (B,), 4, name="path")
+            if flags is not None:
+                _check_out(flags, (B, (S + 63) // 64), name="flags")
         rc = self.lib.hbmpc_batch_recover(self.h, n, d, t, S, ids.ctypes.data, B, e.ptr, _ptr(coeffs), _ptr(path),
                                           _ptr(flags) if flags is not None else None)
         self._check(rc, ok=(0, DECODING_ERROR))
@@ -244,10 +277,14 @@ class Context:
         e = _Buf(evals)
         S, B = e.shape[0], e.shape[1]
         ids = np.ascontiguousarray(sender_ids, dtype=np.uint64)
+        if len(ids) != S:
+            raise ValueError(f"{len(ids)} sender ids for {S} sender vectors")
         if out is None:
             secrets, path = e.like((B, 4)), e.like((B,), "i32")
         else:
             secrets, path = out
+            _check_out(secrets, (B, 4), name="secrets")
+            _check_out(path, (B,), 4, name="path")
         rc = self.lib.hbmpc_batch_recover_secrets(self.h, n, d, t, S, ids.ctypes.data, B, e.ptr, _ptr(secrets), _ptr(path))
         self._check(rc, ok=(0, DECODING_ERROR))
         return rc, secrets, path
@@ -258,11 +295,18 @@ class Context:
         s = _Buf(shares)
         B, S = s.shape[0], s.shape[1]
         idv = np.ascontiguousarray(ids, dtype=np.uint64)
+        if len(idv) != S:
+            raise ValueError(f"{len(idv)} ids for codewords of {S} shares")
         if out is None:
             coeffs, secrets, path = s.like((B, d + 1, 4)), s.like((B, 4)), s.like((B,), "i32")
             flags = s.like((B, (S + 63) // 64), "u64") if want_flags else None
         else:
             coeffs, secrets, path, flags = out
+            _check_out(coeffs, (B, d + 1, 4), name="coeffs")
+            _check_out(secrets, (B, 4), name="secrets")
+            _check_out(path, (B,), 4, name="path")
+            if flags is not None:
+                _check_out(flags, (B, (S + 63) // 64), name="flags")
         rc = self.lib.hbmpc_robust_interpolate_batch(self.h, n, d, t, S, idv.ctypes.data, B, s.ptr, _ptr(coeffs), _ptr(secrets),
                                                      _ptr(path), _ptr(flags) if flags is not None else None)
         self._check(rc, ok=(0, DECODING_ERROR))
@@ -307,10 +351,15 @@ class Context:
         s = _Buf(shares)
         S, B = (s.shape[0], s.shape[1]) if sender_major else (s.shape[1], s.shape[0])
         idv = np.ascontiguousarray(ids, dtype=np.uint64)
+        if len(idv) != S:
+            raise ValueError(f"{len(idv)} ids for codewords of {S} shares")
         if out is None:
             coeffs, secrets, status = s.like((B, deg + 1, 4)), s.like((B, 4)), s.like((B,), "i32")
         else:
             coeffs, secrets, status = out
+            _check_out(coeffs, (B, deg + 1, 4), name="coeffs")
+            _check_out(secrets, (B, 4), name="secrets")
+            _check_out(status, (B,), 4, name="status")
         self._check(self.lib.hbmpc_nonrobust_recover_batch(self.h, n, deg, len(idv), idv.ctypes.data, B, s.ptr, int(sender_major),
                                                             _ptr(coeffs), _ptr(secrets), _ptr(status)))
         return coeffs, secrets, status
@@ -319,7 +368,7 @@ class Context:
     def elementwise(self, op: int, a, b, out=None):
         x, y = _Buf(a), _Buf(b)
         count = int(np.prod(x.shape[:-1]))
-        out = x.like(x.shape) if out is None else out
+        out = x.like(x.shape) if out is None else _check_out(out, x.shape)
         self._check(self.lib.hbmpc_elementwise(self.h, op, count, x.ptr, y.ptr, _ptr(out)))
         return out
 

@@ -60,3 +60,16 @@ def test_product_never_imports_oracle():
 def test_limb_helpers(hb):
     v = [0, 1, hb.R_MOD - 1, 1 << 200]
     assert hb.from_limbs(hb.to_limbs(v)) == v
+
+
+def test_binding_rejects_outputs_of_the_wrong_size(hb):
+    """the ctypes layer writes through raw pointers: outputs are checked before the call (no GPU needed to trip the check)"""
+    import numpy as np
+
+    with pytest.raises(ValueError):
+        hb._check_out(np.zeros((3, 4, 4), dtype=np.uint64), (3, 5, 4))
+    with pytest.raises(ValueError):
+        hb._check_out(np.zeros((6, 4), dtype=np.uint64)[::2], (3, 4))          # strided view
+    with pytest.raises(ValueError):
+        hb._check_out(np.zeros(3, dtype=np.int64), (3,), 4, name="path")       # wrong element size
+    assert hb._check_out(np.zeros((3, 4), dtype=np.uint64), (3, 4)) is not None

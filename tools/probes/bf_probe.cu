@@ -58,6 +58,30 @@ __global__ void __launch_bounds__(128) probe(unsigned int *sink, unsigned int se
             fr_add(s, u, t); fr_sub(d, u, t); fr_add(s2, u2, t2); fr_sub(d2, u2, t2);
             for (int i = 0; i < 8; ++i) { u[i] = s[i]; v[i] = d[i]; u2[i] = s2[i]; v2[i] = d2[i]; }
         }
+    } else if (V == 7) {   // register-blocked: 8 elements of a row in registers, 3 stages (12 butterflies), one shared-memory round trip per 12 products
+        for (int it = 0; it < iters; it += 12) {
+            uint32_t x[8][8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) lds8(x[e], D + (e * 2) * 32 + lane);
+#pragma unroll
+            for (int s2 = 0; s2 < 3; ++s2) {
+#pragma unroll
+                for (int bf = 0; bf < 4; ++bf) {
+                    const int h = 1 << s2, lo = bf & (h - 1), bu = ((bf >> s2) << (s2 + 1)) | lo;
+                    uint32_t t[8], sm_[8], d[8], tw[8];
+                    lds8(tw, D + (((lo + s2 + lane) & 7) * 2) * 32 + (lane ^ 1));
+                    tw[7] &= 0x3fffffff;
+                    mont_mul(t, x[bu + h], tw);
+                    fr_add(sm_, x[bu], t); fr_sub(d, x[bu], t);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { x[bu][i] = sm_[i]; x[bu + h][i] = d[i]; }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sts8(D + (e * 2) * 32 + lane, x[e]);
+            __syncwarp();
+        }
     } else if (V == 6) {   // software pipelined: the add/sub of butterfly k overlaps the product of butterfly k+1 (independent data)
         uint32_t t[8];
         mont_mul(t, v, w);
@@ -100,6 +124,7 @@ int main(int argc, char **argv) {
     printf("\"v2_butterfly_smem_inline\": %.2f, ", run<2>(wps, iters, sink));
     printf("\"v3_butterfly_smem_noinline_call\": %.2f, ", run<3>(wps, iters, sink));
     printf("\"v5_two_butterflies_registers\": %.2f, ", run<5>(wps, iters, sink));
-    printf("\"v6_software_pipelined\": %.2f}}\n", run<6>(wps, iters, sink));
+    printf("\"v6_software_pipelined\": %.2f, ", run<6>(wps, iters, sink));
+    printf("\"v7_register_blocked_8x3\": %.2f}}\n", run<7>(wps, iters, sink));
     return 0;
 }
