@@ -503,6 +503,12 @@ def leg_goldilocks(torch, hb, ctx, dev, cm):
     return out
 
 
+def _sync_ok(c, what):
+    rc = c.synchronize()
+    if rc != 0:
+        raise RuntimeError("%s: hbmpc_ctx_synchronize -> %d (%s)" % (what, rc, c.last_error()))
+
+
 def leg_group(torch, hb, n_dev, log2_total, cm):
     """One process, n_dev GPUs: member contexts of an hbmpc_group driven from this process."""
     ids = np.arange(N_PARTIES)
@@ -517,9 +523,10 @@ def leg_group(torch, hb, n_dev, log2_total, cm):
             c.set_async(True)
             co = random_fr_device(torch, (hi - lo, M), 0x5EED0600 + g, dv)
             sh = torch.empty((hi - lo, N_PARTIES, 4), dtype=torch.int64, device=dv)
+            torch.cuda.synchronize(dv)   # the context's stream is not ordered against torch's: the inputs must be complete
             c.compute_shares_batch(co, N_PARTIES, out=sh)
             torch.cuda.synchronize(dv)
-            assert c.synchronize() == 0
+            _sync_ok(c, 'group member %d set-up' % g)
             ev = sh.permute(1, 0, 2).contiguous()
             rec = torch.empty((hi - lo, M, 4), dtype=torch.int64, device=dv)
             pth = torch.empty((hi - lo,), dtype=torch.int32, device=dv)
@@ -530,8 +537,8 @@ def leg_group(torch, hb, n_dev, log2_total, cm):
         for c, co, sh, ev, rec, pth in members:     # enqueue-only calls: all devices run concurrently
             c.compute_shares_batch(co, N_PARTIES, out=sh)
             c.batch_recover(ids, ev, N_PARTIES, DEG, T_FAULTS, out=(rec, pth, None))
-        for c, *_ in members:
-            assert c.synchronize() == 0
+        for i, (c, *_) in enumerate(members):
+            _sync_ok(c, 'group member %d step' % i)
 
     for _ in range(3):
         step()

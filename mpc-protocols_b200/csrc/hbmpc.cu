@@ -260,7 +260,8 @@ struct RecoverTables {
     // general optimistic check without flags: erasure-weighted inverse NTT + triangular coefficient recovery
     int er_logn = 0, er_zero_from = 0;
     bool er_all = false;  // tables built over ALL supplied ids (calls with flags): a chunk that passes has every flag clear
-    int *er_row_len = nullptr;
+    int *er_row_len = nullptr, *er_row_start = nullptr;
+    int er_h1 = 0, er_h2 = 0, er_hi_top = 0;   // two-sided recovery: low / high rows, index of the top coefficient of Q
     uint4 *er_wt = nullptr, *er_tri = nullptr;
     std::vector<void *> allocs;  // device memory of this entry (freed when the entry is evicted)
 };
@@ -1219,26 +1220,51 @@ static int build_recover_tables(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, si
             for (size_t i = Z.size(); i-- > 0;) acc = hfr::add(hfr::mul(acc, domN[k]), Z[i]);
             wt[k] = acc;
         }
-        // W = (N*Zc)^{-1} mod x^m
+        // P = Q / (N*Zc), from BOTH ends of Q (Q = P*N*Zc is exact when the check passes, deg Q <= d + zdeg, zdeg = deg Zc):
+        //   low half   p_k     = sum_{i<=k} q_i          * Wlo[k-i],  k < h1,   Wlo = (N*Zc)^{-1}      mod x^h1
+        //   high half  p_{d-i} = sum_{j<=i} q_{d+zdeg-j} * Whi[i-j],  i < h2,   Whi = rev(N*Zc)^{-1}   mod x^h2
+        // two triangles of h1 and h2 = m - h1 rows (132 terms at m = 22) instead of one of m rows (253).  The transform stores
+        // q_0 .. q_{h1-1} and then q_{d+zdeg}, q_{d+zdeg-1}, ... (NttArgs::hi_top / hi_cnt); row k of the matrix reads its
+        // row_len[k] columns from column row_start[k].  Secrets only (mout = 1): one product with Wlo[0].
         HFr Nf = hfr::from_u64((uint64_t)N);
-        std::vector<HFr> Zs(m, hfr::ZERO), W(m, hfr::ZERO);
-        for (size_t i = 0; i < m && i < Z.size(); ++i) Zs[i] = hfr::mul(Z[i], Nf);
-        W[0] = hfr::inv(Zs[0]);
-        HFr nW0 = hfr::neg(W[0]);
-        for (size_t k = 1; k < m; ++k) {
-            HFr acc = hfr::ZERO;
-            for (size_t i = 1; i <= k; ++i) acc = hfr::add(acc, hfr::mul(Zs[i], W[k - i]));
-            W[k] = hfr::mul(nW0, acc);
-        }
+        const size_t zdeg = Z.size() - 1;
+        const size_t h1 = (mout + 1) / 2, h2 = mout - h1;
+        auto series_inverse = [&](const std::vector<HFr> &A, size_t terms) {   // (sum A_i x^i)^{-1} mod x^terms
+            std::vector<HFr> W(terms, hfr::ZERO);
+            if (!terms) return W;
+            W[0] = hfr::inv(A[0]);
+            const HFr nW0 = hfr::neg(W[0]);
+            for (size_t k = 1; k < terms; ++k) {
+                HFr acc = hfr::ZERO;
+                for (size_t i = 1; i <= k && i < A.size(); ++i) acc = hfr::add(acc, hfr::mul(A[i], W[k - i]));
+                W[k] = hfr::mul(nW0, acc);
+            }
+            return W;
+        };
+        std::vector<HFr> Zs(Z.size()), Zr(Z.size());
+        for (size_t i = 0; i <= zdeg; ++i) Zs[i] = hfr::mul(Z[i], Nf);
+        for (size_t i = 0; i <= zdeg; ++i) Zr[i] = Zs[zdeg - i];
+        const std::vector<HFr> Wlo = series_inverse(Zs, h1), Whi = series_inverse(Zr, h2);
         std::vector<HFr> tri(mout * mout, hfr::ZERO);
-        std::vector<int> row_len(mout);
-        for (size_t k = 0; k < mout; ++k) {
+        std::vector<int> row_len(mout), row_start(mout);
+        for (size_t k = 0; k < h1; ++k) {
+            row_start[k] = 0;
             row_len[k] = (int)k + 1;
-            for (size_t i = 0; i <= k; ++i) tri[k * mout + i] = W[k - i];
+            for (size_t i = 0; i <= k; ++i) tri[k * mout + i] = Wlo[k - i];
+        }
+        for (size_t k = h1; k < mout; ++k) {   // k = d - i
+            const size_t i = (mout - 1) - k;
+            row_start[k] = (int)h1;
+            row_len[k] = (int)i + 1;
+            for (size_t j = 0; j <= i; ++j) tri[k * mout + h1 + j] = Whi[i - j];
         }
         if ((rc = upload(ctx, row_len, &T.er_row_len, &T.allocs))) return rc;
+        if ((rc = upload(ctx, row_start, &T.er_row_start, &T.allocs))) return rc;
         if ((rc = upload_fr(ctx, wt, &T.er_wt, &T.allocs))) return rc;
         if ((rc = upload_fr(ctx, tri, &T.er_tri, &T.allocs))) return rc;
+        T.er_h1 = (int)h1;
+        T.er_h2 = (int)h2;
+        T.er_hi_top = (int)((mout - 1) + zdeg);   // mout = d + 1 whenever h2 > 0
         if (!T.itw && (rc = get_inverse_twiddles(ctx, N, &T.itw, &T.iscale))) return rc;
         T.er_zero_from = N - (int)(xcount - m);  // deg Q <= d + N - |X|
         while ((1 << T.er_logn) < N) ++T.er_logn;
@@ -1704,7 +1730,9 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             na.in_map = er_all ? P.in_map : P.er_in_map;
             na.wt = T.er_wt;
             na.m = T.er_zero_from;
-            na.mout = T.mout;
+            na.mout = T.er_h1;
+            na.hi_top = T.er_hi_top;
+            na.hi_cnt = T.er_h2;
             na.fail = er_all ? fail1 : fail;
             na.path = (int *)vp.dev;
             if ((rc = launch_ntt<2>(ctx, ln.stream, T.er_logn, na))) return rc;
@@ -1718,6 +1746,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             tr.in_sb = T.mout; tr.in_sc = 1; tr.in_chunk_major = 1;
             tr.out_sb = T.mout; tr.out_sr = 1;
             tr.row_len = T.er_row_len;
+            tr.row_start = T.er_row_start;
             if ((rc = launch_matvec(ctx, ln, tr, 0))) return rc;
             if (er_all) {  // like the all-points check: only the chunks it rejects see the dense check (which sets the flags)
                 compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail1, (long long)Bc, list1, count1);

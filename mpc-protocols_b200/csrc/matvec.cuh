@@ -43,7 +43,8 @@ struct MatvecArgs {
     int in_chunk_major;        // 1: in_sc == 1 (tile is contiguous), 0: in_sb == 1 (sender-major)
     const unsigned int *item_list;   // optional indirection: process items item_list[0 .. *item_count) instead of 0 .. B
     const unsigned int *item_count;
-    const int *row_len;        // optional [R]: row r uses only its first row_len[r] columns (triangular matrices)
+    const int *row_len;        // optional [R]: row r uses only row_len[r] columns (triangular matrices) ...
+    const int *row_start;      // ... starting at column row_start[r] (optional, with row_len; nullptr: column 0)
     int M_ld;                  // leading dimension of M in elements (0: C) -- column blocks of a wider matrix
     int col0;                  // first column of the block: column c reads input col_map[col0 + c] (or col0 + c)
 };
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
             const bool live = b < NB;
             if (live && a.item_list) b = a.item_list[b];
             const uint4 *Mrow = sM + (size_t)rl * C * 2;
-            const uint4 *Dsub = sD + (size_t)sub * C * 64 + lane;
+            const uint4 *Dsub = sD + (size_t)sub * C * 64 + lane;   // (both advanced to the row's first column below)
             const bool is_chk = r < a.n_chk;
             // the supplied share a check row is compared with (prefetched; hidden behind the dot product)
             uint4 y_lo = make_uint4(0, 0, 0, 0), y_hi = y_lo;
@@ -130,6 +131,11 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
             acc_zero(A);
             unsigned bad = 0;
             const int Cr = a.row_len ? a.row_len[r] : C;  // terms of this row
+            if (a.row_len && a.row_start) {                // ... starting at column row_start[r]
+                const int cs = a.row_start[r];
+                Mrow += cs * 2;
+                Dsub += cs * 64;
+            }
             const bool validate = (rl == 0);  // one row per slice validates the tile's inputs (each input exactly once per slice)
             // two register sets, loads issued one term ahead, no register moves (loop unrolled by two)
             uint4 a0 = Dsub[0], a1 = Dsub[32], b0 = Mrow[0], b1 = Mrow[1];

@@ -55,6 +55,9 @@ struct NttArgs {
     // in[b] at the q-th set bit of rootmask[b]), scaled by N^{-1}, SUBTRACTED from out[item_list[b]][k], k < mout
     int out_group32;       // MODE 2: output slot b, element pos at out[(((b>>5)*out_sb + pos)*2 + half)*32 + (b&31)] (groups of 32
                            // slots interleaved at 16-byte granularity: one thread per slot reads it coalesced)
+    // MODE 2, two-sided recovery (hi_cnt > 0): besides the coefficients k < mout, the hi_cnt coefficients hi_top, hi_top-1, ... are
+    // stored, at out positions mout, mout+1, ... (the top of Q = P*Zc in reversed order: P's upper half is recovered from it)
+    int hi_top, hi_cnt;
     // ntt16x_kernel: dynamic tile queue (nullptr: static round-robin).  work[0] = tiles handed out beyond the first one of every
     // warp, work[1] = warps that have finished; the last warp to finish zeroes both, so the words are ready for the next launch
     // on the same stream.
@@ -197,6 +200,10 @@ __device__ __forceinline__ void ntt_emit(const NttArgs &a, long long b, int pos,
             }
         } else if (pos >= a.m) {
             if (!fr_is_zero(v)) a.fail[b] = 1;
+        } else if (MODE == 2 && pos <= a.hi_top && pos > a.hi_top - a.hi_cnt) {
+            uint4 *o = a.out + (b * a.out_sb + (long long)(a.mout + a.hi_top - pos) * a.out_sr) * 2;
+            stg_stream(o, make_uint4(v[0], v[1], v[2], v[3]));
+            stg_stream(o + 1, make_uint4(v[4], v[5], v[6], v[7]));
         }
     }
 }

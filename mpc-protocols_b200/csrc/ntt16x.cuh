@@ -118,11 +118,16 @@ __device__ __noinline__ unsigned bf_scale(unsigned pv, unsigned pw) {
 // scaled by 1/N), pos >= lim1 = m must vanish (bit 1 of the return value set otherwise), anything between is not wanted.
 // mul == 0: trivial twiddle.
 template <int LOGN, int MODE>
-__device__ __noinline__ unsigned bf_emit(unsigned pu, unsigned pv, unsigned pw, int mul, uint4 *out, long long out_sr, int posU, int posV, int lim0, int lim1) {
+__device__ __noinline__ unsigned bf_emit(unsigned pu, unsigned pv, unsigned pw, int mul, uint4 *out, long long out_sr, int posU, int posV, int lim0p, int lim1) {
+    // MODE 2: lim0p packs (mout, hi_cnt << 8, hi_top << 16): positions hi_top - hi_cnt < pos <= hi_top are stored too, at out index
+    // mout + hi_top - pos (NttArgs::hi_top / hi_cnt: the reversed top of the product polynomial)
+    const int lim0 = MODE == 2 ? (lim0p & 0xff) : lim0p;
+    const int hi_cnt = MODE == 2 ? ((lim0p >> 8) & 0xff) : 0, hi_top = MODE == 2 ? (lim0p >> 16) : -1;
     uint32_t u[8], v[8], t[8], sm[8], df[8];
     unsigned rc = 0;
     if (MODE != 0) {
-        const bool needU = posU < lim0 || posU >= lim1, needV = posV < lim0 || posV >= lim1;
+        const bool hiU = MODE == 2 && posU <= hi_top && posU > hi_top - hi_cnt, hiV = MODE == 2 && posV <= hi_top && posV > hi_top - hi_cnt;
+        const bool needU = posU < lim0 || posU >= lim1 || hiU, needV = posV < lim0 || posV >= lim1 || hiV;
         if (!needU && !needV) return 0u;
         if (posU >= lim1) {   // both must vanish <=> u == 0 and v == 0: no product
             lds_fr(u, pu);
@@ -148,14 +153,15 @@ __device__ __noinline__ unsigned bf_emit(unsigned pu, unsigned pv, unsigned pw, 
         uint32_t val[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) val[i] = z ? df[i] : sm[i];
-        if (pos < lim0) {
+        const bool hi = MODE == 2 && pos <= hi_top && pos > hi_top - hi_cnt && pos >= lim0 && pos < lim1;
+        if (pos < lim0 || hi) {
             uint32_t c[8];
             if (MODE == 1) fr_div_pow2<LOGN>(c, val);
             else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) c[i] = val[i];
             }
-            uint4 *o = out + (long long)pos * out_sr * 2;
+            uint4 *o = out + (long long)(hi ? lim0 + hi_top - pos : pos) * out_sr * 2;
             stg_stream(o, make_uint4(c[0], c[1], c[2], c[3]));
             stg_stream(o + 1, make_uint4(c[4], c[5], c[6], c[7]));
         } else if (MODE != 0 && pos >= lim1) {
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(NTT16X_WARPS * 32, ntt16x_minb<LOGN>()) ntt16x
     for (int i = 0; i < cnt; ++i) mask0 |= 1u << (__brev((unsigned)i) >> (32 - LOGS));
     // window address of element (row p, column c); half 1 at +512
     auto slot = [&](int p, int c) -> unsigned { return dD + (unsigned)(((p * 2) * 32 + (c ^ (p & (L - 1)))) * 16); };
-    const int lim0 = MODE == 0 ? a.n : a.mout, lim1 = a.m;
+    const int lim0 = MODE == 0 ? a.n : (MODE == 2 ? (a.mout | (a.hi_cnt << 8) | (a.hi_top << 16)) : a.mout), lim1 = a.m;
 
     const long long ntiles = (a.B + IPW - 1) / IPW;
     unsigned bad = 0;
