@@ -893,6 +893,8 @@ def run_b200(args):
             s4 = configs["c4"]["uniform"]["ms"] * 1e-3
             line["roofline_k4"] = roof("k4", "robust_interpolate_batch n=128,t=42, e~U{0..42}: all kernels of the call (dominant: bm_segment_kernel)", 13400, s4,
                                        configs["c4"]["codewords"] * (128 * 32 + 43 * 32 + 32 + 4 + 16), "k4", units=configs["c4"]["codewords"])
+            if "k4_per_2p17" in traffic:   # the staged decoder's state lives in HBM between its stages: traffic is far above the call's algorithmic bytes
+                line["roofline_k4"]["traffic"] = traffic["k4_per_2p17"] * configs["c4"]["codewords"] / (1 << 17)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -40,10 +40,13 @@ namespace hb {
 #ifndef HB_NTT16X_LOGS16
 #define HB_NTT16X_LOGS16 3   // log2(rows) for N = 16
 #endif
+#ifndef HB_NTT16X_LOGS128
+#define HB_NTT16X_LOGS128 3  // log2(rows) for N = 128.  3: 8 rows x 16 lanes per item, two lanes share a row in P1 (8 KB of tile per
+#endif                       // warp, 6 CTAs per SM); 4: 16 rows x 8 lanes (16 KB per warp: shared memory allows 3 CTAs per SM)
 constexpr int NTT16X_WARPS = 4;
 
 template <int LOGN>
-__host__ __device__ constexpr int ntt16x_logs() { return LOGN == 7 ? 4 : (LOGN == 4 ? HB_NTT16X_LOGS16 : HB_NTT16X_LOGS); }
+__host__ __device__ constexpr int ntt16x_logs() { return LOGN == 7 ? HB_NTT16X_LOGS128 : (LOGN == 4 ? HB_NTT16X_LOGS16 : HB_NTT16X_LOGS); }
 template <int LOGN>
 __host__ __device__ constexpr int ntt16x_minb() { return ntt16x_logs<LOGN>() == 3 ? HB_NTT16X_MINB8 : 3; }
 
@@ -178,8 +181,10 @@ __global__ void __launch_bounds__(NTT16X_WARPS * 32, ntt16x_minb<LOGN>()) ntt16x
     fma_ballast(a.B < 0, a.err);
     constexpr int LOGS = ntt16x_logs<LOGN>(), S = 1 << LOGS;
     constexpr int N = 1 << LOGN, LL = LOGN - LOGS, L = 1 << LL, IPW = 32 / L;
-    static_assert(L <= S && L <= 32, "every lane of an item owns at least one row in P1");
-    constexpr int ROWS = S / L;                                       // P1: rows per lane
+    static_assert(L <= 32 && (L <= S || L % S == 0), "P1: a lane owns S/L rows, or L/S lanes share one row");
+    constexpr int HALVES = L > S ? L / S : 1;                         // P1: lanes sharing one row (each takes 1/HALVES of a stage's butterflies)
+    constexpr int ROWS = L > S ? 1 : S / L;                           // P1: rows per lane
+    constexpr int BFL = (L / 2) / HALVES;                             // P1: butterflies per lane and stage
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4 *sTw = reinterpret_cast<uint4 *>(smem_raw);                 // [N/2][2]  w^k (w^-k for the inverse), Montgomery form
     uint4 *sWt = sTw + N;                                             // [N][2]    MODE 2: weights by domain index
@@ -281,11 +286,13 @@ __global__ void __launch_bounds__(NTT16X_WARPS * 32, ntt16x_minb<LOGN>()) ntt16x
             __syncwarp();
 #pragma unroll
             for (int e = 0; e < ROWS; ++e) {
-                const int q = L * e + j;
+                const int q = HALVES > 1 ? (j & (S - 1)) : L * e + j;
+                const int hf = HALVES > 1 ? (j >> LOGS) : 0;
 #pragma unroll
                 for (int s2 = 0; s2 < LL; ++s2) {
 #pragma unroll
-                    for (int bf = 0; bf < L / 2; ++bf) {
+                    for (int bfi = 0; bfi < BFL; ++bfi) {
+                        const int bf = hf * BFL + bfi;
                         const int hb2 = 1 << s2, lo = bf & (hb2 - 1), bu = ((bf >> s2) << (s2 + 1)) | lo;
                         const unsigned pu = slot(q, item * L + bu), pv = slot(q, item * L + bu + hb2);
                         const int twi = (S * lo + q) << (LL - 1 - s2);   // w_N^((pos mod h) * N/(2h)), h = S*2^s2
@@ -296,6 +303,7 @@ __global__ void __launch_bounds__(NTT16X_WARPS * 32, ntt16x_minb<LOGN>()) ntt16x
                             bf_mul(pu, pv, dTw + twi * 32, 0u);   // tw[0] is the Montgomery form of 1: the q = 0 row multiplies like the others
                         }
                     }
+                    if (HALVES > 1 && s2 + 1 < LL) __syncwarp();   // the next stage pairs columns written by the row's other lane(s)
                 }
             }
         }

@@ -24,6 +24,29 @@ python tools/ncu_ntt.py --what k4 --log2 17 --reps 2 > gpurun_out/ncu_plain_k4_$
 ncu $SEC --clock-control none --import-source on --profile-from-start off -o /tmp/k4_$TAG python tools/ncu_ntt.py --what k4 --log2 17 --reps 2 > gpurun_out/ncu_k4_$TAG.log 2>&1
 ncu -i /tmp/k4_$TAG.ncu-rep --page raw --csv > /tmp/raw_k4_$TAG.csv 2>/dev/null
 python tools/ncu_summary.py /tmp/raw_k4_$TAG.csv gpurun_out/raw_k4_summary_$TAG.json > /dev/null 2>&1
+python - /tmp/raw_k4_$TAG.csv gpurun_out/k4_traffic_$TAG.json <<'PYEOF'
+# DRAM traffic and duration of the WHOLE captured K4 call (all launches), per kernel name and in total
+import csv, json, sys, collections
+rows = list(csv.reader(open(sys.argv[1])))
+hdr, units, data = rows[0], rows[1], rows[2:]
+def col(name):
+    return hdr.index(name) if name in hdr else None
+ir, iw, it, ik = col("dram__bytes_read.sum"), col("dram__bytes_write.sum"), col("gpu__time_duration.sum"), col("Kernel Name")
+scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+tscale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+per = collections.OrderedDict()
+for r in data:
+    if ir is None or iw is None:
+        break
+    e = per.setdefault(r[ik].split("(")[0], {"launches": 0, "dram_bytes": 0.0, "ms": 0.0})
+    e["launches"] += 1
+    e["dram_bytes"] += float(r[ir] or 0) * scale.get(units[ir], 1) + float(r[iw] or 0) * scale.get(units[iw], 1)
+    if it is not None:
+        e["ms"] += float(r[it] or 0) * tscale.get(units[it], 1)
+tot = {"launches": sum(e["launches"] for e in per.values()), "dram_bytes": sum(e["dram_bytes"] for e in per.values()), "ms": sum(e["ms"] for e in per.values())}
+json.dump({"what": "one robust_interpolate_batch call, n=128, t=42, 2^17 codewords, e~U{0..42}: dram__bytes_read.sum + dram__bytes_write.sum and gpu__time_duration.sum over all its launches (ncu, serialised)", "codewords": 131072, "total": tot, "per_kernel": per}, open(sys.argv[2], "w"), indent=1)
+print(tot)
+PYEOF
 ncu -i /tmp/k4_$TAG.ncu-rep --page source --csv > /tmp/src_k4_$TAG.csv 2>/dev/null
 python tools/ncu_exec_counts.py /tmp/src_k4_$TAG.csv --items 131072 --aggregate --json gpurun_out/exec_k4_$TAG.json > gpurun_out/exec_k4_$TAG.txt
 cat gpurun_out/ncu_plain_k4_$TAG.log
