@@ -321,6 +321,9 @@ struct hbmpc_ctx {
     int staged_seg = 16;                            // HBMPC_STAGED_SEG: Berlekamp-Massey iterations between two re-sorts
     unsigned int *h_spec = nullptr;                 // pinned: failing-item count + per-sender error histogram of the scout pass
     bool attack_seen = false;                       // the last recovery calls met large failing sets: batches <= scan_max are compacted too
+    unsigned int dev_route_calls = 0;               // asynchronous recovery calls since the last status read that took the device-count staged route
+    bool async_staged = true;                       // HBMPC_ASYNC_STAGED=0: asynchronous calls never take it; 2: always, at any batch size (tests)
+    bool force_async_staged = false;
     bool no_er_flags = false;                       // HBMPC_NO_ER_FLAGS=1: calls with flags on a sender subset go straight to the dense check
     bool no_fastpath = false;                       // HBMPC_NO_FASTPATH=1: K3 never takes the all-shares-present inverse-NTT path
     bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
@@ -461,6 +464,8 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
         if (sm) ctx->staged_min = (size_t)atoll(sm);
         const char *sg = getenv("HBMPC_STAGED_SEG");
         if (sg && atoi(sg) > 0) ctx->staged_seg = atoi(sg);
+        const char *as = getenv("HBMPC_ASYNC_STAGED");
+        if (as) { ctx->async_staged = as[0] != '0'; if (as[0] == '2') { ctx->attack_seen = true; ctx->force_async_staged = true; } }
         const char *stl = getenv("HBMPC_STATIC_TILES");
         ctx->static_tiles = stl && stl[0] == '1';
         const char *cm = getenv("HBMPC_CHUNK_MB");
@@ -563,6 +568,11 @@ static int read_status(hbmpc_ctx *ctx, unsigned int &bad, unsigned int &undec) {
         ctx->attack_seen = true;
         hs[1] = 0;
     }
+    if (ctx->dev_route_calls) {   // asynchronous calls took the device-count route: none of them met a large failing set -> the attack is over
+        if (!hs[3] && !ctx->force_async_staged) ctx->attack_seen = false;
+        ctx->dev_route_calls = 0;
+    }
+    hs[3] = 0;
     hs[0] = 0;
     hs[2] = 0;
     return 0;
@@ -585,6 +595,7 @@ static int abandon_call(hbmpc_ctx *ctx, int rc) {
     hs[0] = 0;
     hs[1] = 0;
     hs[2] = 0;
+    hs[3] = 0;
     return rc;
 }
 
@@ -1293,7 +1304,9 @@ static size_t staged_wave_slots(const hbmpc_ctx *ctx, const RecoverTables &T, in
 // earlier call of the same capacity; hist_slots: r.hist samples the first hist_slots slots of every wave.
 static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const RobustArgs &r_in, const int *in_map, unsigned int first,
                          unsigned int cnt, long long fb_blocks, int fb_threads, unsigned int **direct = nullptr, unsigned int list2_cap = 0,
-                         bool append = false, unsigned int hist_slots = 0) {
+                         bool append = false, unsigned int hist_slots = 0, const unsigned int *cnt_dev = nullptr) {
+    // cnt_dev != nullptr (device-count mode, asynchronous calls): `cnt` is only an upper bound (one wave: the caller checks that it
+    // fits), the number of items is read on the device by every stage; slots beyond it are dead from the start
     if (cnt <= first) return 0;
     RobustArgs r = r_in;
     r.skip_coeffs = direct ? 1 : 0;
@@ -1351,6 +1364,11 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
     sa.uinv0 = T.uinv + T.uoff0 * 2;
     sa.list2 = list2; sa.count2 = count2;
     sa.direct = direct ? 1 : 0;
+    sa.cnt_dev = cnt_dev;
+    if (cnt_dev) {   // every wave of this mode re-raises the "attack continues" word while its failing set stays large
+        sa.attack_flag = ctx->d_status + 3;
+        sa.attack_min = (unsigned int)std::max<size_t>(ctx->staged_min / 2, 1);
+    }
     sa.hist_slots = r.hist ? (hist_slots ? hist_slots : 0xffffffffu) : 0u;
     sa.runs = (uint4 *)(w8 + o_runs); sa.okf = (unsigned char *)(w8 + o_okf);
     // resident CTAs of the Berlekamp-Massey kernel are capped through its dynamic shared memory size: the live state of the
@@ -1399,6 +1417,7 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
             na.wt = T.syn_wt;
             na.m = N + 1; na.mout = T.nsyn0;
             na.item_list = r.list + w0;
+            na.b_dev = cnt_dev; na.b_first = (unsigned int)w0;
             if ((rc = launch_ntt<2>(ctx, st, logn, na))) return rc;
         }
         if (prof) cudaEventRecord(pe[1], st);
@@ -1436,6 +1455,7 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
         nb.err = ctx->d_status;
         nb.rootmask = sa.rootmask;
         nb.idset = in_map;
+        nb.b_dev = cnt_dev; nb.b_first = (unsigned int)w0;
         nb.in = sa.lam;   // 4. Chien search
         if ((rc = launch_ntt<3>(ctx, st, logn, nb))) return rc;
         if (prof) cudaEventRecord(pe[4], st);
@@ -1462,6 +1482,7 @@ static int staged_decode(hbmpc_ctx *ctx, Lane &ln, const RecoverTables &T, const
             nc.mout = r.mout;
             nc.rootmask = sa.rootmask;
             nc.item_list = r.list + w0;
+            nc.b_dev = cnt_dev; nc.b_first = (unsigned int)w0;
             if ((rc = launch_ntt<5>(ctx, st, logn, nc))) return rc;
         }
         if (prof) {
@@ -1669,7 +1690,10 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         // session-sized batches: no compaction pass -- the decoder's threads look at fail[] themselves and compute Lc*y; unless the
         // context has just seen an attack (large failing sets): then the count is worth a synchronisation, because it opens the
         // staged decoder
-        const bool scan = Bc <= ctx->scan_max && !lean_phase && !(ctx->attack_seen && !ctx->async && Bc >= 2048);
+        // asynchronous calls of a context under attack (learnt at the last hbmpc_ctx_synchronize) compact too: the staged decoder then
+        // runs in device-count mode (no host decision), see staged_decode
+        const bool dev_route = ctx->async && ctx->async_staged && ctx->attack_seen && T.fast && (Bc >= 2048 || ctx->force_async_staged) && !lean_phase;
+        const bool scan = Bc <= ctx->scan_max && !lean_phase && !(ctx->attack_seen && !ctx->async && Bc >= 2048) && !dev_route;
         bool staged_direct = false;
         unsigned int *dense_list = list1, *dense_count = count1;
         if (fastN && T.fast && !ctx->async && !scan) {
@@ -1802,7 +1826,8 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             return chunk_commit(ctx, ln, bp, b0, Bc, vp);
         }
         r.fail_scan = scan ? fail : nullptr;
-        r.dense_fail_flag = (scan && !ctx->async && Bc >= 2048) ? ctx->d_status + 1 : nullptr;
+        r.dense_fail_flag = (Bc >= 2048 && (scan || ctx->async)) ? ctx->d_status + 1 : nullptr;
+        r.attack_min = (unsigned int)ctx->staged_min;
         r.need_lc = (scan && erasure) ? 1 : 0;
         void *ws = nullptr;
         if ((rc = scratch_get(ctx, ln, 6, (size_t)blocks * threads * lay.total * 32 + 64, &ws))) return rc;
@@ -1824,6 +1849,10 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         auto decode_list = [&](const RobustArgs &ra, unsigned int cnt_host) -> int {
             if (T.fast && !staged_direct && !ra.hist && cnt_host != UINT_MAX && cnt_host > ra.list_first && (size_t)(cnt_host - ra.list_first) >= ctx->staged_min)
                 return staged_decode(ctx, ln, T, ra, P.in_map, ra.list_first, cnt_host, blocks, threads);
+            if (dev_route && cnt_host == UINT_MAX && !ra.hist && ra.list_first == 0) {
+                ctx->dev_route_calls++;
+                return staged_decode(ctx, ln, T, ra, P.in_map, 0, (unsigned int)Bc, blocks, threads, nullptr, 0, false, 0, ra.count);
+            }
             return launch_robust(ra);
         };
         unsigned int cnt_host = UINT_MAX;

@@ -58,6 +58,9 @@ struct NttArgs {
     // MODE 2, two-sided recovery (hi_cnt > 0): besides the coefficients k < mout, the hi_cnt coefficients hi_top, hi_top-1, ... are
     // stored, at out positions mout, mout+1, ... (the top of Q = P*Zc in reversed order: P's upper half is recovered from it)
     int hi_top, hi_cnt;
+    // ntt_kernel: optional device-side bound of the batch (staged decoder without a host count): items b >= *b_dev - b_first are skipped
+    const unsigned int *b_dev;
+    unsigned int b_first;
     // ntt16x_kernel: dynamic tile queue (nullptr: static round-robin).  work[0] = tiles handed out beyond the first one of every
     // warp, work[1] = warps that have finished; the last warp to finish zeroes both, so the words are ready for the next launch
     // on the same stream.
@@ -233,7 +236,13 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
     // tile ahead of the prefetch, i.e. two ahead of the transform; a.work == nullptr: static round-robin.
     constexpr int IPW = 32 / TPI, WPC = HB_NTT_BLOCK / 32;
     const int lane = threadIdx.x & 31, item_w = lane / TPI;
-    const long long ntiles = (a.B + IPW - 1) / IPW;
+    long long Beff = a.B;
+    if (a.b_dev) {
+        const unsigned int c = *a.b_dev;
+        const long long live = c > a.b_first ? (long long)(c - a.b_first) : 0;
+        Beff = live < Beff ? live : Beff;
+    }
+    const long long ntiles = (Beff + IPW - 1) / IPW;
     const long long nwarps = (long long)gridDim.x * WPC;
     unsigned bad = 0;
 
@@ -253,7 +262,7 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
     const unsigned int never = (unsigned int)a.n + 0x7fff0000u;
     auto prefetch = [&](long long t, unsigned int gate) {
         const long long bb = t * IPW + item_w;
-        if (t < ntiles && bb < a.B && gate != never) {
+        if (t < ntiles && bb < Beff && gate != never) {
             const long long src = (MODE == 2 && a.item_list) ? (long long)a.item_list[bb] : bb;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
@@ -278,7 +287,7 @@ __global__ void __launch_bounds__(HB_NTT_BLOCK, HB_NTT_MINB) ntt_kernel(const Nt
         unsigned long long q2 = 0;
         if (a.work && lane == 0) q2 = atomicAdd(a.work, 1ull);   // the tile after `next`; consumed at the end of this iteration
         const long long b = tile * IPW + item_w;
-        const bool active = b < a.B;
+        const bool active = b < Beff;
         uint32_t x[E][8];
         // ---- pass 0: inputs from the prefetch staging (thread-private slots: no barrier), stages with half = 1, 2, 4
         cp_async_wait_all();

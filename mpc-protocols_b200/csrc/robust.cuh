@@ -78,6 +78,7 @@ struct RobustArgs {
     uint4 *ws;                  // workspace: ws_elems Fr per thread, strided by total thread count
     int ws_elems;
     unsigned int *dense_fail_flag;  // scan mode: set to 1 when some warp finds at least half of its items failing
+    unsigned int attack_min;        // list mode: dense_fail_flag is set when at least this many items are listed (0: never)
     int hist_only;              // scout pass ahead of any other stage: only the per-sender error histogram is updated
     int skip_coeffs;            // staged decoder, all N points supplied: the coefficients are corrected by a transform afterwards
 };
@@ -530,6 +531,8 @@ __device__ __forceinline__ void robust_store_item(const RobustArgs &a, long long
 __global__ void __launch_bounds__(128, HB_ROBUST_MINB) robust_kernel(const RobustArgs a) {
     fma_ballast(a.rmax < 0, a.fail_any);
     size_t cnt = a.fail_scan ? (size_t)a.B : (size_t)*a.count;
+    if (!a.fail_scan && a.dense_fail_flag && a.attack_min && cnt >= (size_t)a.attack_min && blockIdx.x == 0 && threadIdx.x == 0)
+        *(volatile unsigned int *)a.dense_fail_flag = 1u;   // list mode: a large failing set (asynchronous calls learn of the attack this way)
     if (!a.fail_scan && a.list_max && cnt > (size_t)a.list_first + a.list_max) cnt = (size_t)a.list_first + a.list_max;
     const size_t T = (size_t)gridDim.x * blockDim.x;
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -662,7 +665,18 @@ struct StagedArgs {
     unsigned char *okf;         // [W] by sorted index: the fast attempt has produced a consistent locator
     int direct;                 // the items come straight from the all-points NTT check (no dense check has looked at the examined
                                 // prefix): no error inside the prefix means the reference's optimistic attempt succeeds (path 0)
+    // device-count mode (asynchronous calls: no host decision): W is an upper bound, the slots s >= *cnt_dev - list_first are not
+    // items at all (dead from the start, never handed to the exact path); attack_flag is raised when the count is large
+    const unsigned int *cnt_dev;
+    unsigned int *attack_flag;
+    unsigned int attack_min;
 };
+__device__ __forceinline__ unsigned int staged_live(const StagedArgs &a) {
+    if (!a.cnt_dev) return a.W;
+    const unsigned int c = *a.cnt_dev;
+    const unsigned int live = c > a.list_first ? c - a.list_first : 0u;
+    return live < a.W ? live : a.W;
+}
 
 __device__ __forceinline__ void ld_fr2(uint32_t (&a)[8], const uint4 *p) { load_fr(a, p[0], p[1]); }
 __device__ __forceinline__ void st_fr2(uint4 *p, const uint32_t (&a)[8]) {
@@ -688,6 +702,16 @@ __global__ void __launch_bounds__(128, HB_BM_MINB) bm_segment_kernel(const Stage
     fma_ballast(a.syn_ld < 0, a.rootmask);
     const unsigned int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= a.W) return;
+    if (a.cnt_dev && a.j0 == 0) {
+        const unsigned int live = staged_live(a);
+        if (pos == 0 && a.attack_flag && live >= a.attack_min) *(volatile unsigned int *)a.attack_flag = 1u;
+        if (pos >= live) {   // not an item: dead from the start
+            a.stateP[0][pos] = make_int4(0, 0, 0, 1);
+            a.originP[0][pos] = pos;
+            a.keyP[pos] = (unsigned char)255;
+            return;
+        }
+    }
     const GView lam(a.lamG[0], pos, a.tp), bp(a.bpG[0], pos, a.tp), syn(a.synG[0], pos, a.syn_ld), bd(a.bdisP[0], pos, 1);
     uint32_t one[8], bdis[8];
     one_mont_limbs(one);
@@ -700,7 +724,10 @@ __global__ void __launch_bounds__(128, HB_BM_MINB) bm_segment_kernel(const Stage
         a.originP[0][pos] = pos;
     } else {
         const int4 st = a.stateP[0][pos];
-        if (st.w) return;  // dead: the fast attempt cannot succeed
+        if (st.w) {  // dead: the fast attempt cannot succeed
+            a.keyP[pos] = (unsigned char)255;   // (the key array is not permuted: keep dead positions sorted to the end)
+            return;
+        }
         L = st.x; lenB = st.y; shift = st.z;
         bd.ld(bdis, 0);
     }
@@ -981,6 +1008,7 @@ __global__ void __launch_bounds__(128, 4) staged_finish_kernel(const RobustArgs 
     const unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= s.W) return;
     const unsigned int slot = s.perm ? s.perm[idx] : idx;
+    if (s.cnt_dev && slot >= staged_live(s)) return;   // device-count mode: not an item
     const unsigned int item = a.list[s.list_first + slot];
     const long long b = (long long)item;
     const int L = s.state[slot].x;

@@ -237,3 +237,88 @@ def test_mid_size_batches_switch_to_the_staged_decoder_under_attack(hb, orc):
         assert honest1 == honest0 and after >= honest0, (honest0, after, honest1)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("n,t,S,B,ws_mb", [(16, 5, 16, 3000, None), (16, 5, 14, 2000, 1), (64, 21, 64, 1500, None), (64, 21, 50, 700, 1), (10, 3, 8, 500, None),
+                                           (128, 42, 128, 300, None)])
+def test_async_calls_take_the_staged_decoder_in_device_count_mode(hb, orc, monkeypatch, n, t, S, B, ws_mb):
+    """Asynchronous calls cannot ask the host how many items failed.  Under attack (HBMPC_ASYNC_STAGED=2 forces the state a context
+    reaches after hbmpc_ctx_synchronize has seen a large failing set) they compact the failing items and run the staged decoder with
+    the count read ON THE DEVICE by every stage (slots beyond it are dead from the start and never reach the exact path).
+    Device tensors, enqueue-only calls, status at synchronize: outcomes equal the oracle's item by item."""
+    import torch
+
+    monkeypatch.setenv("HBMPC_STAGED_MIN", "1")
+    monkeypatch.setenv("HBMPC_ASYNC_STAGED", "2")
+    monkeypatch.setenv("HBMPC_NO_SPECULATION", "1")
+    if ws_mb is not None:
+        monkeypatch.setenv("HBMPC_STAGED_WS_MB", str(ws_mb))
+    c = hb.Context(0)
+    c.set_async(True)
+    d = t
+    rng = np.random.default_rng(S * 17 + n)
+    coeffs, shares = _codewords(orc, n, d, B, 0x5EED7A00 + n + S)
+    ids = np.sort(rng.choice(n, size=S, replace=False))
+    arrival = rng.permutation(S)
+    words = shares[:, ids[arrival]]
+    nerr = np.minimum(rng.integers(0, t + 3, size=B), S)
+    nerr[::5] = 0                                       # honest items in between
+    bad = _corrupt(words, rng, nerr)
+    aid = ids[arrival]
+    want = orc.robust_interpolate_batch(aid, bad, n, d, t, threads=orc.max_threads())
+    dev = torch.device("cuda", 0)
+    tw = torch.from_numpy(np.ascontiguousarray(bad).view(np.int64)).to(dev)
+    te = tw.permute(1, 0, 2).contiguous()
+    torch.cuda.synchronize()
+    for fl in (False, True):
+        l0 = c.launch_count
+        rc, co, sec, path, flags = c.robust_interpolate_batch(aid, tw, n, d, t, want_flags=fl)
+        assert rc == 0                                   # enqueue only
+        status = c.synchronize()
+        assert c.launch_count - l0 > 12, "the staged pipeline did not run"
+        assert status == want["rc"]
+        assert np.array_equal(path.cpu().numpy(), want["path"])
+        assert np.array_equal(co.cpu().numpy().view(np.uint64), want["coeffs"]) and np.array_equal(sec.cpu().numpy().view(np.uint64), want["secrets"])
+        if fl:
+            assert np.array_equal(flags.cpu().numpy().view(np.uint64), want["flags"][:, : flags.shape[1]])
+        rc, co2, path2, _ = c.batch_recover(aid, te, n, d, t)
+        assert c.synchronize() == want["rc"]
+        assert np.array_equal(path2.cpu().numpy(), want["path"]) and np.array_equal(co2.cpu().numpy().view(np.uint64), want["coeffs"])
+    # an honest batch through the same route: nothing to decode, nothing handed to the exact path
+    tw2 = torch.from_numpy(np.ascontiguousarray(words).view(np.int64)).to(dev)
+    torch.cuda.synchronize()
+    rc, co, sec, path, _ = c.robust_interpolate_batch(aid, tw2, n, d, t)
+    assert c.synchronize() == 0 and not path.cpu().numpy().any() and np.array_equal(co.cpu().numpy().view(np.uint64), coeffs)
+    c.close()
+
+
+def test_async_context_learns_of_an_attack_at_synchronize(hb, orc, monkeypatch):
+    """without the forcing knob: the first attacked asynchronous call decodes with robust_kernel and raises the attack word; after
+    hbmpc_ctx_synchronize the next asynchronous calls take the staged decoder (many more launches), honest ones switch it off again"""
+    import torch
+
+    monkeypatch.setenv("HBMPC_STAGED_MIN", "64")
+    monkeypatch.setenv("HBMPC_NO_SPECULATION", "1")
+    c = hb.Context(0)
+    c.set_async(True)
+    n, t, d, B = 64, 21, 21, 4096
+    rng = np.random.default_rng(5)
+    coeffs, shares = _codewords(orc, n, d, B, 0x5EED7B00)
+    bad = _corrupt(shares, rng, rng.integers(1, t + 1, size=B))
+    want = orc.robust_interpolate_batch(np.arange(n), bad[:256], n, d, t, threads=orc.max_threads())
+    dev = torch.device("cuda", 0)
+    tb, tg = torch.from_numpy(bad.view(np.int64)).to(dev), torch.from_numpy(shares.view(np.int64)).to(dev)
+    torch.cuda.synchronize()
+    counts = []
+    for words in (tb, tb, tb, tg, tg, tb):
+        l0 = c.launch_count
+        rc, co, sec, path, _ = c.robust_interpolate_batch(np.arange(n), words, n, d, t)
+        assert c.synchronize() == 0
+        counts.append(c.launch_count - l0)
+        if words is tb:
+            assert np.array_equal(co[:256].cpu().numpy().view(np.uint64), want["coeffs"]) and np.array_equal(path[:256].cpu().numpy(), want["path"])
+        else:
+            assert np.array_equal(co.cpu().numpy().view(np.uint64), coeffs)
+    assert counts[0] < 12 and counts[1] > 25 and counts[2] > 25, counts      # learnt at the first synchronize
+    assert counts[4] < 12 and counts[5] < 12, counts                          # the honest call switched it off; the next attacked call pays the slow route once
+    c.close()
