@@ -324,6 +324,7 @@ struct hbmpc_ctx {
     unsigned int dev_route_calls = 0;               // asynchronous recovery calls since the last status read that took the device-count staged route
     bool async_staged = true;                       // HBMPC_ASYNC_STAGED=0: asynchronous calls never take it; 2: always, at any batch size (tests)
     bool force_async_staged = false;
+    bool no_sync_count = false;                     // HBMPC_NO_SYNC_COUNT=1: synchronous mid-size calls keep round 1's scan route (A/B runs)
     bool no_er_flags = false;                       // HBMPC_NO_ER_FLAGS=1: calls with flags on a sender subset go straight to the dense check
     bool no_fastpath = false;                       // HBMPC_NO_FASTPATH=1: K3 never takes the all-shares-present inverse-NTT path
     bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
@@ -466,6 +467,8 @@ extern "C" int hbmpc_ctx_create(int device, hbmpc_ctx **out) {
         if (sg && atoi(sg) > 0) ctx->staged_seg = atoi(sg);
         const char *as = getenv("HBMPC_ASYNC_STAGED");
         if (as) { ctx->async_staged = as[0] != '0'; if (as[0] == '2') { ctx->attack_seen = true; ctx->force_async_staged = true; } }
+        const char *nsc = getenv("HBMPC_NO_SYNC_COUNT");
+        ctx->no_sync_count = nsc && nsc[0] == '1';
         const char *stl = getenv("HBMPC_STATIC_TILES");
         ctx->static_tiles = stl && stl[0] == '1';
         const char *cm = getenv("HBMPC_CHUNK_MB");
@@ -1693,10 +1696,16 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         // asynchronous calls of a context under attack (learnt at the last hbmpc_ctx_synchronize) compact too: the staged decoder then
         // runs in device-count mode (no host decision), see staged_decode
         const bool dev_route = ctx->async && ctx->async_staged && ctx->attack_seen && T.fast && (Bc >= 2048 || ctx->force_async_staged) && !lean_phase;
-        const bool scan = Bc <= ctx->scan_max && !lean_phase && !(ctx->attack_seen && !ctx->async && Bc >= 2048) && !dev_route;
+        const bool scan_early = Bc <= ctx->scan_max && !lean_phase && !(ctx->attack_seen && !ctx->async && Bc >= 2048) && !dev_route;
+        // Synchronous calls of 2048 .. scan_max chunks: the failing items are compacted and robust_kernel is enqueued for them at once,
+        // told to do nothing when there are >= SPEC_MIN of them; the call's one synchronisation then also brings the count, and a
+        // large failing set takes the scouts / staged decoder below -- on the FIRST attacked call, at the price of one or two
+        // near-empty launches for honest ones (round 1 learnt of an attack only for the context's next calls).
+        const bool spec_small = scan_early && !ctx->async && Bc >= 2048 && T.fast && T.rmax >= 1 && !ctx->no_sync_count;
+        const bool scan = scan_early && !spec_small;
         bool staged_direct = false;
         unsigned int *dense_list = list1, *dense_count = count1;
-        if (fastN && T.fast && !ctx->async && !scan) {
+        if (fastN && T.fast && !ctx->async && !scan_early) {
             CK(cudaMemcpyAsync(ctx->h_spec, count1, sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
             CK(cudaStreamSynchronize(ln.stream));
             const unsigned int c1 = ctx->h_spec[0];
@@ -1857,9 +1866,18 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         };
         unsigned int cnt_host = UINT_MAX;
         if (!scan && !ctx->async && T.rmax >= 1) {
-            CK(cudaMemcpyAsync(ctx->h_spec, count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
+            if (spec_small) {   // enqueued before the count is known: decodes a small failing set, skips a large one, reports the count
+                RobustArgs rq = r;
+                rq.skip_above = SPEC_MIN;
+                rq.count_out = ctx->h_spec;   // pinned host memory (device-accessible under unified addressing): no copy to wait for
+                if ((rc = launch_robust(rq))) return rc;
+            } else {
+                CK(cudaMemcpyAsync(ctx->h_spec, count, sizeof(unsigned int), cudaMemcpyDeviceToHost, ln.stream));
+            }
             CK(cudaStreamSynchronize(ln.stream));
-            cnt_host = ctx->h_spec[0];
+            cnt_host = ((volatile unsigned int *)ctx->h_spec)[0];
+            if (spec_small && cnt_host < SPEC_MIN) done = true;
+            if (spec_small && cnt_host >= ctx->staged_min) ctx->attack_seen = true;   // later calls of this shape may skip the dense check
             if (Bc <= ctx->scan_max && cnt_host < ctx->staged_min / 2 && !staged_direct) ctx->attack_seen = false;  // the attack is over
         }
         if (cnt_host != UINT_MAX && !ctx->no_speculation) {

@@ -79,6 +79,10 @@ struct RobustArgs {
     int ws_elems;
     unsigned int *dense_fail_flag;  // scan mode: set to 1 when some warp finds at least half of its items failing
     unsigned int attack_min;        // list mode: dense_fail_flag is set when at least this many items are listed (0: never)
+    unsigned int *count_out;        // list mode: the number of listed items is stored here (pinned host memory: the host reads it after
+                                    // the call's synchronisation without a copy of its own)
+    unsigned int skip_above;        // list mode: do nothing when at least this many items are listed (0: no limit) -- a launch enqueued
+                                    // before the host knows the count; larger sets are decoded by the staged pipeline instead
     int hist_only;              // scout pass ahead of any other stage: only the per-sender error histogram is updated
     int skip_coeffs;            // staged decoder, all N points supplied: the coefficients are corrected by a transform afterwards
 };
@@ -531,6 +535,8 @@ __device__ __forceinline__ void robust_store_item(const RobustArgs &a, long long
 __global__ void __launch_bounds__(128, HB_ROBUST_MINB) robust_kernel(const RobustArgs a) {
     fma_ballast(a.rmax < 0, a.fail_any);
     size_t cnt = a.fail_scan ? (size_t)a.B : (size_t)*a.count;
+    if (!a.fail_scan && a.count_out && blockIdx.x == 0 && threadIdx.x == 0) *(volatile unsigned int *)a.count_out = (unsigned int)cnt;
+    if (!a.fail_scan && a.skip_above && cnt >= (size_t)a.skip_above) return;
     if (!a.fail_scan && a.dense_fail_flag && a.attack_min && cnt >= (size_t)a.attack_min && blockIdx.x == 0 && threadIdx.x == 0)
         *(volatile unsigned int *)a.dense_fail_flag = 1u;   // list mode: a large failing set (asynchronous calls learn of the attack this way)
     if (!a.fail_scan && a.list_max && cnt > (size_t)a.list_first + a.list_max) cnt = (size_t)a.list_first + a.list_max;

@@ -206,16 +206,24 @@ def test_staged_after_speculation(staged_ctx, orc):
     _check_all_entry_points(c, orc, np.arange(n), words, n, d, t)
 
 
-def test_mid_size_batches_switch_to_the_staged_decoder_under_attack(hb, orc):
-    """Batches below HBMPC_SCAN_MAX are not compacted (no host-visible failing count), so the first attacked call decodes with
-    robust_kernel; it reports the densely failing batch, and the next calls of the context count their failing items and take the
-    staged decoder, until a call finds (almost) nothing to decode.  Every call equals the oracle whatever the route."""
+@pytest.mark.parametrize("sync_count", [True, False])
+def test_mid_size_batches_switch_to_the_staged_decoder_under_attack(hb, orc, monkeypatch, sync_count):
+    """Synchronous batches of 2048 .. HBMPC_SCAN_MAX chunks.  Round 2 (sync_count): the failing items are compacted, robust_kernel is
+    enqueued for a small failing set and told to skip a large one, and the call's one synchronisation brings the count: the FIRST
+    attacked call already takes the staged decoder.  Round 1's route (HBMPC_NO_SYNC_COUNT=1): no compaction, the first attacked call
+    decodes with robust_kernel and reports the densely failing batch, the next calls of the context count their failing items, until a
+    call finds (almost) nothing to decode.  Every call equals the oracle whatever the route."""
+    if not sync_count:
+        monkeypatch.setenv("HBMPC_NO_SYNC_COUNT", "1")
     n, t, d, B = 16, 5, 5, 6000
     rng = np.random.default_rng(2024)
     coeffs, shares = _codewords(orc, n, d, B, 0x5EED7400)
     bad = _corrupt(shares, rng, rng.integers(1, t + 1, size=B))
+    few = shares.copy()
+    few[:300] = bad[:300]                      # a small failing set: decoded by the speculative robust_kernel launch
     ids = np.arange(n)
     want_bad = orc.robust_interpolate_batch(ids, bad, n, d, t, threads=orc.max_threads())
+    want_few = orc.robust_interpolate_batch(ids, few, n, d, t, threads=orc.max_threads())
     c = hb.Context(0)
     try:
         def call(words, want=None):
@@ -228,13 +236,19 @@ def test_mid_size_batches_switch_to_the_staged_decoder_under_attack(hb, orc):
                 assert rc == 0 and not path.any() and np.array_equal(co, coeffs)
             return c.launch_count - l0
         honest0 = call(shares)
-        first = call(bad, want_bad)          # scan route: robust_kernel, few launches
-        second = call(bad, want_bad)         # the context has seen the attack: compaction + staged decoder
+        small = call(few, want_few) if sync_count else 0   # (round 1's route takes 300 consecutive failing items for an attack)
+        first = call(bad, want_bad)
+        second = call(bad, want_bad)
         third = call(bad, want_bad)
-        assert second >= first + 8 and third == second, (honest0, first, second, third)
+        if sync_count:
+            assert small <= honest0 + 1 and first >= honest0 + 8 and second >= honest0 + 8 and third == second, (honest0, small, first, second, third)
+        else:
+            assert second >= first + 8 and third == second, (honest0, first, second, third)
         after = call(shares)                 # counted, nothing to decode: the attack is over
         honest1 = call(shares)
         assert honest1 == honest0 and after >= honest0, (honest0, after, honest1)
+        if sync_count:
+            assert call(few, want_few) == small
     finally:
         c.close()
 

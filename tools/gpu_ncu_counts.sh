@@ -21,7 +21,7 @@ python tools/ncu_exec_counts.py /tmp/src_dense_$TAG.csv --items 1048576 --json g
 # K4: every kernel of ONE robust_interpolate_batch call (n=128, t=42, 2^17 codewords, e~U{0..42}); the call is bracketed by
 # cudaProfilerStart/Stop in tools/ncu_ntt.py
 python tools/ncu_ntt.py --what k4 --log2 17 --reps 2 > gpurun_out/ncu_plain_k4_$TAG.log 2>&1 && \
-ncu $SEC --clock-control none --import-source on --profile-from-start off -o /tmp/k4_$TAG python tools/ncu_ntt.py --what k4 --log2 17 --reps 2 > gpurun_out/ncu_k4_$TAG.log 2>&1
+ncu $SEC --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --import-source on --profile-from-start off -o /tmp/k4_$TAG python tools/ncu_ntt.py --what k4 --log2 17 --reps 2 > gpurun_out/ncu_k4_$TAG.log 2>&1
 ncu -i /tmp/k4_$TAG.ncu-rep --page raw --csv > /tmp/raw_k4_$TAG.csv 2>/dev/null
 python tools/ncu_summary.py /tmp/raw_k4_$TAG.csv gpurun_out/raw_k4_summary_$TAG.json > /dev/null 2>&1
 python - /tmp/raw_k4_$TAG.csv gpurun_out/k4_traffic_$TAG.json <<'PYEOF'
