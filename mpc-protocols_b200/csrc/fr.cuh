@@ -224,8 +224,12 @@ HB_DEV void mod_limbs(uint32_t (&r)[8]) {
     r[0] = HB_R0; r[1] = HB_R1; r[2] = HB_R2; r[3] = HB_R3; r[4] = HB_R4; r[5] = HB_R5; r[6] = HB_R6; r[7] = HB_R7;
 }
 
-// x >= r ?
+// x >= r ?   The top limb decides in all but one case in 2^31 for values that are uniform below r (x_7 < r_7: no; x_7 > r_7: yes);
+// only x_7 == r_7 needs the full-width comparison (one compare instead of an 8-limb borrow chain per validated input).
 HB_DEV bool geq_mod(const uint32_t (&x)[8]) {
+#if defined(__CUDA_ARCH__)
+    if (x[7] != HB_R7) return x[7] > HB_R7;
+#endif
     uint32_t r[8], d[8];
     mod_limbs(r);
     return sub8(d, x, r) == 0;
