@@ -328,7 +328,7 @@ struct hbmpc_ctx {
     bool no_er_flags = false;                       // HBMPC_NO_ER_FLAGS=1: calls with flags on a sender subset go straight to the dense check
     bool no_fastpath = false;                       // HBMPC_NO_FASTPATH=1: K3 never takes the all-shares-present inverse-NTT path
     bool force_dense = false;                       // HBMPC_FORCE_DENSE=1: K1/K2 through the dense matvec kernel
-    size_t chunk_bytes = 64u << 20;                 // HBMPC_CHUNK_MB: target bytes per pipelined host copy (measured: 16 MB 75.3, 64 MB 71.7, 128 MB 69.5 ms per e2e step)
+    size_t chunk_bytes = 128u << 20;                // HBMPC_CHUNK_MB: target bytes per pipelined host copy (measured, e2e step of bench.py: 16 MB 75.3, 64 MB 71.8, 128 MB 67.6, 256 MB 67.6 ms)
     // status words in mapped pinned host memory (device view d_status, host view h_status): kernels store 1 on the rare
     // error, the host reads them after a stream synchronize -- no copy, no memset on the call path
     unsigned int *d_status = nullptr;  // [0] non-canonical input seen, [2] some item failed to decode
