@@ -52,8 +52,8 @@ __host__ __device__ constexpr int ntt16x_minb() { return ntt16x_logs<LOGN>() == 
 
 template <int LOGN, int MODE>
 inline size_t ntt16x_smem_bytes() {
-    constexpr int N = 1 << LOGN, S = 1 << ntt16x_logs<LOGN>();
-    return (size_t)((N / 2) * 2 + (MODE == 2 ? N * 2 : 0) + NTT16X_WARPS * S * 2 * 32) * 16 + 16;
+    constexpr int N = 1 << LOGN, S = 1 << ntt16x_logs<LOGN>(), L = N / S;
+    return (size_t)((N / 2) * 2 + (L - 1) * S * 2 + (MODE == 2 ? N * 2 : 0) + NTT16X_WARPS * S * 2 * 32) * 16 + 16;
 }
 
 // ---- shared-memory accesses by 32-bit window address (the butterfly routines are real calls: generic pointers would turn
@@ -187,16 +187,25 @@ __global__ void __launch_bounds__(NTT16X_WARPS * 32, ntt16x_minb<LOGN>()) ntt16x
     constexpr int BFL = (L / 2) / HALVES;                             // P1: butterflies per lane and stage
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4 *sTw = reinterpret_cast<uint4 *>(smem_raw);                 // [N/2][2]  w^k (w^-k for the inverse), Montgomery form
-    uint4 *sWt = sTw + N;                                             // [N][2]    MODE 2: weights by domain index
+    // P1's twiddles depend on the lane's row q: in sTw the entries of one (stage, lo) for q = 0 .. S-1 lie 32 << (LL-1-s2) bytes
+    // apart -- the same bank group for every lane in the early stages (ncu: 16.7 wavefronts per LDS.128, 2/3 of the kernel's
+    // excess shared-memory wavefronts).  sTw1 holds them contiguous in q: block (2^s2 - 1 + lo) of S entries.
+    uint4 *sTw1 = sTw + N;                                            // [(L-1)*S][2]
+    uint4 *sWt = sTw1 + (L - 1) * S * 2;                              // [N][2]    MODE 2: weights by domain index
     uint4 *sD = sWt + (MODE == 2 ? 2 * N : 0);                        // [warps][S rows][2 halves][32 columns]
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int i = t; i < N; i += blockDim.x) sTw[i] = a.tw[i];
+    for (int i = t; i < (L - 1) * S * 2; i += blockDim.x) {
+        const int half = i & 1, e = i >> 1, q = e & (S - 1), blk = e >> LOGS;          // blk = 2^s2 - 1 + lo
+        const int s2 = 31 - __clz(blk + 1), lo = blk + 1 - (1 << s2);
+        sTw1[i] = a.tw[(((S * lo + q) << (LL - 1 - s2)) << 1) + half];
+    }
     if (MODE == 2)
         for (int i = t; i < 2 * N; i += blockDim.x) sWt[i] = a.wt[i];
     __syncthreads();
     uint4 *D = sD + (size_t)warp * (S * 2 * 32);
     const unsigned dD = (unsigned)__cvta_generic_to_shared(D), dTw = (unsigned)__cvta_generic_to_shared(sTw),
-                   dWt = (unsigned)__cvta_generic_to_shared(sWt);
+                   dTw1 = (unsigned)__cvta_generic_to_shared(sTw1), dWt = (unsigned)__cvta_generic_to_shared(sWt);
     const int j = lane & (L - 1), item = lane >> LL;
     const int cj = (LL == 0) ? 0 : (int)(__brev((unsigned)j) >> (32 - (LL == 0 ? 1 : LL)));   // residue class of this lane's inputs
     const int cols = a.cols < N ? a.cols : N;
@@ -295,12 +304,13 @@ __global__ void __launch_bounds__(NTT16X_WARPS * 32, ntt16x_minb<LOGN>()) ntt16x
                         const int bf = hf * BFL + bfi;
                         const int hb2 = 1 << s2, lo = bf & (hb2 - 1), bu = ((bf >> s2) << (s2 + 1)) | lo;
                         const unsigned pu = slot(q, item * L + bu), pv = slot(q, item * L + bu + hb2);
-                        const int twi = (S * lo + q) << (LL - 1 - s2);   // w_N^((pos mod h) * N/(2h)), h = S*2^s2
+                        // twiddle w_N^((pos mod h) * N/(2h)), h = S*2^s2: index (S*lo + q) << (LL-1-s2) of sTw = entry q of block 2^s2 - 1 + lo of sTw1
+                        const unsigned ptw = dTw1 + (unsigned)((((hb2 - 1 + lo) << LOGS) + q) * 32);
                         if (s2 == LL - 1) {
-                            const unsigned r = bf_emit<LOGN, MODE>(pu, pv, dTw + twi * 32, 1, outb, a.out_sr, S * bu + q, S * bu + q + S * hb2, l0, l1);
+                            const unsigned r = bf_emit<LOGN, MODE>(pu, pv, ptw, 1, outb, a.out_sr, S * bu + q, S * bu + q + S * hb2, l0, l1);
                             if (active) rcs |= r;
                         } else {
-                            bf_mul(pu, pv, dTw + twi * 32, 0u);   // tw[0] is the Montgomery form of 1: the q = 0 row multiplies like the others
+                            bf_mul(pu, pv, ptw, 0u);   // tw[0] is the Montgomery form of 1: the q = 0 row multiplies like the others
                         }
                     }
                     if (HALVES > 1 && s2 + 1 < LL) __syncwarp();   // the next stage pairs columns written by the row's other lane(s)
