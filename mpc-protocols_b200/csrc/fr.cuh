@@ -627,6 +627,19 @@ __device__ __forceinline__ void fma_ballast(bool never, unsigned int *sink) {
 }
 #endif
 
+#if defined(__CUDACC__)
+// fail[b] = 1, and -- exactly once per item, whichever thread gets there first -- b is appended to list[(*count)++] (list may be
+// nullptr).  The checking kernels build the list of failing items themselves: no compaction pass over fail[] on the call path.
+// (fail buffers are zero-filled and padded to a multiple of 4 bytes by the host side.)
+__device__ __forceinline__ void mark_fail(unsigned char *fail, long long b, unsigned int *list, unsigned int *count) {
+    const unsigned long long addr = (unsigned long long)(fail + b);
+    unsigned int *w = reinterpret_cast<unsigned int *>(addr & ~3ull);
+    const unsigned int bit = 1u << (8u * (unsigned int)(addr & 3ull));
+    const unsigned int old = atomicOr(w, bit);
+    if (!(old & bit) && list) list[atomicAdd(count, 1u)] = (unsigned int)b;
+}
+#endif
+
 // R^2 mod r (to Montgomery form: mont_mul(x, R2)); 1 (from Montgomery form: mont_mul(x, 1))
 HB_DEV void r2_limbs(uint32_t (&r)[8]) {
     r[0] = 0xf3f29c6du; r[1] = 0xc999e990u; r[2] = 0x87925c23u; r[3] = 0x2b6cedcbu;

@@ -1659,11 +1659,9 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             na.m = (int)m;
             na.mout = T.mout;
             na.fail = fail1;
+            na.fail_list = list1; na.fail_count = count1;   // the check lists its failing items itself (no compaction launch)
             na.path = (int *)vp.dev;
             if ((rc = launch_ntt<1>(ctx, ln.stream, T.fast_logn, na))) return rc;
-            compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail1, (long long)Bc, list1, count1);
-            ctx->launches++;
-            CK(cudaGetLastError());
         }
 
         // decoder arguments (shared by the staged decoder and robust_kernel)
@@ -1767,6 +1765,8 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             na.hi_top = T.er_hi_top;
             na.hi_cnt = T.er_h2;
             na.fail = er_all ? fail1 : fail;
+            na.fail_list = er_all ? list1 : (scan ? nullptr : list);     // the check lists its failing items itself
+            na.fail_count = er_all ? count1 : (scan ? nullptr : count);
             na.path = (int *)vp.dev;
             if ((rc = launch_ntt<2>(ctx, ln.stream, T.er_logn, na))) return rc;
             MatvecArgs tr{};
@@ -1781,11 +1781,7 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
             tr.row_len = T.er_row_len;
             tr.row_start = T.er_row_start;
             if ((rc = launch_matvec(ctx, ln, tr, 0))) return rc;
-            if (er_all) {  // like the all-points check: only the chunks it rejects see the dense check (which sets the flags)
-                compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail1, (long long)Bc, list1, count1);
-                ctx->launches++;
-                CK(cudaGetLastError());
-            }
+            // (er_all: like the all-points check, only the chunks it rejects -- listed in list1 -- see the dense check, which sets the flags)
         }
         MatvecArgs a{};
         if (fastN || er_all) { a.item_list = dense_list; a.item_count = dense_count; }
@@ -1804,14 +1800,9 @@ static int recover_impl(hbmpc_ctx *ctx, size_t n, size_t d, size_t t, size_t S, 
         a.n_gate = T.n_gate;
         a.chk_map = P.chk_map;
         a.fail = fail;
+        if (!scan) { a.fail_list = list; a.fail_count = count; }   // list mode: the check appends its failing items (no compaction launch)
         a.flags = want_flags ? (unsigned long long *)vf.dev : nullptr;
         if (!erasure && (rc = launch_matvec(ctx, ln, a, fw))) return rc;
-
-        if (!scan) {
-            compact_kernel<<<ctx->num_sms * 4, 256, 0, ln.stream>>>(fail, (long long)Bc, list, count);
-            ctx->launches++;
-            CK(cudaGetLastError());
-        }
         if (erasure && !lean_phase && !scan) {
             // the robust decoder corrects Lc*y[lowest d+1] by linearity: provide it for the failing items
             MatvecArgs lc{};

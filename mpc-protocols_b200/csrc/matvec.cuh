@@ -35,7 +35,8 @@ struct MatvecArgs {
     const int *col_map;                     // [C] input index of column c, or nullptr (identity)
     int n_chk, n_gate;
     const int *chk_map;        // [n_chk] input index checked by check row r (< 0: compare with zero)
-    unsigned char *fail;       // [B] set to 1 when a gate row mismatches (may be nullptr when n_gate == 0)
+    unsigned char *fail;       // [B] set to 1 when a gate row mismatches (may be nullptr when n_gate == 0) ...
+    unsigned int *fail_list, *fail_count;   // ... and the item is appended to fail_list[(*fail_count)++] (optional)
     unsigned long long *flags; // [B][flag_words] or nullptr
     int flag_words;
     unsigned int *err;         // device word: bit0 set when a non-canonical (>= r) input is seen
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
                 long long b = b0 + i;
                 if (b < NB) {
                     if (a.item_list) b = a.item_list[b];
-                    if (a.fail && sFail[i]) a.fail[b] = 1;  // slices only ever raise the flag (buffer pre-zeroed by the host side)
+                    if (a.fail && sFail[i]) mark_fail(a.fail, b, a.fail_list, a.fail_count);  // slices only ever raise the flag (buffer pre-zeroed by the host side)
                     if (a.flags)
                         for (int w = 0; w < a.flag_words; ++w) {
                             unsigned long long f = sFlags[(size_t)i * a.flag_words + w];
@@ -223,7 +224,7 @@ __global__ void matvec_combine_kernel(const MatvecArgs a, const uint4 *T1, const
                 load_fr(w, ldg_stream(p), ldg_stream(p + 1));
             }
             if (!fr_eq(v, w)) {
-                if (r < a.n_gate && a.fail) a.fail[b] = 1;
+                if (r < a.n_gate && a.fail) mark_fail(a.fail, b, a.fail_list, a.fail_count);
                 if (a.flags && chk_j >= 0) atomicOr(&a.flags[b * a.flag_words + (chk_j >> 6)], 1ull << (chk_j & 63));
             }
         } else {

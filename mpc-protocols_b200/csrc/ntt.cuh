@@ -38,7 +38,8 @@ struct NttArgs {
     const int *in_map;     // domain index j -> record index of the share with id j (nullptr: identity)
     const uint4 *scale;    // N^{-1} in Montgomery form (unused by the kernels since the scaling is a shift: fr_div_pow2)
     int m, mout;           // coefficients k < mout are stored (scaled), coefficients k >= m must vanish
-    unsigned char *fail;   // fail[b] = 1 when some coefficient k >= m is non-zero
+    unsigned char *fail;   // fail[b] = 1 when some coefficient k >= m is non-zero ...
+    unsigned int *fail_list, *fail_count;   // ... and b is appended to fail_list[(*fail_count)++] (optional)
     // MODE 2 (inverse transform of an erasure-weighted word, the general optimistic check of K3): the share with id k is
     // multiplied by wt[k] = Zc(w^k) (Zc = product over the ids outside the examined set; Montgomery form) while it is
     // loaded, ids outside the examined set contribute zero (in_map[k] < 0); outputs are left unscaled.
@@ -202,7 +203,7 @@ __device__ __forceinline__ void ntt_emit(const NttArgs &a, long long b, int pos,
                 stg_stream(o + 1, make_uint4(c[4], c[5], c[6], c[7]));
             }
         } else if (pos >= a.m) {
-            if (!fr_is_zero(v)) a.fail[b] = 1;
+            if (!fr_is_zero(v)) mark_fail(a.fail, b, a.fail_list, a.fail_count);
         } else if (MODE == 2 && pos <= a.hi_top && pos > a.hi_top - a.hi_cnt) {
             uint4 *o = a.out + (b * a.out_sb + (long long)(a.mout + a.hi_top - pos) * a.out_sr) * 2;
             stg_stream(o, make_uint4(v[0], v[1], v[2], v[3]));

@@ -318,7 +318,11 @@ __global__ void __launch_bounds__(NTT16X_WARPS * 32, ntt16x_minb<LOGN>()) ntt16x
             }
         }
         bad |= rcs & 1u;
-        if (MODE != 0 && (rcs & 2u) && active) a.fail[b] = 1;
+        if (MODE != 0) {   // one lane per failing item raises the flag and appends the item to the list
+            const unsigned fm = __ballot_sync(0xffffffffu, (rcs & 2u) && active);
+            const unsigned grp = (L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << (item * L);
+            if ((fm & grp) && j == 0) mark_fail(a.fail, b, a.fail_list, a.fail_count);
+        }
         __syncwarp();   // the rows are reloaded by other lanes' columns in the next tile
         tile = a.work ? nwarps + (long long)__shfl_sync(0xffffffffu, nxt, 0) : tile + nwarps;
     }
