@@ -5,6 +5,7 @@ runs hbmpc_robust_interpolate_batch / hbmpc_batch_recover through
   (a) the staged decoder (production thresholds, synchronous call),
   (b) the staged decoder with tiny waves and the direct mode switched off,
   (c) robust_kernel alone (HBMPC_STAGED_MIN huge),
+  (d) asynchronous (enqueue-only) calls through the staged decoder in device-count mode (HBMPC_ASYNC_STAGED=2), status at synchronize,
 and requires identical return codes, coefficients, secrets, paths and flags.  The decoded polynomials are also checked against
 the ground truth wherever the number of errors is decodable.
    python tools/soak_k4.py [--seconds 120] [--seed 1]"""
@@ -39,7 +40,9 @@ def main():
     base = {"HBMPC_SCAN_MAX": "0"}
     ctxs = {"staged": make_ctx(hb, {**base}),
             "staged_small_waves_no_direct": make_ctx(hb, {**base, "HBMPC_STAGED_MIN": "1", "HBMPC_STAGED_WS_MB": "64", "HBMPC_NO_STAGED_DIRECT": "1", "HBMPC_STAGED_SEG": "5"}),
-            "per_thread": make_ctx(hb, {**base, "HBMPC_STAGED_MIN": str(1 << 40)})}
+            "per_thread": make_ctx(hb, {**base, "HBMPC_STAGED_MIN": str(1 << 40)}),
+            "async_device_count": make_ctx(hb, {"HBMPC_ASYNC_STAGED": "2", "HBMPC_STAGED_WS_MB": "256"})}
+    ctxs["async_device_count"].set_async(True)
     rng = np.random.default_rng(a.seed)
     g = torch.Generator(device=dev)
     g.manual_seed(a.seed)
@@ -92,7 +95,11 @@ def main():
         for name, c in ctxs.items():
             for fl in (True, False):
                 rc, co, sec, path, flags = c.robust_interpolate_batch(ids_arr, words, n, d, t, want_flags=fl)
+                if name == "async_device_count":
+                    rc = c.synchronize()
                 rb = c.batch_recover(ids_arr, evals, n, d, t, want_flags=fl)
+                if name == "async_device_count":
+                    rb = (c.synchronize(),) + tuple(rb[1:])
                 outs[(name, fl)] = (rc, co, sec, path, flags, rb)
         ref = outs[("per_thread", True)]
         for (name, fl), o in outs.items():
@@ -113,7 +120,7 @@ def main():
         items += B
     for c in ctxs.values():
         c.close()
-    print(f"soak ok: {rounds} rounds, {items} codewords x 3 routes x 4 calls, {time.time() - t0:.0f} s")
+    print(f"soak ok: {rounds} rounds, {items} codewords x 4 routes x 4 calls, {time.time() - t0:.0f} s")
 
 
 if __name__ == "__main__":
