@@ -286,10 +286,39 @@ HB_DEV void cond_sub_mod(uint32_t (&x)[8]) {
     if (x[7] == HB_R7) cond_sub_mod_slow(x);
 #endif
 }
-HB_DEV void fr_add(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
-    add8(d, a, b);  // a,b < r < 2^255: no carry out
-    cond_sub_mod(d);
+// EXACT = true: branch-free variant (full-width borrow chain + selects, no rare path).  A few more ALU instructions, no branch and no
+// convergence barrier: slower in the transforms (9.53 against 9.42 ms per 2^22, their lanes run in lockstep anyway), faster in the
+// decoder's one-thread-per-codeword kernels, whose lanes diverge (Berlekamp-Massey: +4.5 % on the n = 128 leg).  robust.cuh selects it.
+template <bool EXACT>
+HB_DEV void cond_sub_mod_t(uint32_t (&x)[8]) {
+#if defined(__CUDA_ARCH__)
+    if (EXACT) {
+        uint32_t d[8], br;
+        asm("sub.cc.u32 %0, %9, " HB_PR0 ";\n\t"
+            "subc.cc.u32 %1, %10, " HB_PR1 ";\n\t"
+            "subc.cc.u32 %2, %11, " HB_PR2 ";\n\t"
+            "subc.cc.u32 %3, %12, " HB_PR3 ";\n\t"
+            "subc.cc.u32 %4, %13, " HB_PR4 ";\n\t"
+            "subc.cc.u32 %5, %14, " HB_PR5 ";\n\t"
+            "subc.cc.u32 %6, %15, " HB_PR6 ";\n\t"
+            "subc.cc.u32 %7, %16, " HB_PR7 ";\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(br)
+            : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]));
+        const bool ge = br == 0;   // no borrow: x >= r
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = ge ? d[i] : x[i];
+        return;
+    }
+#endif
+    cond_sub_mod(x);
 }
+template <bool EXACT>
+HB_DEV void fr_add_t(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    add8(d, a, b);  // a,b < r < 2^255: no carry out
+    cond_sub_mod_t<EXACT>(d);
+}
+HB_DEV void fr_add(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { fr_add_t<false>(d, a, b); }
 // a, b < r < 2^255: the 256-bit difference is negative exactly when its top bit is set (no borrow capture needed)
 HB_DEV void fr_sub(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
 #if defined(__CUDA_ARCH__)
@@ -343,7 +372,8 @@ HB_DEV bool fr_is_zero(const uint32_t (&a)[8]) {
 // acc_reduce: out = (sum of accumulated products) * R^{-1} mod r, fully reduced (< r).
 // Valid for up to 256 accumulated products of factors < r (T < 2^518).
 // ----------------------------------------------------------------------------------------------
-HB_DEV void acc_reduce(const acc_t &A, uint32_t (&out)[8]) {
+template <bool EXACT>
+HB_DEV void acc_reduce_t(const acc_t &A, uint32_t (&out)[8]) {
     uint32_t T[17];
     uint32_t AE[16], AO[16];  // 32-bit views: AE[p] / AO[p] = limb at position p
 #pragma unroll
@@ -403,8 +433,9 @@ HB_DEV void acc_reduce(const acc_t &A, uint32_t (&out)[8]) {
     }
     // U - q*r < 2r < 2^256: arithmetic mod 2^256 is exact
     sub8(out, U, P);
-    cond_sub_mod(out);
+    cond_sub_mod_t<EXACT>(out);
 }
+HB_DEV void acc_reduce(const acc_t &A, uint32_t (&out)[8]) { acc_reduce_t<false>(A, out); }
 
 // Montgomery product through the lazy accumulator (kept for the unit test of acc_mac / acc_reduce)
 HB_DEV void mont_mul_acc(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
@@ -519,7 +550,8 @@ HB_DEV void cios_row(unsigned long long &e0, unsigned long long &e1, unsigned lo
 #endif
 }
 
-HB_DEV void mont_mul(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+template <bool EXACT>
+HB_DEV void mont_mul_t(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
     // row 0 is the general row on a zero accumulator (ptxas folds the zero addends into plain IMAD.WIDE): 14 wide multiply-adds.
     // (A hand-specialised row 0 -- products first, then m*r over 32-bit views -- was lowered to 8 IMAD.HI + 6 IMAD.X pairs.)
     unsigned long long E[4] = {0ull, 0ull, 0ull, 0ull}, O[4] = {0ull, 0ull, 0ull, 0ull};
@@ -538,10 +570,11 @@ HB_DEV void mont_mul(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&
 #pragma unroll
     for (int j = 0; j < 4; ++j) { y[2 * j] = (uint32_t)O[j]; y[2 * j + 1] = (uint32_t)(O[j] >> 32); }
     add8(sres, x, y);
-    cond_sub_mod(sres);
+    cond_sub_mod_t<EXACT>(sres);
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = sres[i];
 }
+HB_DEV void mont_mul(uint32_t (&d)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) { mont_mul_t<false>(d, a, b); }
 
 // Two independent products with their rows issued alternately: twice the independent carry chains in flight per thread (a warp
 // issues one IMAD.WIDE of a single chain every ~8 cycles; the multiplier pipe accepts one every ~4).  Bit-identical to two mont_mul.

@@ -71,21 +71,20 @@ __device__ __forceinline__ void lds_tw(uint32_t (&w)[8], unsigned addr) {   // t
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(addr));
 }
 
-// ---- out-of-line butterflies on tile addresses.  Return value: 1 when a non-canonical (>= r) input was seen (chk != 0).
+// ---- out-of-line butterflies on tile addresses.  Return value (bf_add / bf_copy / bf_scale): 1 when a non-canonical (>= r) input was
+// seen (chk != 0).  Values are validated where they are first touched: stage 0, whose twiddles are all trivial, so the product
+// routine itself never checks and returns nothing.
 // (u, v) <- (u + w*v, u - w*v)
-__device__ __noinline__ unsigned bf_mul(unsigned pu, unsigned pv, unsigned pw, unsigned chk) {
+__device__ __noinline__ void bf_mul(unsigned pu, unsigned pv, unsigned pw) {
     uint32_t u[8], v[8], w[8], t[8], sm[8], df[8];
     lds_fr(v, pv);
     lds_tw(w, pw);
     lds_fr(u, pu);
-    unsigned bad = 0;
-    if (chk) bad = (geq_mod(u) || geq_mod(v)) ? 1u : 0u;
     mont_mul(t, v, w);
     fr_add(sm, u, t);
     fr_sub(df, u, t);
     sts_fr(pu, sm);
     sts_fr(pv, df);
-    return bad;
 }
 // (u, v) <- (u + v, u - v)   (trivial twiddle)
 __device__ __noinline__ unsigned bf_add(unsigned pu, unsigned pv, unsigned chk) {
@@ -278,7 +277,7 @@ __global__ void __launch_bounds__(NTT16X_WARPS * 32, ntt16x_minb<LOGN>()) ntt16x
                 } else if (!nv) {
                     rcs |= bf_copy(pu, pv, chk);
                 } else if (twi != 0) {
-                    rcs |= bf_mul(pu, pv, dTw + twi * 32, chk);
+                    bf_mul(pu, pv, dTw + twi * 32);   // (never in stage 0: nothing to validate here)
                 } else {
                     rcs |= bf_add(pu, pv, chk);
                 }
@@ -310,7 +309,7 @@ __global__ void __launch_bounds__(NTT16X_WARPS * 32, ntt16x_minb<LOGN>()) ntt16x
                             const unsigned r = bf_emit<LOGN, MODE>(pu, pv, ptw, 1, outb, a.out_sr, S * bu + q, S * bu + q + S * hb2, l0, l1);
                             if (active) rcs |= r;
                         } else {
-                            bf_mul(pu, pv, ptw, 0u);   // tw[0] is the Montgomery form of 1: the q = 0 row multiplies like the others
+                            bf_mul(pu, pv, ptw);   // tw[0] is the Montgomery form of 1: the q = 0 row multiplies like the others
                         }
                     }
                     if (HALVES > 1 && s2 + 1 < LL) __syncwarp();   // the next stage pairs columns written by the row's other lane(s)
