@@ -372,7 +372,7 @@ def leg_c5(torch, hb, ctx, stream, dev, cm, log2, rank):
     recv = random_fr_device(torch, (cols_rs, n), seed + 4, dev); mix = E(cols_rs, n)           # shares received from the n dealers
     recv_d, mix_d, mix_d2 = random_fr_device(torch, (cols_ds, n), seed + 5, dev), E(cols_ds, n), E(cols_ds, n)
     aS, bS, r2S, rtS = (random_fr_device(torch, (T,), seed + s, dev) for s in (6, 7, 8, 9))    # own shares of a, b, r_2t, r_t
-    prod, masked, cS = E(T), E(T), E(T)
+    masked, cS = E(T), E(T)
     grp = random_fr_device(torch, (groups, 2 * t + 1), seed + 10, dev)                          # opened values a*b - r per group
     y_enc = E(n, groups)
     y_all = E(groups, n)
@@ -390,7 +390,7 @@ def leg_c5(torch, hb, ctx, stream, dev, cm, log2, rank):
         "randousha_mix (2x K2 64x64 per column)": lambda: (ctx.apply_vandermonde_batch(recv_d, n, out=mix_d), ctx.apply_vandermonde_batch(sh_d2, n, out=mix_d2)),
         "randousha_check (NonRobust recover deg t and 2t, all n shares)": lambda: (ctx.nonrobust_recover_batch(ids, sh_d, n, t, out=(chk_co, chk_sec, chk_st)),
                                                                                  ctx.nonrobust_recover_batch(ids, sh_d2, n, 2 * t, out=(chk_co2, chk_sec2, chk_st2))),
-        "triple_mask (K5: a*b - r_2t per triple)": lambda: (ctx.elementwise(2, aS, bS, out=prod), ctx.elementwise(1, prod, r2S, out=masked)),
+        "triple_mask (K5 fused: a*b - r_2t per triple, one pass)": lambda: ctx.share_algebra_fused(0, (aS, bS, r2S), out=masked),
         "triple_open_encode (K2 64x43 per group, recipient-major)": lambda: ctx.apply_vandermonde_batch(grp, n, recipient_major=True, out=y_enc),
         "triple_open_round1 (batch_recover_secrets d=2t, 64 senders)": lambda: ctx.batch_recover_secrets(ids, y_sm, n, 2 * t, t, out=(sec1, p1)),
         "triple_open_round2 (batch_recover d=2t, 64 senders)": lambda: ctx.batch_recover(ids, y_sm, n, 2 * t, t, out=(co2, p2, None)),

@@ -121,6 +121,16 @@ int hbmpc_nonrobust_recover_batch(hbmpc_ctx *ctx, size_t n, size_t deg, size_t S
  * multiplication.rs:79-97,417-426): out[i] = a[i] (op) b[i], op: 0 add, 1 sub, 2 mul (share_mul / Mul<F>). */
 int hbmpc_elementwise(hbmpc_ctx *ctx, int op, size_t count, const uint64_t *a, const uint64_t *b, uint64_t *out);
 
+/* K5 fused.  The share algebra of one protocol step in ONE pass over HBM; every array holds `count` canonical
+ * values (host or device pointers, like every other call); results are bit-identical to the operator-by-operator route above.
+ *   HBMPC_K5_TRIPLE_MASK      in = {a, b, r_2t}                  out = {a*b - r_2t}                triple_generation.rs:332-340
+ *   HBMPC_K5_BEAVER_MASK      in = {a, x, b, y}                  out = {a - x, b - y}              multiplication.rs:417-426
+ *   HBMPC_K5_BEAVER_FINALIZE  in = {c, x, y, a-x (open), b-y (open)}
+ *                             out = {c - (a-x)(b-y) - (a-x)*y - (b-y)*x}                           multiplication.rs:79-97
+ * An output may alias an input.  A non-canonical input value -> HBMPC_INVALID_INPUT. */
+enum { HBMPC_K5_TRIPLE_MASK = 0, HBMPC_K5_BEAVER_MASK = 1, HBMPC_K5_BEAVER_FINALIZE = 2 };
+int hbmpc_share_algebra_fused(hbmpc_ctx *ctx, int op, size_t count, const uint64_t *const *in, uint64_t *const *out);
+
 /* N1 (wire format).  ark-serialize writes a ShamirShare<F,1,_> record as 32-byte LE canonical value + u64 id + u64 degree
  * (48 bytes; Vec<RobustShare> payloads of share_gen.rs:255-268, ran_dou_sha/messages.rs:40-46).  These helpers split such
  * records into the value array the kernels consume (ids / degrees optional, may be NULL) and build records from values

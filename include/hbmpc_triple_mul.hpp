@@ -8,7 +8,8 @@
 //                                                          reconstruct_rbc :101-140, finalize_mul :57-99
 //   mpc/src/honeybadger/triple_gen/mod.rs, mul/mod.rs      ShamirBeaverTriple, error variants
 // Names, thresholds and error behaviour follow the reference; what changes is where the share algebra runs: every elementwise
-// operation on share vectors (share_mul, Sub, Add, Mul<F>: common/mod.rs:167-300) is ONE hbmpc_elementwise call per vector (K5), the
+// operation on share vectors (share_mul, Sub, Add, Mul<F>: common/mod.rs:167-300) runs on the device (K5) -- the three multi-operator
+// steps (a*b - r_2t; a-x and b-y; the Beaver product share) as ONE hbmpc_share_algebra_fused pass each, the rest as hbmpc_elementwise --, the
 // openings are the BatchReconNode mirror (one device call per message), the reconstruction of the remainder values one
 // hbmpc_robust_interpolate_batch call.  No field arithmetic happens in this header; there is no CPU fallback.  Reliable broadcast
 // (Avid / Bracha) is host control flow and out of scope: `Rbc` below is the interface the mirror needs from it (deliver the same bytes
@@ -39,6 +40,21 @@ inline std::vector<U256> elementwise(Context &ctx, int op, const std::vector<U25
     std::vector<U256> out(a.size());
     if (a.empty()) return out;
     check(hbmpc_elementwise(ctx.get(), op, a.size(), a[0].data(), b[0].data(), out[0].data()));
+    return out;
+}
+// K5 fused (hbmpc_share_algebra_fused): the algebra of one protocol step in one pass; `in` holds 3 | 4 | 5 vectors of equal length
+inline std::vector<std::vector<U256>> fused(Context &ctx, int op, const std::vector<const std::vector<U256> *> &in) {
+    const size_t count = in[0]->size(), nout = op == HBMPC_K5_BEAVER_MASK ? 2 : 1;
+    std::vector<std::vector<U256>> out(nout, std::vector<U256>(count));
+    if (count == 0) return out;
+    const uint64_t *pi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint64_t *po[2] = {nullptr, nullptr};
+    for (size_t k = 0; k < in.size(); ++k) {
+        if (in[k]->size() != count) throw ShareError(HBMPC_INVALID_INPUT);
+        pi[k] = (*in[k])[0].data();
+    }
+    for (size_t k = 0; k < nout; ++k) po[k] = out[k][0].data();
+    check(hbmpc_share_algebra_fused(ctx.get(), op, count, pi, po));
     return out;
 }
 inline std::vector<U256> values(const std::vector<Share> &s) {
@@ -87,10 +103,11 @@ class TripleGenNode {
             // share_mul: ids must match, degrees add (common/mod.rs:280-300); then Sub with the degree-2t share
             for (size_t i = 0; i < random_shares_a.size(); ++i)
                 if (random_shares_a[i].id != random_shares_b[i].id) throw ShareError(HBMPC_ID_MISMATCH);
-            std::vector<Share> prod = detail::with_values(random_shares_a, detail::elementwise(ctx_, 2, detail::values(random_shares_a), detail::values(random_shares_b)), 0);
+            std::vector<Share> prod = random_shares_a;   // shape of the product share: same ids, degrees added (the values come below)
             for (size_t i = 0; i < prod.size(); ++i) prod[i].degree = random_shares_a[i].degree + random_shares_b[i].degree;
             detail::same_shape(prod, r2t);
-            sub = detail::with_values(prod, detail::elementwise(ctx_, 1, detail::values(prod), detail::values(r2t)));
+            const std::vector<U256> va = detail::values(random_shares_a), vb = detail::values(random_shares_b), vr = detail::values(r2t);
+            sub = detail::with_values(prod, detail::fused(ctx_, HBMPC_K5_TRIPLE_MASK, {&va, &vb, &vr})[0]);   // a*b - r_2t in one pass
         } catch (const ShareError &e) {
             throw TripleGenError(TripleGenError::ShareErr, e.what());
         }
@@ -183,8 +200,10 @@ class Multiply {
         try {
             detail::same_shape(ta, x);
             detail::same_shape(tb, y);
-            a_sub_x = detail::with_values(ta, detail::elementwise(ctx_, 1, detail::values(ta), detail::values(x)));
-            b_sub_y = detail::with_values(tb, detail::elementwise(ctx_, 1, detail::values(tb), detail::values(y)));
+            const std::vector<U256> va = detail::values(ta), vx = detail::values(x), vb = detail::values(tb), vy = detail::values(y);
+            const std::vector<std::vector<U256>> m = detail::fused(ctx_, HBMPC_K5_BEAVER_MASK, {&va, &vx, &vb, &vy});   // a - x, b - y
+            a_sub_x = detail::with_values(ta, m[0]);
+            b_sub_y = detail::with_values(tb, m[1]);
         } catch (const ShareError &e) {
             throw MulError(MulError::ShareErr, e.what());
         }
@@ -278,12 +297,9 @@ class Multiply {
         da.insert(da.end(), st.openings->first.begin(), st.openings->first.end());
         db.insert(db.end(), st.openings->second.begin(), st.openings->second.end());
         if (da.size() != st.no_of_mul || db.size() != st.no_of_mul) throw MulError(MulError::InvalidInput, "Inconsistent lengths in finalize_mul");
-        const std::vector<U256> mult_subs = detail::elementwise(ctx_, 2, da, db);                       // (a-x)(b-y)
-        const std::vector<U256> sub_a_y = detail::elementwise(ctx_, 2, detail::values(st.y), da);       // (a-x)[y]
-        const std::vector<U256> sub_b_x = detail::elementwise(ctx_, 2, detail::values(st.x), db);       // (b-y)[x]
-        std::vector<U256> z = detail::elementwise(ctx_, 1, detail::values(st.mult), mult_subs);
-        z = detail::elementwise(ctx_, 1, z, sub_a_y);
-        z = detail::elementwise(ctx_, 1, z, sub_b_x);
+        // [xy] = [c] - (a-x)(b-y) - (a-x)[y] - (b-y)[x]   (three Mul and three Sub of the reference) in one pass
+        const std::vector<U256> vc = detail::values(st.mult), vx = detail::values(st.x), vy = detail::values(st.y);
+        const std::vector<U256> z = detail::fused(ctx_, HBMPC_K5_BEAVER_FINALIZE, {&vc, &vx, &vy, &da, &db})[0];
         st.finished = true;
         output[sid] = detail::with_values(st.mult, z);
         return true;

@@ -32,7 +32,7 @@ EXPORTS = [
     "hbmpc_ctx_create", "hbmpc_ctx_destroy", "hbmpc_ctx_set_stream", "hbmpc_ctx_set_async", "hbmpc_ctx_synchronize",
     "hbmpc_ctx_launch_count", "hbmpc_last_error", "hbmpc_compute_shares_batch", "hbmpc_apply_vandermonde_batch",
     "hbmpc_apply_matrix_batch", "hbmpc_batch_recover", "hbmpc_batch_recover_secrets", "hbmpc_robust_interpolate_batch",
-    "hbmpc_nonrobust_recover_batch", "hbmpc_elementwise", "hbmpc_unpack_share_records", "hbmpc_pack_share_records",
+    "hbmpc_nonrobust_recover_batch", "hbmpc_elementwise", "hbmpc_share_algebra_fused", "hbmpc_unpack_share_records", "hbmpc_pack_share_records",
     "hbmpc_measure_imad_peak", "hbmpc_measure_wide_chains", "hbmpc_measure_mont_mul",
     "hbmpc_sample_fr_batch", "hbmpc_sample_polynomials", "hbmpc_share_secrets_batch",
     "hbmpc_batch_recover_msgs", "hbmpc_batch_recover_secrets_msgs", "hbmpc_apply_vandermonde_msgs",
@@ -80,6 +80,7 @@ def load_library():
     lib.hbmpc_robust_interpolate_batch.argtypes = [vp, sz, sz, sz, sz, vp, sz, vp, vp, vp, vp, vp]
     lib.hbmpc_nonrobust_recover_batch.argtypes = [vp, sz, sz, sz, vp, sz, vp, ci, vp, vp, vp]
     lib.hbmpc_elementwise.argtypes = [vp, ci, sz, vp, vp, vp]
+    lib.hbmpc_share_algebra_fused.argtypes = [vp, ci, sz, C.POINTER(vp), C.POINTER(vp)]
     lib.hbmpc_unpack_share_records.argtypes = [vp, sz, vp, vp, vp, vp]
     lib.hbmpc_pack_share_records.argtypes = [vp, sz, vp, sz, sz, vp]
     lib.hbmpc_measure_imad_peak.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -367,10 +368,40 @@ class Context:
     # -- K5
     def elementwise(self, op: int, a, b, out=None):
         x, y = _Buf(a), _Buf(b)
+        if y.shape != x.shape:
+            raise ValueError(f"operands differ in shape: {x.shape} and {y.shape}")
         count = int(np.prod(x.shape[:-1]))
         out = x.like(x.shape) if out is None else _check_out(out, x.shape)
         self._check(self.lib.hbmpc_elementwise(self.h, op, count, x.ptr, y.ptr, _ptr(out)))
         return out
+
+    K5_TRIPLE_MASK, K5_BEAVER_MASK, K5_BEAVER_FINALIZE = 0, 1, 2
+
+    def share_algebra_fused(self, op: int, inputs, out=None):
+        """One pass over HBM for the share algebra of a protocol step (include/hbmpc_b200.h: hbmpc_share_algebra_fused):
+        op 0: (a, b, r_2t) -> a*b - r_2t; op 1: (a, x, b, y) -> (a - x, b - y); op 2: (c, x, y, a-x, b-y) -> the Beaver product share.
+        Returns one array (ops 0, 2) or a pair (op 1)."""
+        nin, nout = {0: (3, 1), 1: (4, 2), 2: (5, 1)}[op]
+        bufs = [_Buf(v) for v in inputs]
+        if len(bufs) != nin:
+            raise ValueError(f"op {op} takes {nin} input arrays, {len(bufs)} given")
+        shape = bufs[0].shape
+        for k, b in enumerate(bufs):
+            if b.shape != shape or b.torch != bufs[0].torch:
+                raise ValueError(f"input {k}: shape {b.shape} differs from input 0 {shape} (or host / device arrays are mixed)")
+        count = int(np.prod(shape[:-1]))
+        if out is None:
+            outs = [bufs[0].like(shape) for _ in range(nout)]
+        else:
+            outs = list(out) if nout == 2 else [out]
+            if len(outs) != nout:
+                raise ValueError(f"op {op} writes {nout} arrays")
+            for k, o in enumerate(outs):
+                _check_out(o, shape, name=f"out[{k}]")
+        pin = (C.c_void_p * nin)(*[b.ptr for b in bufs])
+        pout = (C.c_void_p * nout)(*[_ptr(o) for o in outs])
+        self._check(self.lib.hbmpc_share_algebra_fused(self.h, op, count, pin, pout))
+        return tuple(outs) if nout == 2 else outs[0]
 
     # -- N1: 48-byte ark-serialize share records
     def unpack_share_records(self, records: np.ndarray, count: int):

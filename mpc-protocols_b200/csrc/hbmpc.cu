@@ -51,6 +51,64 @@ __global__ void __launch_bounds__(256) elementwise_kernel(int op, long long coun
     if (bad) *(volatile unsigned int *)err = 1u;  // status words live in mapped host memory: plain store, every writer stores 1
 }
 
+// K5 fused: the share algebra of ONE protocol step in one pass over HBM instead of one pass per operator.
+//   OP 0  triple mask      out0 = in0*in1 - in2                              (triple_generation.rs:332-340)  128 B per element instead of 192
+//   OP 1  Beaver mask      out0 = in0 - in1, out1 = in2 - in3                (multiplication.rs:417-426)     one launch instead of two
+//   OP 2  Beaver finalise  out0 = in0 - in3*in4 - in3*in2 - in4*in1          (multiplication.rs:79-97)       192 B per element instead of 576
+// Values are canonical at the interface; the results are the canonical residues, i.e. bit-identical to the operator-by-operator route.
+struct FusedArgs {
+    const uint4 *in[5];
+    uint4 *out[2];
+    long long count;
+    unsigned int *err;
+};
+template <int OP>
+__global__ void __launch_bounds__(256) elementwise_fused_kernel(const FusedArgs a) {
+    fma_ballast(a.count < 0, a.err);
+    constexpr int NIN = OP == 0 ? 3 : OP == 1 ? 4 : 5;
+    unsigned bad = 0;
+    uint32_t r2[8];
+    r2_limbs(r2);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += (long long)gridDim.x * blockDim.x) {
+        uint32_t v[NIN][8];
+#pragma unroll
+        for (int k = 0; k < NIN; ++k) {
+            load_fr(v[k], ldg_stream(a.in[k] + i * 2), ldg_stream(a.in[k] + i * 2 + 1));
+            bad |= geq_mod(v[k]) ? 1u : 0u;
+        }
+        uint32_t z[8];
+        if (OP == 0) {
+            uint32_t xm[8], p[8];
+            mont_mul(xm, v[0], r2);   // a*R
+            mont_mul(p, xm, v[1]);    // a*b, canonical
+            fr_sub(z, p, v[2]);
+        } else if (OP == 1) {
+            uint32_t z1[8];
+            fr_sub(z, v[0], v[1]);
+            fr_sub(z1, v[2], v[3]);
+            stg_stream(a.out[1] + i * 2, make_uint4(z1[0], z1[1], z1[2], z1[3]));
+            stg_stream(a.out[1] + i * 2 + 1, make_uint4(z1[4], z1[5], z1[6], z1[7]));
+        } else {
+            // c - [(a-x)*((b-y) + y) + (b-y)*x]: the bracket as ONE lazily accumulated sum of two products (one reduction), one more
+            // product to leave the Montgomery domain -- about 2.7 products' worth of wide multiplies instead of 5 (the pass is
+            // multiplier-bound, not HBM-bound, with five: tools/k5_fused_probe.py); field identities only, so the canonical
+            // result is the one the reference's Mul / Sub sequence produces
+            uint32_t s[8], w[8], u[8];
+            fr_add(s, v[4], v[2]);
+            acc_t A;
+            acc_zero(A);
+            acc_mac(A, v[3], s);
+            acc_mac(A, v[4], v[1]);
+            acc_reduce(A, w);         // (...)/R, fully reduced
+            mont_mul(u, w, r2);       // canonical
+            fr_sub(z, v[0], u);
+        }
+        stg_stream(a.out[0] + i * 2, make_uint4(z[0], z[1], z[2], z[3]));
+        stg_stream(a.out[0] + i * 2 + 1, make_uint4(z[4], z[5], z[6], z[7]));
+    }
+    if (bad) *(volatile unsigned int *)a.err = 1u;
+}
+
 // out[b] = in[b*stride]  (secret = coefficient 0)
 __global__ void gather_first_kernel(long long B, long long stride, const uint4 *in, uint4 *out) {
     for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
@@ -2202,6 +2260,46 @@ extern "C" int hbmpc_elementwise(hbmpc_ctx *ctx, int op, size_t count, const uin
         return chunk_commit(ctx, ln, bo, b0, Bc, vo);
     };
     return run_batched(ctx, count, ba.host || bb.host || bo.host, 32, body);
+}
+
+extern "C" int hbmpc_share_algebra_fused(hbmpc_ctx *ctx, int op, size_t count, const uint64_t *const *in, uint64_t *const *out) {
+    if (!ctx) return HBMPC_INVALID_INPUT;
+    if (op < 0 || op > 2) return HBMPC_INVALID_INPUT;
+    if (count == 0) return HBMPC_SUCCESS;
+    if (!in || !out) return HBMPC_INVALID_INPUT;
+    const int nin = op == 0 ? 3 : op == 1 ? 4 : 5, nout = op == 1 ? 2 : 1;
+    for (int k = 0; k < nin; ++k)
+        if (!in[k]) return HBMPC_INVALID_INPUT;
+    for (int k = 0; k < nout; ++k)
+        if (!out[k]) return HBMPC_INVALID_INPUT;
+    cudaSetDevice(ctx->device);
+    BatchBuf bi[5], bo[2];
+    bool host = false;
+    for (int k = 0; k < nin; ++k) { bi[k] = make_buf(in[k], count, 1, false); host = host || bi[k].host; }
+    for (int k = 0; k < nout; ++k) { bo[k] = make_buf(out[k], count, 1, false); host = host || bo[k].host; }
+    auto body = [&](Lane &ln, size_t b0, size_t Bc) -> int {
+        ChunkView vi[5], vo[2];
+        int rc;
+        for (int k = 0; k < nin; ++k)
+            if ((rc = chunk_prepare(ctx, ln, k, bi[k], b0, Bc, true, vi[k]))) return rc;
+        for (int k = 0; k < nout; ++k)
+            if ((rc = chunk_prepare(ctx, ln, 5 + k, bo[k], b0, Bc, false, vo[k]))) return rc;
+        FusedArgs fa{};
+        for (int k = 0; k < nin; ++k) fa.in[k] = (const uint4 *)vi[k].dev;
+        for (int k = 0; k < nout; ++k) fa.out[k] = (uint4 *)vo[k].dev;
+        fa.count = (long long)Bc;
+        fa.err = ctx->d_status;
+        const unsigned blocks = (unsigned)std::min<long long>((long long)ctx->num_sms * 8, (long long)((Bc + 255) / 256));
+        if (op == 0) elementwise_fused_kernel<0><<<blocks, 256, 0, ln.stream>>>(fa);
+        else if (op == 1) elementwise_fused_kernel<1><<<blocks, 256, 0, ln.stream>>>(fa);
+        else elementwise_fused_kernel<2><<<blocks, 256, 0, ln.stream>>>(fa);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        for (int k = 0; k < nout; ++k)
+            if ((rc = chunk_commit(ctx, ln, bo[k], b0, Bc, vo[k]))) return rc;
+        return 0;
+    };
+    return run_batched(ctx, count, host, 32, body);
 }
 
 // ------------------------------------------------------------------------------------------------ N1: 48-byte share records

@@ -66,6 +66,9 @@ extern "C" {
 
     // ---- K5, wire records, randomness
     pub fn hbmpc_elementwise(ctx: *mut hbmpc_ctx, op: c_int, count: usize, a: *const u64, b: *const u64, out: *mut u64) -> c_int;
+    /// `op`: 0 triple mask (in = {a, b, r_2t}), 1 Beaver mask (in = {a, x, b, y}; two outputs), 2 Beaver finalise
+    /// (in = {c, x, y, a-x, b-y}); `inputs` / `outputs` are arrays of 3|4|5 and 1|2|1 pointers to `count` values each.
+    pub fn hbmpc_share_algebra_fused(ctx: *mut hbmpc_ctx, op: c_int, count: usize, inputs: *const *const u64, outputs: *const *mut u64) -> c_int;
     pub fn hbmpc_unpack_share_records(ctx: *mut hbmpc_ctx, count: usize, records: *const c_void, values: *mut u64, ids: *mut u64,
                                       degrees: *mut u64) -> c_int;
     pub fn hbmpc_pack_share_records(ctx: *mut hbmpc_ctx, count: usize, values: *const u64, per_id: usize, degree: usize,

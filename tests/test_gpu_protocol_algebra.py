@@ -107,3 +107,90 @@ def test_beaver_mul_known_answers(ctx, hb, orc):
     z = ctx.elementwise(0, z, rep(ctx.elementwise(2, d, e)))                  # + d*e
     rc, _, prod, path, _ = ctx.robust_interpolate_batch(ids, z, n, t, t)
     assert rc == 0 and hb.from_limbs(prod) == [100, 400]
+
+
+def _edge_values(hb, orc, count, seed):
+    """random canonical values with the edge cases of the field mixed in (0, 1, r-1, r-2, 2^255-ish top limb patterns)"""
+    R = hb.R_MOD
+    v = orc.random_fr((count,), seed)
+    edges = hb.to_limbs([0, 1, R - 1, R - 2, (R - 1) // 2, (R + 1) // 2, 1 << 32, (1 << 224) + 5])
+    k = min(len(edges), count)
+    pos = np.random.default_rng(seed).permutation(count)[:k]
+    v[pos] = edges[:k]
+    return v
+
+
+@pytest.mark.parametrize("count", [1, 7, 257, 70001])
+def test_fused_share_algebra_matches_operator_route(ctx, hb, orc, count):
+    """hbmpc_share_algebra_fused against the oracle's operator-by-operator route, which is how the reference computes
+    these values: triple_generation.rs:332-340 (share_mul, then Sub), multiplication.rs:417-426 (two Subs), multiplication.rs:79-97
+    (three Muls, three Subs, in the reference's order)."""
+    a, b, r2t, x, y = (_edge_values(hb, orc, count, 100 + s) for s in range(5))
+    ew = lambda op, u, v: orc.elementwise(op, u, v)[1]
+    # triple mask
+    want = ew(1, ew(2, a, b), r2t)
+    got = ctx.share_algebra_fused(ctx.K5_TRIPLE_MASK, (a, b, r2t))
+    assert np.array_equal(got, want)
+    assert np.array_equal(got, ctx.elementwise(1, ctx.elementwise(2, a, b), r2t))
+    # Beaver mask: (a - x, b - y)
+    ax, by = ctx.share_algebra_fused(ctx.K5_BEAVER_MASK, (a, x, b, y))
+    assert np.array_equal(ax, ew(1, a, x)) and np.array_equal(by, ew(1, b, y))
+    # Beaver finalise in the reference's order: ((c - da*db) - da*[y]) - db*[x]
+    c, da, db = r2t, ax, by
+    want = ew(1, ew(1, ew(1, c, ew(2, da, db)), ew(2, y, da)), ew(2, x, db))
+    got = ctx.share_algebra_fused(ctx.K5_BEAVER_FINALIZE, (c, x, y, da, db))
+    assert np.array_equal(got, want)
+    R = hb.R_MOD
+    if count <= 257:  # and against Python integers
+        ci, xi, yi, dai, dbi = (hb.from_limbs(v) for v in (c, x, y, da, db))
+        assert hb.from_limbs(got) == [(cc - p * q - p * yy - q * xx) % R for cc, xx, yy, p, q in zip(ci, xi, yi, dai, dbi)]
+
+
+def test_fused_share_algebra_device_arrays_in_place_and_errors(ctx, hb, orc):
+    """device-resident operands (torch tensors), an output aliasing an input, and the call's error behaviour"""
+    import torch
+
+    count = 4099
+    a, b, r = (_edge_values(hb, orc, count, 200 + s) for s in range(3))
+    want = orc.elementwise(1, orc.elementwise(2, a, b)[1], r)[1]
+    dev = lambda v: torch.from_numpy(v.view(np.int64)).cuda()
+    ad, bd, rd = dev(a), dev(b), dev(r)
+    got = ctx.share_algebra_fused(0, (ad, bd, rd), out=ad)          # in place: out0 aliases in0
+    assert got.is_cuda
+    assert np.array_equal(got.cpu().numpy().view(np.uint64), want)
+    # a non-canonical operand (>= r) is an input error, like hbmpc_elementwise
+    bad = a.copy()
+    bad[3] = hb.to_limbs([hb.R_MOD])[0]
+    with pytest.raises(hb.HbmpcError) as e:
+        ctx.share_algebra_fused(0, (bad, b, r))
+    assert e.value.code == hb.INVALID_INPUT
+    with pytest.raises(ValueError):
+        ctx.share_algebra_fused(2, (a, b, r))                       # op 2 takes five arrays
+    with pytest.raises(ValueError):
+        ctx.share_algebra_fused(0, (a, b[:5], r))
+    assert np.array_equal(ctx.share_algebra_fused(0, (a, b, r)), want)   # the context is usable after the errors
+
+
+def test_triple_pipeline_with_fused_algebra_n7_t2(ctx, hb, orc):
+    """triple_generation.rs:332-340,196-208 with the fused mask; then Beaver multiplication of two fresh sharings with the triple
+    (multiplication.rs:417-426, 79-97) through the fused mask / finalise: the product share reconstructs to x*y."""
+    n, t, R = 7, 2, hb.R_MOD
+    G = 2 * t + 1
+    a, b, r, xs_, ys_ = (orc.random_fr((G,), s) for s in (1, 2, 3, 4, 5))
+    sh = lambda sec, d, s: ctx.compute_shares_batch(np.concatenate([sec[:, None, :], orc.random_fr((G, d), s)], axis=1), n)
+    a_sh, b_sh, rt_sh, r2t_sh, x_sh, y_sh = sh(a, t, 10), sh(b, t, 11), sh(r, t, 12), sh(r, 2 * t, 13), sh(xs_, t, 14), sh(ys_, t, 15)
+    ids = np.arange(n)
+    masked = ctx.share_algebra_fused(0, (a_sh, b_sh, r2t_sh))        # degree 2t sharing of a*b - r
+    rc, _, opened, _, _ = ctx.robust_interpolate_batch(ids, masked, n, 2 * t, t)
+    assert rc == 0
+    av, bv, rv, xv, yv = (hb.from_limbs(v) for v in (a, b, r, xs_, ys_))
+    assert hb.from_limbs(opened) == [(p * q - z) % R for p, q, z in zip(av, bv, rv)]
+    rep = lambda v: np.ascontiguousarray(np.repeat(v[:, None, :], n, axis=1))
+    c_sh = ctx.elementwise(0, rt_sh, rep(opened))                    # [ab]_t
+    ax_sh, by_sh = ctx.share_algebra_fused(1, (a_sh, x_sh, b_sh, y_sh))
+    _, _, da, _, _ = ctx.robust_interpolate_batch(ids, ax_sh, n, t, t)
+    _, _, db, _, _ = ctx.robust_interpolate_batch(ids, by_sh, n, t, t)
+    z_sh = ctx.share_algebra_fused(2, (c_sh, x_sh, y_sh, rep(da), rep(db)))
+    rc, _, prod, path, _ = ctx.robust_interpolate_batch(ids, z_sh, n, t, t)
+    assert rc == 0 and (path == 0).all()
+    assert hb.from_limbs(prod) == [(p * q) % R for p, q in zip(xv, yv)]
