@@ -684,6 +684,34 @@ HB_DEV void one_mont_limbs(uint32_t (&r)[8]) {
     r[4] = 0xecbc4ff5u; r[5] = 0x998c4fefu; r[6] = 0xacc5056fu; r[7] = 0x1824b159u;
 }
 
+// ---- K5 fused (elementwise_fused_kernel).  Canonical values in, canonical values out.
+// z = a*b - c                                   (triple_generation.rs:332-340: share_mul, then Sub)
+HB_DEV void k5_triple_mask(uint32_t (&z)[8], const uint32_t (&a)[8], const uint32_t (&b)[8], const uint32_t (&c)[8]) {
+    uint32_t r2[8], am[8], p[8];
+    r2_limbs(r2);
+    mont_mul(am, a, r2);   // a*R
+    mont_mul(p, am, b);    // a*b, canonical
+    fr_sub(z, p, c);
+}
+// z = c - da*db - da*y - db*x                   (multiplication.rs:79-97: three Mul, three Sub)
+// computed as c - [da*(db + y) + db*x]: the bracket is ONE lazily accumulated sum of two products (one reduction), one more product
+// leaves the Montgomery domain -- about 2.7 products' worth of wide multiplies instead of the 5 of the literal formula, with which the
+// pass is multiplier-bound instead of HBM-bound (tools/k5_fused_probe.py).  Field identities only, so the canonical result is the one
+// the reference's operator sequence produces.
+HB_DEV void k5_beaver_finalize(uint32_t (&z)[8], const uint32_t (&c)[8], const uint32_t (&x)[8], const uint32_t (&y)[8], const uint32_t (&da)[8],
+                               const uint32_t (&db)[8]) {
+    uint32_t r2[8], s[8], w[8], u[8];
+    r2_limbs(r2);
+    fr_add(s, db, y);
+    acc_t A;
+    acc_zero(A);
+    acc_mac(A, da, s);
+    acc_mac(A, db, x);
+    acc_reduce(A, w);      // (...)/R, fully reduced
+    mont_mul(u, w, r2);    // canonical
+    fr_sub(z, c, u);
+}
+
 HB_DEV void load_fr(uint32_t (&a)[8], const uint4 lo, const uint4 hi) {
     a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
 }

@@ -67,8 +67,6 @@ __global__ void __launch_bounds__(256) elementwise_fused_kernel(const FusedArgs 
     fma_ballast(a.count < 0, a.err);
     constexpr int NIN = OP == 0 ? 3 : OP == 1 ? 4 : 5;
     unsigned bad = 0;
-    uint32_t r2[8];
-    r2_limbs(r2);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += (long long)gridDim.x * blockDim.x) {
         uint32_t v[NIN][8];
 #pragma unroll
@@ -78,10 +76,7 @@ __global__ void __launch_bounds__(256) elementwise_fused_kernel(const FusedArgs 
         }
         uint32_t z[8];
         if (OP == 0) {
-            uint32_t xm[8], p[8];
-            mont_mul(xm, v[0], r2);   // a*R
-            mont_mul(p, xm, v[1]);    // a*b, canonical
-            fr_sub(z, p, v[2]);
+            k5_triple_mask(z, v[0], v[1], v[2]);
         } else if (OP == 1) {
             uint32_t z1[8];
             fr_sub(z, v[0], v[1]);
@@ -89,19 +84,7 @@ __global__ void __launch_bounds__(256) elementwise_fused_kernel(const FusedArgs 
             stg_stream(a.out[1] + i * 2, make_uint4(z1[0], z1[1], z1[2], z1[3]));
             stg_stream(a.out[1] + i * 2 + 1, make_uint4(z1[4], z1[5], z1[6], z1[7]));
         } else {
-            // c - [(a-x)*((b-y) + y) + (b-y)*x]: the bracket as ONE lazily accumulated sum of two products (one reduction), one more
-            // product to leave the Montgomery domain -- about 2.7 products' worth of wide multiplies instead of 5 (the pass is
-            // multiplier-bound, not HBM-bound, with five: tools/k5_fused_probe.py); field identities only, so the canonical
-            // result is the one the reference's Mul / Sub sequence produces
-            uint32_t s[8], w[8], u[8];
-            fr_add(s, v[4], v[2]);
-            acc_t A;
-            acc_zero(A);
-            acc_mac(A, v[3], s);
-            acc_mac(A, v[4], v[1]);
-            acc_reduce(A, w);         // (...)/R, fully reduced
-            mont_mul(u, w, r2);       // canonical
-            fr_sub(z, v[0], u);
+            k5_beaver_finalize(z, v[0], v[1], v[2], v[3], v[4]);
         }
         stg_stream(a.out[0] + i * 2, make_uint4(z[0], z[1], z[2], z[3]));
         stg_stream(a.out[0] + i * 2 + 1, make_uint4(z[4], z[5], z[6], z[7]));

@@ -49,5 +49,15 @@ int main(int argc, char **argv) {
         uint32_t mc[8]; hb::mont_mul(mc, a, b);
         printf("ops "); print(a); printf(" "); print(b); printf(" "); print(m); printf(" "); print(s); printf(" "); print(d); printf(" "); print(mc); printf("\n");
     }
+    // K5 fused: triple mask and Beaver product share (edge operands in the first cases)
+    for (int t = 0; t < 48; ++t) {
+        uint32_t v[5][8], m[8], f[8];
+        for (int k = 0; k < 5; ++k) rnd(v[k], t < 5 ? (k == t ? 1 : 2) : (t == 5 ? 1 : (t == 6 ? 2 : 0)));
+        hb::k5_triple_mask(m, v[0], v[1], v[2]);
+        hb::k5_beaver_finalize(f, v[0], v[1], v[2], v[3], v[4]);
+        printf("k5");
+        for (int k = 0; k < 5; ++k) { printf(" "); print(v[k]); }
+        printf(" "); print(m); printf(" "); print(f); printf("\n");
+    }
     return 0;
 }

@@ -1,5 +1,5 @@
 """Host emulation of the device limb arithmetic (mpc-protocols_b200/csrc/fr.cuh compiled with g++ under
-HB_HOST_EMULATION) against Python big ints: even/odd lazy accumulator, carry counters, final reduction."""
+HB_HOST_EMULATION) against Python big ints: even/odd lazy accumulator, carry counters, final reduction, the fused share algebra of K5."""
 import os
 import subprocess
 
@@ -13,10 +13,15 @@ def test_fr_cuh_limb_logic(tmp_path):
     subprocess.run(["g++", "-O1", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "host", "fr_emul.cpp")], check=True)
     for seed in (1, 2, 3):
         out = subprocess.run([str(exe), str(seed)], capture_output=True, text=True, check=True).stdout.splitlines()
-        n_acc = n_ops = 0
+        n_acc = n_ops = n_k5 = 0
         for ln in out:
             p = ln.split()
-            if p[0] == "ops":
+            if p[0] == "k5":   # fused share algebra: a*b - c and c - da*db - da*y - db*x (operands: c, x, y, da, db)
+                v = [int(x, 16) for x in p[1:8]]
+                assert v[5] == (v[0] * v[1] - v[2]) % R
+                assert v[6] == (v[0] - v[3] * v[4] - v[3] * v[2] - v[4] * v[1]) % R
+                n_k5 += 1
+            elif p[0] == "ops":
                 a, b, m, s, d, mc = (int(x, 16) for x in p[1:7])
                 assert m == a * b * RINV % R and s == (a + b) % R and d == (a - b) % R
                 assert mc == m, "mont_mul_cios differs"
@@ -27,7 +32,7 @@ def test_fr_cuh_limb_logic(tmp_path):
                 acc = sum(vals[2 * k] * vals[2 * k + 1] for k in range(terms))
                 assert vals[-1] == acc * RINV % R, f"terms={terms}"
                 n_acc += 1
-        assert n_acc == 10 and n_ops == 64
+        assert n_acc == 10 and n_ops == 64 and n_k5 == 48
 
 
 def test_division_by_power_of_two_identity():
