@@ -78,6 +78,11 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
         for (int i = tid; i < nrows * C * 2; i += blockDim.x) sM[i] = a.M[((size_t)(r0 + i / (C * 2)) * ld) * 2 + i % (C * 2)];
     }
 
+    // staging (below): this thread's first element of a chunk-major tile and the step of one pass of the CTA, as (chunk, 2*column + half)
+    constexpr int STAGE_U = 8;
+    const int stage_bl0 = tid / (2 * C), stage_c20 = tid - stage_bl0 * (2 * C);
+    const int stage_qd = (int)blockDim.x / (2 * C), stage_rd = (int)blockDim.x - stage_qd * (2 * C);
+
     const long long TILE = TBT * 32;
     const long long NB = a.item_list ? (long long)*a.item_count : a.B;  // items to process
     const long long ntiles = (NB + TILE - 1) / TILE;
@@ -88,19 +93,38 @@ __global__ void __launch_bounds__(512) matvec_kernel(const MatvecArgs a) {
         const long long b0 = tile * TILE;
         __syncthreads();  // previous tile fully consumed (and sM visible on the first pass)
         // ---- stage the data tile: element (b, c) -> sD[sub][c][half][lane]
+        // STAGE_U loads are issued before the first of their stores (a load followed at once by its dependent store exposes one
+        // DRAM round trip per element: with few rows per tile -- the triangular recovery has 132 terms per chunk -- staging was a
+        // third of the kernel's time); chunk-major tiles advance (chunk, column) incrementally instead of dividing by C per element
         const int nhalves = TBT * 32 * C * 2;
-        for (int i = tid; i < nhalves; i += blockDim.x) {
-            int half = i & 1, bl, c;
-            if (a.in_chunk_major) { c = (i >> 1) % C; bl = (i >> 1) / C; }
-            else { bl = (i >> 1) % (TBT * 32); c = (i >> 1) / (TBT * 32); }
-            long long b = b0 + bl;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (b < NB) {
-                if (a.item_list) b = a.item_list[b];
-                int j = a.col_map ? a.col_map[a.col0 + c] : a.col0 + c;
-                v = ldg_stream(a.in + (b * a.in_sb + (long long)j * a.in_sc) * 2 + half);
+        int bl_i = stage_bl0, c2_i = stage_c20;
+        for (int i0 = tid; i0 < nhalves; i0 += (int)blockDim.x * STAGE_U) {
+            uint4 v[STAGE_U];
+            int dst[STAGE_U];
+#pragma unroll
+            for (int u = 0; u < STAGE_U; ++u) {
+                const int i = i0 + u * (int)blockDim.x;
+                v[u] = make_uint4(0, 0, 0, 0);
+                dst[u] = -1;
+                if (i < nhalves) {
+                    int half, bl, c;
+                    if (a.in_chunk_major) {   // i = (bl*C + c)*2 + half
+                        half = c2_i & 1; c = c2_i >> 1; bl = bl_i;
+                        c2_i += stage_rd; bl_i += stage_qd;
+                        if (c2_i >= 2 * C) { c2_i -= 2 * C; ++bl_i; }
+                    } else { half = i & 1; bl = (i >> 1) % (TBT * 32); c = (i >> 1) / (TBT * 32); }
+                    long long b = b0 + bl;
+                    if (b < NB) {
+                        if (a.item_list) b = a.item_list[b];
+                        int j = a.col_map ? a.col_map[a.col0 + c] : a.col0 + c;
+                        v[u] = ldg_stream(a.in + (b * a.in_sb + (long long)j * a.in_sc) * 2 + half);
+                    }
+                    dst[u] = (((bl >> 5) * C + c) * 2 + half) * 32 + (bl & 31);
+                }
             }
-            sD[(((bl >> 5) * C + c) * 2 + half) * 32 + (bl & 31)] = v;
+#pragma unroll
+            for (int u = 0; u < STAGE_U; ++u)
+                if (dst[u] >= 0) sD[dst[u]] = v[u];
         }
         if (checks_here) {
             for (int i = tid; i < TBT * 32; i += blockDim.x) sFail[i] = 0;
