@@ -48,6 +48,7 @@ def load(native: bool = False):
     lib.orc_gao_rs_decode.argtypes = [sz, sz, u64p, szp, sz, u64p, szp]
     lib.orc_lagrange_interpolate.argtypes = [sz, u64p, u64p, u64p, szp]
     lib.orc_elementwise.argtypes = [ci, sz, u64p, u64p, u64p, ci]
+    lib.orc_share_algebra_step.argtypes = [ci, sz, C.POINTER(u64p), C.POINTER(u64p)]
     lib.orc_domain_element.argtypes = [sz, sz, u64p]
     lib.orc_domain_element.restype = None
     lib.orc_max_threads.restype = ci
@@ -201,6 +202,22 @@ def elementwise(op: int, a: np.ndarray, b: np.ndarray, threads: int = 1):
     out = np.zeros_like(a)
     rc = lib.orc_elementwise(op, a.size // 4, _p(a), _p(b), _p(out), threads)
     return rc, out
+
+
+def share_algebra_step(step: int, inputs):
+    """The multi-operator steps of the share algebra in the reference's operator order (orc_share_algebra_step): step 0
+    (a, b, r_2t) -> a*b - r_2t; step 1 (a, x, b, y) -> (a - x, b - y); step 2 (c, x, y, a-x, b-y) -> the Beaver product share.
+    Returns (rc, outputs)."""
+    lib = load()
+    ins = [_u64(v) for v in inputs]
+    nin, nout = {0: (3, 1), 1: (4, 2), 2: (5, 1)}[step]
+    assert len(ins) == nin and all(v.shape == ins[0].shape for v in ins)
+    outs = [np.zeros_like(ins[0]) for _ in range(nout)]
+    u64p = C.POINTER(C.c_uint64)
+    pin = (u64p * nin)(*[_p(v) for v in ins])
+    pout = (u64p * nout)(*[_p(v) for v in outs])
+    rc = lib.orc_share_algebra_step(step, ins[0].size // 4, pin, pout)
+    return rc, outs
 
 
 def domain_element(n: int, j: int) -> int:

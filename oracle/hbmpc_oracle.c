@@ -691,6 +691,36 @@ int orc_elementwise(int op, size_t B, const uint64_t *a, const uint64_t *b, uint
     return c.bad ? ORC_INVALID_INPUT : ORC_OK;
 }
 
+/* The multi-operator steps of the share algebra, operator by operator in the reference's order (what the product's
+ * hbmpc_share_algebra_fused computes in one pass over the vectors):
+ *   step 0  triple_generation.rs:332-340   out0 = share_mul(a, b) - r_2t                       in = {a, b, r_2t}
+ *   step 1  multiplication.rs:417-426      out0 = a - x, out1 = b - y                          in = {a, x, b, y}
+ *   step 2  multiplication.rs:79-97        mult_subs = da*db; share = c - mult_subs;
+ *                                          share2 = share - y*da; out0 = share2 - x*db         in = {c, x, y, da, db}  */
+int orc_share_algebra_step(int step, size_t B, const uint64_t *const *in, uint64_t *const *out) {
+    const int nin = step == 0 ? 3 : step == 1 ? 4 : 5;
+    if (step < 0 || step > 2) return ORC_INVALID_INPUT;
+    for (size_t i = 0; i < B; ++i) {
+        fr v[5];
+        for (int k = 0; k < nin; ++k)
+            if (!fr_from_canon(in[k] + 4 * i, &v[k])) return ORC_INVALID_INPUT;
+        if (step == 0) {
+            fr_to_canon(fr_sub(fr_mul(v[0], v[1]), v[2]), out[0] + 4 * i);
+        } else if (step == 1) {
+            fr_to_canon(fr_sub(v[0], v[1]), out[0] + 4 * i);
+            fr_to_canon(fr_sub(v[2], v[3]), out[1] + 4 * i);
+        } else {
+            fr mult_subs = fr_mul(v[3], v[4]);
+            fr mult_sub_a_y = fr_mul(v[2], v[3]);
+            fr mult_sub_b_x = fr_mul(v[1], v[4]);
+            fr share = fr_sub(v[0], mult_subs);
+            fr share2 = fr_sub(share, mult_sub_a_y);
+            fr_to_canon(fr_sub(share2, mult_sub_b_x), out[0] + 4 * i);
+        }
+    }
+    return ORC_OK;
+}
+
 void orc_domain_element(size_t n, size_t j, uint64_t *out) {
     int N = domain_size(n); fr w = domain_gen(N);
     fr_to_canon(fr_pow_u64(w, j), out);
