@@ -28,9 +28,14 @@ def _weights(xs):
     return out
 
 
-def attempt(xs, ys, d: int, max_l: int):
+def attempt(xs, ys, d: int, max_l: int, values: str = "forney"):
     """rs_attempt (robust.cuh:189-446) on the points xs (distinct, id-sorted prefix) with received values ys.
-    Returns [(position, error value)] (ascending position) or None when the attempt fails."""
+    Returns [(position, error value)] (ascending position) or None when the attempt fails.
+    values = "forney": Omega = S*Lambda mod z^L, as the kernels compute today.
+    values = "hk": the same error values WITHOUT Omega (Horiguchi-Koetter form), from the auxiliary polynomial B
+    that Berlekamp-Massey keeps anyway.  With j* = nsyn - shift the iteration of the last length change, B its locator before that change and
+    bdis the discrepancy it met there, Lambda*(S*B mod z^deg) - B*Omega = -bdis * Lambda(0) * z^j* exactly (both sides have degree <= L + L_B - 1 = j*
+    and S*Lambda = Omega as power series), so at a root z of Lambda:  Omega(z) = bdis * Lambda(0) * z^j* / B(z)."""
     P = len(xs)
     nsyn = P - (d + 1)
     u = _weights(xs)
@@ -74,7 +79,14 @@ def attempt(xs, ys, d: int, max_l: int):
         den = pm.p_eval(dlam, z)
         if den == 0:
             return None
-        c = (-xs[i] * pm.p_eval(omega, z)) % R * inv(den) % R       # Forney
+        if values == "hk":
+            bz = pm.p_eval(bp, z)
+            if bz == 0:
+                return None
+            om = bdis * lam[0] % R * pow(z, nsyn - shift, R) % R * inv(bz) % R
+        else:
+            om = pm.p_eval(omega, z)
+        c = (-xs[i] * om) % R * inv(den) % R                        # Forney
         out.append((i, c * inv(u[i]) % R))                          # e_i = c_i * prod_{l != i}(x_i - x_l)
     return out
 

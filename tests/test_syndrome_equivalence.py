@@ -79,3 +79,31 @@ def test_path_rule_on_chosen_error_positions():
     for i in range(6):
         vals[i] = (vals[i] + 9) % R
     assert _both([(i, vals[i], d) for i in range(n)], n, t) is None
+
+
+def test_error_values_without_omega():
+    """the error values from Berlekamp-Massey's auxiliary polynomial (no Omega = S*Lambda mod z^L, i.e. no
+    omega_kernel) are the ones Forney's formula gives -- every attempt that succeeds returns the same positions and values either way."""
+    rnd = random.Random(4242)
+    checked = 0
+    for _ in range(300):
+        n = rnd.choice([7, 10, 13, 16, 32])
+        t = (n - 1) // 3
+        d = rnd.choice([t, min(2 * t, n - t - 2)])
+        S = rnd.randrange(d + t + 1, n + 1)
+        ids = sorted(rnd.sample(range(n), S))
+        xs = [pm.domain_element(n, i) for i in ids]
+        coeffs = [rnd.randrange(R) for _ in range(d + 1)]
+        ys = [pm.p_eval(coeffs, x) for x in xs]
+        max_l = min(t, (S - d - 1) // 2)
+        nerr = rnd.randrange(0, max_l + 2)
+        truth = {}
+        for i in rnd.sample(range(S), min(nerr, S)):
+            truth[i] = 1 + rnd.randrange(R - 1)
+            ys[i] = (ys[i] + truth[i]) % R
+        a, b = sm.attempt(xs, ys, d, max_l), sm.attempt(xs, ys, d, max_l, values="hk")
+        assert a == b
+        if len(truth) <= max_l:
+            assert a == sorted(truth.items())
+            checked += 1
+    assert checked > 100
